@@ -1,0 +1,75 @@
+"""tcgen05 GEMM building block vs. a plain PyTorch fp32 matmul of the same bf16 operands."""
+import ctypes
+
+import pytest
+import torch
+
+from ucod_dpl_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _gemm(a, w, mode, bias=None, scale=None, out=None):
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if mode in (2, 5) else torch.bfloat16)
+    _lib.call("ucod_gemm_bf16", _lib.ptr(a), a.stride(0), _lib.ptr(w), w.stride(0), M, N, K, mode,
+              _lib.ptr(bias), _lib.ptr(scale), _lib.ptr(out), out.stride(0), _lib.stream_ptr())
+    return out
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 64), (256, 256, 128), (300, 768, 768),
+                                    (1370, 2304, 768), (1370 * 3 + 5, 768, 3072), (77, 128, 768), (5000, 3072, 768),
+                                    (129, 256, 640)])
+def test_gemm_bias_f32(M, N, K):
+    g = torch.Generator(device="cuda").manual_seed(M * 7 + N)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    out = _gemm(a, w, 5, bias=bias)
+    ref = a.float() @ w.float().t() + bias
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, ref.abs().max().item()), f"max err {err}"
+
+
+def test_gemm_epilogues():
+    M, N, K = 1000, 768, 768
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda", generator=g)
+    scale = torch.rand(N, device="cuda", generator=g) + 0.5
+    ref = a.float() @ w.float().t() + bias
+    out0 = _gemm(a, w, 0, bias=bias)
+    assert (out0.float() - ref).abs().max().item() < 0.05
+    out1 = _gemm(a, w, 1, bias=bias)
+    assert (out1.float() - torch.nn.functional.gelu(ref)).abs().max().item() < 0.05
+    x = torch.randn(M, N, device="cuda", generator=g)
+    x0 = x.clone()
+    _gemm(a, w, 2, bias=bias, scale=scale, out=x)
+    assert (x - (x0 + scale * ref)).abs().max().item() < 5e-3
+    # no-bias / no-scale variant
+    x = x0.clone()
+    _gemm(a, w, 2, out=x)
+    assert (x - (x0 + ref - bias)).abs().max().item() < 5e-3
+
+
+def test_gemm_strided_rows():
+    # A and W taken as column slices of wider buffers (lda/ldw != K), as the QKV weight slices are.
+    M, N, K = 512, 256, 128
+    g = torch.Generator(device="cuda").manual_seed(2)
+    abig = torch.randn(M, 3 * K, device="cuda", generator=g).to(torch.bfloat16)
+    wbig = torch.randn(N, 2 * K, device="cuda", generator=g).to(torch.bfloat16)
+    a, w = abig[:, K:2 * K], wbig[:, K:]
+    out = _gemm(a, w, 5)
+    ref = a.float() @ w.float().t()
+    assert (out - ref).abs().max().item() < 1e-2
+
+
+def test_gemm_error_reporting():
+    a = torch.zeros(128, 64, device="cuda", dtype=torch.bfloat16)
+    w = torch.zeros(100, 64, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.UcodError):
+        _gemm(a, w, 5)

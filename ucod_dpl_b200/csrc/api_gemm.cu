@@ -1,0 +1,28 @@
+// C-ABI entry points: library info, error string, and the raw GEMM building block (used by tests/bench).
+#include "../../include/ucod_b200.h"
+#include "gemm.cuh"
+
+using namespace ucod;
+
+extern "C" {
+
+const char* ucod_last_error(void) { return get_last_error(); }
+
+int ucod_abi_version(void) { return UCOD_B200_ABI_VERSION; }
+
+int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n, int k, int epi_mode,
+                   const float* bias, const float* scale, void* out, int ld_out, void* stream) {
+    UCOD_REQUIRE(a && w && out, "ucod_gemm_bf16: null pointer");
+    UCOD_REQUIRE(epi_mode == EPI_BIAS_BF16 || epi_mode == EPI_BIAS_GELU_BF16 || epi_mode == EPI_RESID_F32 ||
+                     epi_mode == EPI_BIAS_F32,
+                 "ucod_gemm_bf16: epilogue mode %d is internal to the ViT pipeline", epi_mode);
+    GemmEpi ep;
+    ep.mode = epi_mode;
+    ep.bias = bias;
+    ep.scale = scale;
+    ep.out = out;
+    ep.ld_out = ld_out;
+    return launch_gemm_bf16(a, lda, w, ldw, m, n, k, ep, reinterpret_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
