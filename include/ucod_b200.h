@@ -34,6 +34,14 @@ int ucod_abi_version(void);
 int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n, int k, int epi_mode,
                    const float* bias, const float* scale, void* out, int ld_out, void* stream);
 
+/* Fused softmax(q k^T * scale) v, head_dim 64, non-causal (tcgen05 flash-attention forward).
+ * q,k: [batch*heads, tokens, 64] bf16 ; vt: [batch*heads, 64, tokens_pad] bf16 (V transposed, pad columns zero,
+ * tokens_pad % 8 == 0) ; ctx: [batch, tokens, heads*64] bf16.
+ * Replaces: HF Dinov2SelfAttention/ViTSelfAttention (modeling_dinov2.py:153-235) under
+ * data/utils/feature_extractor.py:49-59. */
+int ucod_attention_d64(const void* q, const void* k, const void* vt, void* ctx, int batch, int heads, int tokens,
+                       int tokens_pad, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,6 +1,7 @@
 // C-ABI entry points: library info, error string, and the raw GEMM building block (used by tests/bench).
 #include "../../include/ucod_b200.h"
 #include "gemm.cuh"
+#include "attention.cuh"
 
 using namespace ucod;
 
@@ -23,6 +24,13 @@ int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n,
     ep.out = out;
     ep.ld_out = ld_out;
     return launch_gemm_bf16(a, lda, w, ldw, m, n, k, ep, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ucod_attention_d64(const void* q, const void* k, const void* vt, void* ctx, int batch, int heads, int tokens,
+                       int tokens_pad, float scale, void* stream) {
+    UCOD_REQUIRE(q && k && vt && ctx, "ucod_attention_d64: null pointer");
+    return launch_attention_d64(q, k, vt, ctx, batch, heads, tokens, tokens_pad, scale,
+                                reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
