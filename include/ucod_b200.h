@@ -42,6 +42,49 @@ int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n,
 int ucod_attention_d64(const void* q, const void* k, const void* vt, void* ctx, int batch, int heads, int tokens,
                        int tokens_pad, float scale, void* stream);
 
+/* ---- frozen ViT-B backbone: last-layer key tokens ---------------------------------------------
+ * Replaces `backbone.__init__/forward` (data/utils/feature_extractor.py:31-59) and the hook + attentions of
+ * generate_pseudo_label.py:24-27,76-81,111-112.  Weights are device pointers owned by the caller
+ * (bf16 matrices row-major [out,in]; fp32 vectors); the handle only records them. */
+typedef struct ucod_vit_cfg {
+    int hidden;      /* 768 */
+    int layers;      /* 12 */
+    int heads;       /* 12 (head_dim 64) */
+    int mlp_dim;     /* 3072 */
+    int patch;       /* 14 (DINOv2) or 8 (DINO ViT-B/8) */
+    int patch_kpad;  /* 3*patch*patch rounded up to a multiple of 64 (row pitch of patch_w) */
+    float ln_eps;    /* 1e-6 (DINOv2) / 1e-12 (HF ViT) */
+} ucod_vit_cfg;
+
+typedef struct ucod_vit_layer {
+    const float* ln1_w; const float* ln1_b;
+    const void* w_qkv;  const float* b_qkv;   /* bf16 [3*hidden, hidden] = [Wq;Wk;Wv], fp32 [3*hidden] */
+    const void* w_o;    const float* b_o;     /* bf16 [hidden, hidden] */
+    const float* ls1;                         /* LayerScale lambda1 [hidden] or NULL */
+    const float* ln2_w; const float* ln2_b;
+    const void* w_fc1;  const float* b_fc1;   /* bf16 [mlp_dim, hidden] */
+    const void* w_fc2;  const float* b_fc2;   /* bf16 [hidden, mlp_dim] */
+    const float* ls2;                         /* LayerScale lambda2 [hidden] or NULL */
+} ucod_vit_layer;
+
+/* patch_w: bf16 [hidden, patch_kpad] (conv weight flattened c-major, zero padded), patch_b fp32 [hidden],
+ * cls_token fp32 [hidden], layers: host array of cfg->layers entries (copied). */
+int ucod_vit_create(void** handle, const ucod_vit_cfg* cfg, const void* patch_w, const float* patch_b,
+                    const float* cls_token, const ucod_vit_layer* layers);
+int ucod_vit_destroy(void* handle);
+int ucod_vit_workspace_bytes(void* handle, int batch, int img_h, int img_w, uint64_t* bytes);
+/* images: [batch,3,img_h,img_w] NCHW; image_dtype 0 = fp32 already normalised (reference transform output),
+ * 1 = uint8 raw RGB (ToTensor+Normalize fused into the loader, transforms.py:14-18).
+ * pos_emb: fp32 [1+P, hidden] position embedding for this resolution (row 0 = CLS).
+ * Outputs (any may be NULL, at least one required):
+ *   keys_f32  [batch, P (+1 if keep_cls), hidden] fp32  — `self.key` of feature_extractor.py:46-58 (token-major)
+ *   keys_bf16 same shape, bf16 (feeds the decoder GEMM without a conversion pass)
+ *   cls_attn  [batch, heads, P] fp32 — attentions[-1][:, :, 0, 1:] (found_bkg_mask.py:24)
+ * workspace: device scratch of >= ucod_vit_workspace_bytes(), 1 KiB aligned. */
+int ucod_vit_keys(void* handle, const void* images, int image_dtype, int batch, int img_h, int img_w,
+                  const float* pos_emb, void* workspace, uint64_t workspace_bytes, float* keys_f32, void* keys_bf16,
+                  float* cls_attn, int keep_cls, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -2,6 +2,7 @@
 #include "../../include/ucod_b200.h"
 #include "gemm.cuh"
 #include "attention.cuh"
+#include "vit.cuh"
 
 using namespace ucod;
 
@@ -31,6 +32,24 @@ int ucod_attention_d64(const void* q, const void* k, const void* vt, void* ctx, 
     UCOD_REQUIRE(q && k && vt && ctx, "ucod_attention_d64: null pointer");
     return launch_attention_d64(q, k, vt, ctx, batch, heads, tokens, tokens_pad, scale,
                                 reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ucod_vit_create(void** handle, const ucod_vit_cfg* cfg, const void* patch_w, const float* patch_b,
+                    const float* cls_token, const ucod_vit_layer* layers) {
+    return vit_create(handle, cfg, patch_w, patch_b, cls_token, layers);
+}
+int ucod_vit_destroy(void* handle) { return vit_destroy(handle); }
+int ucod_vit_workspace_bytes(void* handle, int batch, int img_h, int img_w, uint64_t* bytes) {
+    size_t b = 0;
+    int rc = vit_workspace_bytes(handle, batch, img_h, img_w, &b);
+    if (rc == 0 && bytes) *bytes = (uint64_t)b;
+    return rc;
+}
+int ucod_vit_keys(void* handle, const void* images, int image_dtype, int batch, int img_h, int img_w,
+                  const float* pos_emb, void* workspace, uint64_t workspace_bytes, float* keys_f32, void* keys_bf16,
+                  float* cls_attn, int keep_cls, void* stream) {
+    return vit_keys(handle, images, image_dtype, batch, img_h, img_w, pos_emb, workspace, (size_t)workspace_bytes,
+                    keys_f32, keys_bf16, cls_attn, keep_cls, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"
