@@ -85,6 +85,29 @@ int ucod_vit_keys(void* handle, const void* images, int image_dtype, int batch, 
                   const float* pos_emb, void* workspace, uint64_t workspace_bytes, float* keys_f32, void* keys_bf16,
                   float* cls_attn, int keep_cls, void* stream);
 
+/* ---- Dual-Branch Adversarial decoder ------------------------------------------------------------
+ * Replaces `RevDecoder.forward` (models/modules/DBA.py:31-59) incl. the preceding bilinear feature upsample
+ * of engine/runner/loop_UCOD_DPL.py:153,236,305 (commuted past the 1x1 conv) and `calc_orthogonal_loss`
+ * (DBA.py:25-29, via the Gram identity).
+ * keys: bf16 token-major [batch, gin_h*gin_w, dim]; logits are produced on the (out_h, out_w) grid.
+ * Weights are device pointers: w_dec bf16 [128,dim]; b_dec[128], emb[2*64], w_fg[64], b_fg[1], w_bg[64], b_bg[1] fp32.
+ * fg [batch,out_h*out_w] (required); bg same shape or NULL; ortho: device scalar or NULL (student only). */
+uint64_t ucod_decoder_workspace_bytes(int batch, int gin_h, int gin_w, int out_h, int out_w, int want_ortho);
+int ucod_decoder_fwd(const void* keys_bf16, int batch, int dim, int gin_h, int gin_w, int out_h, int out_w,
+                     const void* w_dec, const float* b_dec, const float* emb, const float* w_fg, const float* b_fg,
+                     const float* w_bg, const float* b_bg, float* fg, float* bg, float* ortho, void* workspace,
+                     uint64_t workspace_bytes, void* stream);
+
+/* [batch, channels, pixels] fp32 with element strides (sb, sc, sp) -> token-major bf16 [batch, pixels, channels].
+ * Lets `baseline.forward` accept the reference's NCHW feature tensors (models/uscod.py:16-22). */
+int ucod_features_to_tokens_bf16(const float* in, void* out, int batch, int channels, int pixels, int64_t sb,
+                                 int64_t sc, int64_t sp, void* stream);
+
+/* F.interpolate(mode='bilinear', align_corners=False) of [batch,in_h,in_w] fp32.  binarize = 0: fp32 output;
+ * binarize = 1: uint8 {0,1} mask of `sigmoid(x) > 0.5` (engine/runner/loop_UCOD_DPL.py:356-361). */
+int ucod_upsample_bilinear(const float* in, void* out, int batch, int in_h, int in_w, int out_h, int out_w,
+                           int binarize, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

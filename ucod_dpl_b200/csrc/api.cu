@@ -3,6 +3,7 @@
 #include "gemm.cuh"
 #include "attention.cuh"
 #include "vit.cuh"
+#include "decoder.cuh"
 
 using namespace ucod;
 
@@ -50,6 +51,29 @@ int ucod_vit_keys(void* handle, const void* images, int image_dtype, int batch, 
                   float* cls_attn, int keep_cls, void* stream) {
     return vit_keys(handle, images, image_dtype, batch, img_h, img_w, pos_emb, workspace, (size_t)workspace_bytes,
                     keys_f32, keys_bf16, cls_attn, keep_cls, reinterpret_cast<cudaStream_t>(stream));
+}
+
+uint64_t ucod_decoder_workspace_bytes(int batch, int gin_h, int gin_w, int out_h, int out_w, int want_ortho) {
+    return (uint64_t)decoder_workspace_bytes(batch, gin_h, gin_w, out_h, out_w, want_ortho);
+}
+int ucod_decoder_fwd(const void* keys_bf16, int batch, int dim, int gin_h, int gin_w, int out_h, int out_w,
+                     const void* w_dec, const float* b_dec, const float* emb, const float* w_fg, const float* b_fg,
+                     const float* w_bg, const float* b_bg, float* fg, float* bg, float* ortho, void* workspace,
+                     uint64_t workspace_bytes, void* stream) {
+    UCOD_REQUIRE(w_dec && b_dec && emb && w_fg && b_fg && w_bg && b_bg, "ucod_decoder_fwd: null weight pointer");
+    DecoderWeights w{dim, w_dec, b_dec, emb, w_fg, b_fg, w_bg, b_bg};
+    return decoder_forward(keys_bf16, batch, gin_h, gin_w, out_h, out_w, w, fg, bg, ortho, workspace,
+                           (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_features_to_tokens_bf16(const float* in, void* out, int batch, int channels, int pixels, int64_t sb,
+                                 int64_t sc, int64_t sp, void* stream) {
+    return features_to_tokens_bf16(in, out, batch, channels, pixels, sb, sc, sp,
+                                   reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_upsample_bilinear(const float* in, void* out, int batch, int in_h, int in_w, int out_h, int out_w,
+                           int binarize, void* stream) {
+    return upsample_bilinear(in, out, batch, in_h, in_w, out_h, out_w, binarize,
+                             reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

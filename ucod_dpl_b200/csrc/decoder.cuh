@@ -1,0 +1,26 @@
+// DBA decoder forward + layout / upsample helpers (see decoder.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ucod {
+
+struct DecoderWeights {
+    int dim;              // input channels (768)
+    const void* w_dec;    // bf16 [128, dim]      decoupling.weight
+    const float* b_dec;   // [128]                decoupling.bias
+    const float* emb;     // [2, 64]              learnable_embedding
+    const float* w_fg;    // [64]                 conv_out_fg.weight
+    const float* b_fg;    // [1]
+    const float* w_bg;    // [64]                 conv_out_bg.weight
+    const float* b_bg;    // [1]
+};
+
+size_t decoder_workspace_bytes(int B, int gin_h, int gin_w, int out_h, int out_w, int want_ortho);
+int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_h, int out_w, const DecoderWeights& w,
+                    float* fg, float* bg, float* ortho, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int features_to_tokens_bf16(const float* in, void* out, int B, int C, int P, long long sb, long long sc, long long sp,
+                            cudaStream_t stream);
+int upsample_bilinear(const float* in, void* out, int B, int in_h, int in_w, int out_h, int out_w, int binarize,
+                      cudaStream_t stream);
+
+}  // namespace ucod
