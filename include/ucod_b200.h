@@ -25,6 +25,15 @@ extern "C" {
 const char* ucod_last_error(void);
 int ucod_abi_version(void);
 
+/* Launch accounting (bench.py): total kernels launched by this library in the process, and optional
+ * per-kernel-class CUDA-event timing.  Classes: 0 gemm, 1 attention, 2 layernorm, 3 embed, 4 decoder,
+ * 5 resample, 6 pseudo-label, 7 ccl/boxes, 8 other (arrays of UCOD_KERNEL_CLASSES entries).
+ * `work` is FLOPs for classes 0-1 and algorithmic bytes for the rest. */
+#define UCOD_KERNEL_CLASSES 9
+void ucod_prof_enable(int on);
+int ucod_prof_collect(double* ms, double* work, long long* launches);
+long long ucod_launch_count(void);
+
 /* ---- dense building block -------------------------------------------------------------------
  * out[M,N] = epilogue(A[M,K] * W[N,K]^T) ; A, W bf16 row-major (K contiguous), fp32 accumulate (tcgen05).
  * epi_mode: 0 = bf16 out, +bias ; 1 = bf16 out, gelu(+bias) ; 2 = fp32 in-place residual

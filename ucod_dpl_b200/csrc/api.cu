@@ -4,6 +4,7 @@
 #include "attention.cuh"
 #include "vit.cuh"
 #include "decoder.cuh"
+#include "prof.cuh"
 
 using namespace ucod;
 
@@ -12,6 +13,10 @@ extern "C" {
 const char* ucod_last_error(void) { return get_last_error(); }
 
 int ucod_abi_version(void) { return UCOD_B200_ABI_VERSION; }
+
+void ucod_prof_enable(int on) { prof_enable(on); }
+int ucod_prof_collect(double* ms, double* work, long long* launches) { return prof_collect(ms, work, launches); }
+long long ucod_launch_count(void) { return launch_count_total(); }
 
 int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n, int k, int epi_mode,
                    const float* bias, const float* scale, void* out, int ld_out, void* stream) {

@@ -15,6 +15,7 @@
 // Replaces: HF Dinov2SelfAttention / ViTSelfAttention eager+sdpa paths (transformers
 // modeling_dinov2.py:153-235) reached from data/utils/feature_extractor.py:49-59.
 #include "attention.cuh"
+#include "prof.cuh"
 
 namespace ucod {
 
@@ -267,8 +268,11 @@ int launch_attention_d64(const void* q, const void* k, const void* vt, void* ctx
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(T, ATT_BM), (unsigned)BH);
-    attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(ctx), T,
-                                                                 H, scale * 1.4426950408889634f);
+    {
+        ProfScope ps(KC_ATTENTION, stream, 4.0 * B * H * (double)T * T * ATT_D);
+        attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(
+            tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(ctx), T, H, scale * 1.4426950408889634f);
+    }
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -12,6 +12,7 @@
 #include "decoder.cuh"
 
 #include "gemm.cuh"
+#include "prof.cuh"
 
 namespace ucod {
 
@@ -234,17 +235,28 @@ int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_
         return rc;
     UCOD_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, (size_t)B * 128 * 4, stream));
     dim3 grid(ceil_div(npix, DEC_PIX_PER_BLOCK), B);
-    decoder_sumsq_kernel<<<grid, 256, 0, stream>>>(d_in, sumsq, gin_h, gin_w, out_h, out_w);
+    const double d_bytes = (double)B * gin_h * gin_w * 128 * 4;
+    {
+        ProfScope ps(KC_DECODER, stream, d_bytes);
+        decoder_sumsq_kernel<<<grid, 256, 0, stream>>>(d_in, sumsq, gin_h, gin_w, out_h, out_w);
+    }
     UCOD_CHECK_CUDA(cudaGetLastError());
-    decoder_head_kernel<<<grid, 256, 0, stream>>>(d_in, sumsq, w.emb, w.w_fg, w.b_fg, w.w_bg, w.b_bg, fg, bg, fhat,
-                                                  gin_h, gin_w, out_h, out_w);
+    {
+        ProfScope ps(KC_DECODER, stream, d_bytes + (double)B * npix * 8);
+        decoder_head_kernel<<<grid, 256, 0, stream>>>(d_in, sumsq, w.emb, w.w_fg, w.b_fg, w.w_bg, w.b_bg, fg, bg, fhat,
+                                                      gin_h, gin_w, out_h, out_w);
+    }
     UCOD_CHECK_CUDA(cudaGetLastError());
     if (ortho) {
         UCOD_CHECK_CUDA(cudaMemsetAsync(gram, 0, (size_t)B * 8192 * 4 + (size_t)B * 4, stream));
         const int chunk = 256;
         dim3 g2(ceil_div(npix, chunk), B);
-        decoder_gram_kernel<<<g2, 256, 0, stream>>>(fhat, gram, diag, npix, chunk);
+        {
+            ProfScope ps(KC_DECODER, stream, (double)B * npix * 128 * 4);
+            decoder_gram_kernel<<<g2, 256, 0, stream>>>(fhat, gram, diag, npix, chunk);
+        }
         UCOD_CHECK_CUDA(cudaGetLastError());
+        ProfScope ps(KC_DECODER, stream, (double)B * 8192 * 4);
         decoder_ortho_finish_kernel<<<1, 256, 0, stream>>>(gram, diag, ortho, B, npix);
         UCOD_CHECK_CUDA(cudaGetLastError());
     }
@@ -285,6 +297,7 @@ int features_to_tokens_bf16(const float* in, void* out, int B, int C, int P, lon
                             cudaStream_t stream) {
     UCOD_REQUIRE(in && out && B > 0 && C > 0 && P > 0, "features_to_tokens: bad argument");
     dim3 grid(ceil_div(P, 32), ceil_div(C, 32), B), block(32, 8);
+    ProfScope ps(KC_DECODER, stream, (double)B * C * P * 6);
     features_to_tokens_kernel<<<grid, block, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), C, P, sb, sc, sp);
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -333,6 +346,7 @@ int upsample_bilinear(const float* in, void* out, int B, int in_h, int in_w, int
                       cudaStream_t stream) {
     UCOD_REQUIRE(in && out && B > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0, "upsample: bad argument");
     dim3 block(128), grid(ceil_div(ceil_div(out_w, 4), 128), out_h, B);
+    ProfScope ps(KC_RESAMPLE, stream, (double)B * in_h * in_w * 4 + (double)B * out_h * out_w * (binarize ? 1 : 4));
     if (binarize)
         upsample_bilinear_kernel<1><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
     else

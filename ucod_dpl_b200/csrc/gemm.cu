@@ -11,6 +11,7 @@
 // (transformers modeling_dinov2.py:153-235,348-387), patch-embed Conv2d (:38-117), the decoder's
 // `decoupling` 1x1 conv (models/modules/DBA.py:13,35) and the CORAL CSF projections (models/modules/mlp.py:116-148).
 #include "gemm.cuh"
+#include "prof.cuh"
 
 namespace ucod {
 
@@ -265,7 +266,10 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
     }
     const int tiles = ceil_div(M, Cfg::BM) * (N / BN);
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
+    {
+        ProfScope ps(KC_GEMM, stream, 2.0 * M * N * K);
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
+    }
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -13,6 +13,7 @@
 
 #include "attention.cuh"
 #include "gemm.cuh"
+#include "prof.cuh"
 
 namespace ucod {
 
@@ -233,6 +234,7 @@ int vit_workspace_bytes(void* handle, int B, int img_h, int img_w, size_t* out) 
 static int layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows, float eps,
                      cudaStream_t s) {
     const int wpb = 8;
+    ProfScope ps(KC_LAYERNORM, s, (double)rows * 768 * 6);
     layernorm_bf16_kernel<768><<<ceil_div(rows, wpb), wpb * 32, 0, s>>>(x, w, b, y, rows, eps);
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
@@ -258,12 +260,14 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
     const float3 mean = make_float3(0.485f, 0.456f, 0.406f);
     const float3 istd = make_float3(1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f);
     dim3 g_im(gh, B);
+    prof_pre(KC_EMBED, stream, (double)B * 3 * img_h * img_w * (image_dtype ? 1 : 4) + (double)B * P * c.patch_kpad * 2);
     if (image_dtype == 0)
         im2col_patch_kernel<float><<<g_im, 256, 0, stream>>>(static_cast<const float*>(images), w.patches, B, img_h,
                                                              img_w, p, c.patch_kpad, mean, istd);
     else
         im2col_patch_kernel<uint8_t><<<g_im, 256, 0, stream>>>(static_cast<const uint8_t*>(images), w.patches, B,
                                                                img_h, img_w, p, c.patch_kpad, mean, istd);
+    prof_post(KC_EMBED, stream);
     UCOD_CHECK_CUDA(cudaGetLastError());
     {
         GemmEpi ep;
@@ -277,7 +281,10 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
                                       stream))
             return rc;
     }
-    cls_init_kernel<<<B, 256, 0, stream>>>(w.x, m->cls, pos_emb, T, D);
+    {
+        ProfScope ps(KC_EMBED, stream, (double)B * D * 4);
+        cls_init_kernel<<<B, 256, 0, stream>>>(w.x, m->cls, pos_emb, T, D);
+    }
     UCOD_CHECK_CUDA(cudaGetLastError());
     UCOD_CHECK_CUDA(cudaMemsetAsync(w.vt, 0, (size_t)B * D * Tpad * 2, stream));
 
@@ -354,8 +361,11 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
         if (int rc = launch_gemm_bf16(w.xn, D, wk, D, M, D, D, ep, stream)) return rc;
         const size_t smem = (64 + (size_t)T) * sizeof(float);
         UCOD_REQUIRE(smem <= 48 * 1024, "ucod_vit_keys: CLS-row attention supports at most %d tokens", 48 * 256 - 64);
-        cls_row_attention_kernel<<<B * H, 256, smem, stream>>>(w.xn, static_cast<const __nv_bfloat16*>(L.w_qkv),
-                                                               L.b_qkv, w.keys_all, cls_attn, T, D, H, scale);
+        {
+            ProfScope ps(KC_EMBED, stream, (double)B * T * D * 4);
+            cls_row_attention_kernel<<<B * H, 256, smem, stream>>>(w.xn, static_cast<const __nv_bfloat16*>(L.w_qkv),
+                                                                   L.b_qkv, w.keys_all, cls_attn, T, D, H, scale);
+        }
         UCOD_CHECK_CUDA(cudaGetLastError());
     }
     return 0;

@@ -1,0 +1,40 @@
+"""Seeded synthetic inputs: no datasets or pretrained DINO weights exist offline.
+
+Images: uint8, i.i.d. U{0..255} noise blended 50/50 with 2-4 random soft-edged ellipses so that features have
+spatial structure.  Image i of a job always uses `torch.Generator().manual_seed(1234 + i)`, independent of how
+the job is sharded over ranks.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+
+def synth_image_u8(index: int, height: int, width: int) -> torch.Tensor:
+    """[3,H,W] uint8 (CPU)."""
+    g = torch.Generator().manual_seed(1234 + int(index))
+    noise = torch.randint(0, 256, (3, height, width), generator=g, dtype=torch.int16).float()
+    n_ell = int(torch.randint(2, 5, (1,), generator=g).item())
+    yy = torch.arange(height, dtype=torch.float32).view(-1, 1)
+    xx = torch.arange(width, dtype=torch.float32).view(1, -1)
+    canvas = torch.full((3, height, width), 96.0)
+    for _ in range(n_ell):
+        r = torch.rand(8, generator=g)
+        cy, cx = float(r[0]) * height, float(r[1]) * width
+        ay = (0.05 + 0.25 * float(r[2])) * height
+        ax = (0.05 + 0.25 * float(r[3])) * width
+        th = float(r[4]) * math.pi
+        c, s = math.cos(th), math.sin(th)
+        u = ((xx - cx) * c + (yy - cy) * s) / ax
+        v = (-(xx - cx) * s + (yy - cy) * c) / ay
+        soft = torch.sigmoid((1.0 - torch.sqrt(u * u + v * v)) * 8.0)  # soft edge
+        colour = (r[5:8] * 255.0).view(3, 1, 1)
+        canvas = canvas * (1 - soft) + colour * soft
+    img = 0.5 * noise + 0.5 * canvas
+    return img.round().clamp_(0, 255).to(torch.uint8)
+
+
+def synth_batch_u8(start: int, count: int, height: int, width: int) -> torch.Tensor:
+    """[count,3,H,W] uint8 (CPU) — images start .. start+count-1."""
+    return torch.stack([synth_image_u8(start + i, height, width) for i in range(count)], dim=0)
