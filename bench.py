@@ -155,8 +155,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     lib = _lib.load()
 
     # weights: random-init ViT-B/14 (no DINOv2 weights offline), shipped decoder checkpoint
-    from oracle.vit import random_vit_state_dict, spec_for as ospec_for  # weight generator only (test infra)
-    vit_sd = random_vit_state_dict(ospec_for("dinov2"), seed=0)
+    from ucod_dpl_b200.synth import random_vit_state_dict
+    vit_sd = random_vit_state_dict(spec_for("dinov2"), seed=0)
     model = baseline(SimpleNamespace(dim=768))
     model.load_state_dict(_load_decoder_sd(), strict=True)
     pipe = FirstStageEval(vit_sd, spec_for("dinov2"), model, (IMAGE, IMAGE), FEATURE, device=dev)

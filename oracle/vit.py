@@ -58,42 +58,9 @@ def layer_keys(spec: VitSpec, i: int) -> dict:
 
 
 def random_vit_state_dict(spec: VitSpec, seed: int = 0, layerscale_init: float = 1.0) -> dict:
-    """Deterministic random-init weights under HF key names (no pretrained DINO weights exist offline).
-
-    Scales are chosen so activations stay O(1) through 12 layers (std 0.02 linears like HF's init, but
-    non-trivial biases / LayerNorm affine / LayerScale so every fused epilogue term is exercised)."""
-    g = torch.Generator().manual_seed(seed)
-    D, Dm, p = spec.hidden, spec.mlp_dim, spec.patch
-
-    def rn(*shape, std=0.02):
-        return torch.randn(*shape, generator=g) * std
-
-    sd = {
-        "embeddings.cls_token": rn(1, 1, D, std=1.0),
-        "embeddings.position_embeddings": rn(1, spec.native_grid ** 2 + 1, D, std=0.2),
-        "embeddings.patch_embeddings.projection.weight": rn(D, 3, p, p, std=0.05),
-        "embeddings.patch_embeddings.projection.bias": rn(D, std=0.1),
-        "layernorm.weight": 1.0 + rn(D, std=0.1),
-        "layernorm.bias": rn(D, std=0.1),
-    }
-    if spec.kind == "dinov2":
-        sd["embeddings.mask_token"] = torch.zeros(1, D)
-    for i in range(spec.layers):
-        k = layer_keys(spec, i)
-        for name in ("ln1", "ln2"):
-            sd[k[name] + ".weight"] = 1.0 + rn(D, std=0.1)
-            sd[k[name] + ".bias"] = rn(D, std=0.05)
-        for name in ("q", "k", "v", "o"):
-            sd[k[name] + ".weight"] = rn(D, D, std=0.04)
-            sd[k[name] + ".bias"] = rn(D, std=0.05)
-        sd[k["fc1"] + ".weight"] = rn(Dm, D, std=0.03)
-        sd[k["fc1"] + ".bias"] = rn(Dm, std=0.05)
-        sd[k["fc2"] + ".weight"] = rn(D, Dm, std=0.02)
-        sd[k["fc2"] + ".bias"] = rn(D, std=0.05)
-        if spec.layerscale:
-            sd[k["ls1"]] = layerscale_init * (1.0 + rn(D, std=0.1))
-            sd[k["ls2"]] = layerscale_init * (1.0 + rn(D, std=0.1))
-    return sd
+    """Seeded random-init weights (shared generator of the product package: it is input data, not algorithm)."""
+    from ucod_dpl_b200.synth import random_vit_state_dict as gen
+    return gen(spec, seed=seed, layerscale_init=layerscale_init)
 
 
 def interpolate_pos_embedding(pos: torch.Tensor, native_grid: int, gh: int, gw: int) -> torch.Tensor:

@@ -10,6 +10,8 @@ import math
 
 import torch
 
+from .vit import _layer_keys
+
 
 def synth_image_u8(index: int, height: int, width: int) -> torch.Tensor:
     """[3,H,W] uint8 (CPU)."""
@@ -38,3 +40,42 @@ def synth_image_u8(index: int, height: int, width: int) -> torch.Tensor:
 def synth_batch_u8(start: int, count: int, height: int, width: int) -> torch.Tensor:
     """[count,3,H,W] uint8 (CPU) — images start .. start+count-1."""
     return torch.stack([synth_image_u8(start + i, height, width) for i in range(count)], dim=0)
+
+
+def random_vit_state_dict(spec, seed: int = 0, layerscale_init: float = 1.0) -> dict:
+    """Deterministic random-init weights under HF key names (no pretrained DINO weights exist offline).
+
+    Scales are chosen so activations stay O(1) through 12 layers (std 0.02 linears like HF's init, but
+    non-trivial biases / LayerNorm affine / LayerScale so every fused epilogue term is exercised)."""
+    g = torch.Generator().manual_seed(seed)
+    D, Dm, p = spec.hidden, spec.mlp_dim, spec.patch
+
+    def rn(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    sd = {
+        "embeddings.cls_token": rn(1, 1, D, std=1.0),
+        "embeddings.position_embeddings": rn(1, spec.native_grid ** 2 + 1, D, std=0.2),
+        "embeddings.patch_embeddings.projection.weight": rn(D, 3, p, p, std=0.05),
+        "embeddings.patch_embeddings.projection.bias": rn(D, std=0.1),
+        "layernorm.weight": 1.0 + rn(D, std=0.1),
+        "layernorm.bias": rn(D, std=0.1),
+    }
+    if spec.kind == "dinov2":
+        sd["embeddings.mask_token"] = torch.zeros(1, D)
+    for i in range(spec.layers):
+        k = _layer_keys(spec, i)
+        for name in ("ln1", "ln2"):
+            sd[k[name] + ".weight"] = 1.0 + rn(D, std=0.1)
+            sd[k[name] + ".bias"] = rn(D, std=0.05)
+        for name in ("q", "k", "v", "o"):
+            sd[k[name] + ".weight"] = rn(D, D, std=0.04)
+            sd[k[name] + ".bias"] = rn(D, std=0.05)
+        sd[k["fc1"] + ".weight"] = rn(Dm, D, std=0.03)
+        sd[k["fc1"] + ".bias"] = rn(Dm, std=0.05)
+        sd[k["fc2"] + ".weight"] = rn(D, Dm, std=0.02)
+        sd[k["fc2"] + ".bias"] = rn(D, std=0.05)
+        if spec.layerscale:
+            sd[k["ls1"]] = layerscale_init * (1.0 + rn(D, std=0.1))
+            sd[k["ls2"]] = layerscale_init * (1.0 + rn(D, std=0.1))
+    return sd
