@@ -117,6 +117,22 @@ int ucod_features_to_tokens_bf16(const float* in, void* out, int batch, int chan
 int ucod_upsample_bilinear(const float* in, void* out, int batch, int in_h, int in_w, int out_h, int out_w,
                            int binarize, void* stream);
 
+/* ---- fixed-strategy pseudo-labels ----------------------------------------------------------------
+ * `compute_img_bkg_seg` (data/utils/found_bkg_mask.py:4-85) for the CLS attention row and patch keys:
+ * attn_cls fp32 [batch, heads, patches] (= attentions[-1][:, :, 0, 1:]), keys [batch, patches, heads*64]
+ * (fp32, or bf16 when keys_bf16 != 0).  Outputs: cos fp32 [batch,patches] (cosine to the least-attended patch),
+ * bkg uint8 [batch,patches] (cos > th_bkg), ref_idx int32 [batch]; sim fp32 [batch,patches] or NULL
+ * ((1-cos)/max(1-cos) * (1-bkg), the max taken over the whole call as in the reference, :81-85);
+ * scratch: 4 device bytes (required when sim != NULL). */
+int ucod_pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf16, int batch, int heads, int patches,
+                            float th_bkg, float epsilon, float* cos, uint8_t* bkg, int32_t* ref_idx, float* sim,
+                            void* scratch, void* stream);
+/* `refine_post_process` (generate_pseudo_label.py:30-67): flip 8-connected foreground components with
+ * area < area_threshold whose 1-px ring is entirely the opposite label; OpenCV label order; h*w <= 1024.
+ * mask_in/mask_out: uint8 {0,1} [batch, h, w] (may alias). */
+int ucod_refine_small_components(const uint8_t* mask_in, uint8_t* mask_out, int batch, int h, int w,
+                                 int area_threshold, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

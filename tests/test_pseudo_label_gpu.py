@@ -1,0 +1,113 @@
+"""Pseudo-label scoring + cleanup (CUDA) vs. the oracle on planted inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import pseudo_label as opl
+from ucod_dpl_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+
+def planted(B, P=256, nh=12, seed=0):
+    """keys = cluster centre (2-3 clusters) + 0.3*N(0,1); CLS attention = softmax of cluster-dependent logits."""
+    g = torch.Generator().manual_seed(seed)
+    keys = torch.empty(B, P, nh * 64)
+    att = torch.empty(B, nh, P)
+    for b in range(B):
+        nc = 2 + (b % 2)
+        centres = torch.randn(nc, nh * 64, generator=g)
+        assign = torch.randint(0, nc, (P,), generator=g)
+        keys[b] = centres[assign] + 0.3 * torch.randn(P, nh * 64, generator=g)
+        logits = torch.randn(nh, nc, generator=g)[:, assign] * 2 + 0.3 * torch.randn(nh, P, generator=g)
+        att[b] = torch.softmax(torch.cat([torch.zeros(nh, 1), logits], 1), dim=1)[:, 1:]
+    return att, keys
+
+
+@pytest.mark.parametrize("B", [1, 5])
+def test_score_matches_oracle(B):
+    att, keys = planted(B, seed=B)
+    for b in range(B):  # the reference evaluates image by image (batch-global max in sim_map)
+        bkg_r, sim_r, row_r, ref_r = opl.compute_img_bkg_seg(att[b:b + 1], keys[b:b + 1], (16, 16), 0.6)
+        cos, bkg, ref, sim = ops.pseudo_label_score(att[b:b + 1].cuda(), keys[b:b + 1].cuda(), 0.6, want_sim=True)
+        assert ref.item() == ref_r.item()
+        assert (cos.cpu().reshape(16, 16) - row_r[0]).abs().max().item() < 1e-5
+        mism = bkg.cpu().reshape(16, 16).float() != bkg_r[0]
+        assert not mism.any() or (row_r[0][mism] - 0.6).abs().max().item() < 1e-5
+        assert (sim.cpu().reshape(16, 16) - sim_r[0]).abs().max().item() < 1e-4
+
+
+def test_score_batched_equals_per_image_masks():
+    att, keys = planted(7, seed=3)
+    _, bkg, ref, _ = ops.pseudo_label_score(att.cuda(), keys.cuda(), 0.6)
+    for b in range(7):
+        _, bkg1, ref1, _ = ops.pseudo_label_score(att[b:b + 1].cuda(), keys[b:b + 1].cuda(), 0.6)
+        assert torch.equal(bkg[b], bkg1[0]) and ref[b] == ref1[0]
+
+
+def test_dropin_signature():
+    from ucod_dpl_b200.data.utils.found_bkg_mask import compute_img_bkg_seg
+    att, keys = planted(1, seed=9)
+    T = 257
+    full_att = torch.rand(1, 12, T, T)
+    full_att[:, :, 0, 1:] = att
+    feats = torch.cat([torch.randn(1, 1, 768), keys], 1)
+    bkg, sim = compute_img_bkg_seg(full_att.cuda(), feats.cuda(), (16, 16), 0.6, dim=64)
+    bkg_r, sim_r, _, _ = opl.compute_img_bkg_seg(full_att, feats, (16, 16), 0.6)
+    assert bkg.shape == (1, 16, 16) and torch.equal(bkg.cpu(), bkg_r)
+    assert (sim.cpu() - sim_r).abs().max().item() < 1e-4
+
+
+def _edge_masks():
+    ms = []
+    m = np.zeros((16, 16), np.uint8); ms.append(m.copy())                       # empty
+    m = np.ones((16, 16), np.uint8); ms.append(m.copy())                        # full (component fills image)
+    m = np.zeros((16, 16), np.uint8); m[0, 0] = 1; m[15, 15] = 1; m[0, 15] = 1; ms.append(m.copy())  # corners
+    m = np.zeros((16, 16), np.uint8); m[5, 5] = m[6, 6] = m[7, 7] = 1; ms.append(m.copy())          # diagonal, area 3
+    m = np.zeros((16, 16), np.uint8); m[5, 5] = m[6, 6] = m[7, 7] = m[8, 8] = 1; ms.append(m.copy())  # area 4 (kept)
+    m = np.ones((16, 16), np.uint8); m[4:7, 4:7] = 0; m[5, 5] = 1; ms.append(m.copy())              # nested ring
+    m = np.zeros((16, 16), np.uint8); m[3, 3] = 1; m[3, 5] = 1; m[10:14, 10:14] = 1; m[9, 9] = 1; ms.append(m.copy())
+    m = np.zeros((16, 16), np.uint8); m[2, 2:4] = 1; m[4, 2] = 1; m[2, 6] = 1; ms.append(m.copy())  # neighbours in ring
+    m = np.zeros((16, 16), np.uint8); m[0, 3:5] = 1; m[7, 0] = 1; m[15, 8:11] = 1; ms.append(m.copy())  # border touching
+    return ms
+
+
+def test_refine_edge_cases_and_random():
+    rng = np.random.default_rng(0)
+    masks = _edge_masks()
+    for p in (0.05, 0.15, 0.3, 0.5, 0.8, 0.95):
+        for _ in range(40):
+            masks.append((rng.random((16, 16)) < p).astype(np.uint8))
+    stack = np.stack(masks)
+    out = ops.refine_small_components(torch.from_numpy(stack).cuda(), 4).cpu().numpy()
+    for i, m in enumerate(masks):
+        ref = opl.refine_post_process(m, 4)
+        assert np.array_equal(out[i], ref), f"mask {i} differs\n{m}\n{out[i]}\n{ref}"
+
+
+def test_refine_other_sizes_and_thresholds():
+    rng = np.random.default_rng(1)
+    for (h, w, thr) in [(8, 8, 4), (32, 32, 4), (16, 16, 2), (16, 16, 9), (5, 29, 4), (1, 7, 4)]:
+        stack = (rng.random((20, h, w)) < 0.2).astype(np.uint8)
+        out = ops.refine_small_components(torch.from_numpy(stack).cuda(), thr).cpu().numpy()
+        for i in range(20):
+            assert np.array_equal(out[i], opl.refine_post_process(stack[i].reshape(h, w), thr).reshape(h, w))
+
+
+def test_generator_end_to_end_small():
+    """ViT@224 -> scoring -> cleanup vs oracle ViT (fp32) -> oracle scoring: masks agree except near-threshold."""
+    from oracle import vit as ovit
+    from ucod_dpl_b200.generate_pseudo_label import PseudoLabelGenerator
+    from ucod_dpl_b200.synth import random_vit_state_dict, synth_batch_u8
+    spec = ovit.spec_for("dinov2")
+    sd = random_vit_state_dict(spec, seed=0)
+    imgs = synth_batch_u8(0, 3, 224, 224)
+    gen = PseudoLabelGenerator(sd, "dinov2")
+    masks = gen(imgs.cuda()).cpu().numpy()
+    ref = ovit.vit_forward(sd, spec, ovit.normalize_u8(imgs), want_attn=True)
+    agree = 0
+    for b in range(3):
+        bkg, _, row, _ = opl.compute_img_bkg_seg(ref["cls_attn"][b:b + 1], ref["key_tokens"][b:b + 1], (16, 16), 0.6)
+        want = opl.refine_post_process((1 - bkg[0]).numpy())
+        agree += (want == masks[b]).mean()
+    assert agree / 3 >= 0.99

@@ -5,6 +5,7 @@
 #include "vit.cuh"
 #include "decoder.cuh"
 #include "prof.cuh"
+#include "pseudo_label.cuh"
 
 using namespace ucod;
 
@@ -79,6 +80,18 @@ int ucod_upsample_bilinear(const float* in, void* out, int batch, int in_h, int 
                            int binarize, void* stream) {
     return upsample_bilinear(in, out, batch, in_h, in_w, out_h, out_w, binarize,
                              reinterpret_cast<cudaStream_t>(stream));
+}
+
+int ucod_pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf16, int batch, int heads, int patches,
+                            float th_bkg, float epsilon, float* cos, uint8_t* bkg, int32_t* ref_idx, float* sim,
+                            void* scratch, void* stream) {
+    return pseudo_label_score(attn_cls, keys, keys_bf16, batch, heads, patches, th_bkg, epsilon, cos, bkg, ref_idx,
+                              sim, static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_refine_small_components(const uint8_t* mask_in, uint8_t* mask_out, int batch, int h, int w,
+                                 int area_threshold, void* stream) {
+    return refine_small_components(mask_in, mask_out, batch, h, w, area_threshold,
+                                   reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,27 @@
+"""`compute_img_bkg_seg` with the reference's signature (data/utils/found_bkg_mask.py:4-85); the arithmetic runs
+in `csrc/pseudo_label.cu` (one CTA per image, only the needed row of the cosine matrix)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from ... import ops
+from ..._lib import UcodError
+
+
+def compute_img_bkg_seg(attentions, feats, featmap_dims, th_bkg, up_size: int = None, dim=64,
+                        epsilon: float = 1e-10, apply_weights: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """attentions [B,nh,T,T] (last layer), feats [B,T,nh*dim] (last-layer keys incl. CLS).
+    Returns (bkg_mask [B,h,w] float {0,1}, sim_map [B,h,w] float), exactly as the reference."""
+    w_f, h_f = featmap_dims
+    if up_size is not None and up_size != w_f:
+        raise UcodError("compute_img_bkg_seg: up_size != featmap size is never used by the reference path "
+                        "and is not implemented")
+    if not apply_weights or dim != 64:
+        raise UcodError("compute_img_bkg_seg: only apply_weights=True with head dim 64 (ViT-B) is implemented")
+    att = attentions[:, :, 0, 1:] if attentions.dim() == 4 else attentions
+    keys = feats[:, 1:] if feats.shape[1] == w_f * h_f + 1 else feats
+    cos, bkg, _, sim = ops.pseudo_label_score(att, keys, float(th_bkg), float(epsilon), want_sim=True)
+    nb = att.shape[0]
+    return bkg.reshape(nb, w_f, h_f).float(), sim.reshape(nb, w_f, h_f)

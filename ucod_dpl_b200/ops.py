@@ -79,3 +79,39 @@ def upsample_bilinear(x: torch.Tensor, size, binarize: bool = False) -> torch.Te
         _lib.call("ucod_upsample_bilinear", ptr(x3), ptr(out), x3.shape[0], shp[-2], shp[-1], oh, ow,
                   1 if binarize else 0, stream_ptr(x.device))
     return out.reshape(*shp[:-2], oh, ow)
+
+
+# ------------------------------------------------------------------------------------------------
+def pseudo_label_score(attn_cls: torch.Tensor, keys: torch.Tensor, th_bkg: float, epsilon: float = 1e-10,
+                       want_sim: bool = False):
+    """attn_cls [B,heads,P] fp32, keys [B,P,heads*64] fp32|bf16 -> (cos [B,P], bkg u8 [B,P], ref_idx [B], sim|None)."""
+    _lib.require_cuda(attn_cls, keys)
+    attn_cls = attn_cls.float().contiguous()
+    keys = keys.contiguous()
+    if keys.dtype not in (torch.float32, torch.bfloat16):
+        keys = keys.float()
+    B, nh, P = attn_cls.shape
+    if keys.shape != (B, P, nh * 64):
+        raise UcodError(f"pseudo_label_score: keys {tuple(keys.shape)} do not match attention {tuple(attn_cls.shape)}")
+    dev = attn_cls.device
+    cos = torch.empty(B, P, device=dev, dtype=torch.float32)
+    bkg = torch.empty(B, P, device=dev, dtype=torch.uint8)
+    ref = torch.empty(B, device=dev, dtype=torch.int32)
+    sim = torch.empty(B, P, device=dev, dtype=torch.float32) if want_sim else None
+    scratch = torch.empty(1, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_pseudo_label_score", ptr(attn_cls), ptr(keys), 1 if keys.dtype == torch.bfloat16 else 0, B,
+                  nh, P, c_float(th_bkg), c_float(epsilon), ptr(cos), ptr(bkg), ptr(ref), ptr(sim), ptr(scratch),
+                  stream_ptr(dev))
+    return cos, bkg, ref, sim
+
+
+def refine_small_components(mask_u8: torch.Tensor, area_threshold: int = 4) -> torch.Tensor:
+    """mask uint8 {0,1} [B,h,w] -> refined uint8 [B,h,w] (refine_post_process, batched)."""
+    _lib.require_cuda(mask_u8)
+    m = mask_u8.to(torch.uint8).contiguous()
+    B, h, w = m.shape
+    out = torch.empty_like(m)
+    with torch.cuda.device(m.device):
+        _lib.call("ucod_refine_small_components", ptr(m), ptr(out), B, h, w, int(area_threshold), stream_ptr(m.device))
+    return out
