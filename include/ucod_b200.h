@@ -133,6 +133,43 @@ int ucod_pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf
 int ucod_refine_small_components(const uint8_t* mask_in, uint8_t* mask_out, int batch, int h, int w,
                                  int area_threshold, void* stream);
 
+/* ---- Look-Twice -----------------------------------------------------------------------------------
+ * `ValLoop_Look_Twice.process_preds` box logic (engine/runner/loop_UCOD_DPL.py:366-384) + `expand_bbox`
+ * (:399-417) for a batch of binarised masks [batch,h,w] uint8 (non-zero = foreground):
+ * 8-connected components (cv2.connectedComponents order), area fractions, boundingRect, dynamic/const
+ * expansion in exact fp64, stable sort by -w*h.
+ * boxes: int32 [batch, UCOD_LT_MAX_BOXES, 4] (x,y,w,h); nbox: int32 [batch] — >= 0 number of boxes,
+ * -1 = "None" (largest component fraction >= look_twice_th, no second look), -2 = the reference would raise
+ * ValueError (sqrt of a negative scale); status: int32 [batch] bit0 = sqrt domain, bit1 = box table overflow.
+ * labels (optional, int32 [batch,h,w]): per-pixel component root (min raster index of the component, -1 = bg). */
+#define UCOD_LT_MAX_BOXES 128
+uint64_t ucod_lt_boxes_workspace_bytes(int batch, int h, int w);
+int ucod_lt_boxes(const uint8_t* mask, int batch, int h, int w, double look_twice_th, int expand_dynamic,
+                  double const_scale, int32_t* boxes, int32_t* nbox, int32_t* status, int32_t* labels,
+                  void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* PIL `crop` + torchvision `Resize((out_h,out_w))` (Pillow antialiased BILINEAR, bit-exact fixed-point two-pass
+ * resample) of ROIs of uint8 RGB images (loop_UCOD_DPL.py:335-342).  images: uint8, element strides given
+ * (planar CHW or interleaved HWC both work); jobs: device int32 [njobs,5] = (image index, x, y, w, h) in source
+ * pixels (out-of-image area reads as 0, like PIL); max_crop_h >= max job h; out: uint8 planar [njobs,3,out_h,out_w];
+ * err_flag: device int32, bit0 set if a scale exceeds the supported tap count. */
+uint64_t ucod_roi_crop_resize_workspace_bytes(int njobs, int max_crop_h, int out_h, int out_w);
+int ucod_roi_crop_resize(const uint8_t* images, int n_images, int src_h, int src_w, int64_t image_stride,
+                         int64_t channel_stride, int64_t row_stride, int64_t pixel_stride, const int32_t* jobs,
+                         int njobs, int max_crop_h, uint8_t* out, int out_h, int out_w, void* workspace,
+                         uint64_t workspace_bytes, int32_t* err_flag, void* stream);
+
+/* Second-look paste (loop_UCOD_DPL.py:348-351): binarise logits [njobs,g_h,g_w] (sigmoid > 0.5), Pillow default
+ * BICUBIC resize of the {0,255} map to (w,h), paste at (x,y) into mask uint8 [n_images,s_h,s_w] (values 0..255).
+ * jobs: device int32 [njobs,6] = (image index, x, y, w, h, rank); jobs of one image are applied in rank order
+ * (0..max_rank). out_cap >= max(w,h) over jobs. */
+uint64_t ucod_paste_bicubic_workspace_bytes(int njobs, int g_h, int out_cap);
+int ucod_paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const int32_t* jobs, int max_rank,
+                       uint8_t* mask, int n_images, int s_h, int s_w, int out_cap, void* workspace,
+                       uint64_t workspace_bytes, int32_t* err_flag, void* stream);
+/* out[i] = in[i] ? mul : 0  ({0,1} mask -> {0,255} canvas, loop_UCOD_DPL.py:330). */
+int ucod_mask_scale_u8(const uint8_t* in, uint8_t* out, uint64_t n, int mul, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,6 +6,7 @@
 #include "decoder.cuh"
 #include "prof.cuh"
 #include "pseudo_label.cuh"
+#include "looktwice.cuh"
 
 using namespace ucod;
 
@@ -92,6 +93,39 @@ int ucod_refine_small_components(const uint8_t* mask_in, uint8_t* mask_out, int 
                                  int area_threshold, void* stream) {
     return refine_small_components(mask_in, mask_out, batch, h, w, area_threshold,
                                    reinterpret_cast<cudaStream_t>(stream));
+}
+
+uint64_t ucod_lt_boxes_workspace_bytes(int batch, int h, int w) {
+    return (uint64_t)lt_boxes_workspace_bytes(batch, h, w);
+}
+int ucod_lt_boxes(const uint8_t* mask, int batch, int h, int w, double look_twice_th, int expand_dynamic,
+                  double const_scale, int32_t* boxes, int32_t* nbox, int32_t* status, int32_t* labels,
+                  void* workspace, uint64_t workspace_bytes, void* stream) {
+    return lt_boxes(mask, batch, h, w, look_twice_th, expand_dynamic, const_scale, boxes, nbox, status, labels,
+                    workspace, (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+uint64_t ucod_roi_crop_resize_workspace_bytes(int njobs, int max_crop_h, int out_h, int out_w) {
+    return (uint64_t)roi_crop_resize_workspace_bytes(njobs, max_crop_h, out_h, out_w);
+}
+int ucod_roi_crop_resize(const uint8_t* images, int n_images, int src_h, int src_w, int64_t image_stride,
+                         int64_t channel_stride, int64_t row_stride, int64_t pixel_stride, const int32_t* jobs,
+                         int njobs, int max_crop_h, uint8_t* out, int out_h, int out_w, void* workspace,
+                         uint64_t workspace_bytes, int32_t* err_flag, void* stream) {
+    return roi_crop_resize(images, n_images, src_h, src_w, image_stride, channel_stride, row_stride, pixel_stride,
+                           jobs, njobs, max_crop_h, out, out_h, out_w, workspace, (size_t)workspace_bytes, err_flag,
+                           reinterpret_cast<cudaStream_t>(stream));
+}
+uint64_t ucod_paste_bicubic_workspace_bytes(int njobs, int g_h, int out_cap) {
+    return (uint64_t)paste_bicubic_workspace_bytes(njobs, g_h, out_cap);
+}
+int ucod_paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const int32_t* jobs, int max_rank,
+                       uint8_t* mask, int n_images, int s_h, int s_w, int out_cap, void* workspace,
+                       uint64_t workspace_bytes, int32_t* err_flag, void* stream) {
+    return paste_bicubic(logits, njobs, g_h, g_w, jobs, max_rank, mask, n_images, s_h, s_w, out_cap, workspace,
+                         (size_t)workspace_bytes, err_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_mask_scale_u8(const uint8_t* in, uint8_t* out, uint64_t n, int mul, void* stream) {
+    return mask_scale_u8(in, out, (size_t)n, mul, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,606 @@
+// Look-Twice device stages (engine/runner/loop_UCOD_DPL.py:326-417).
+//
+//  1. lt_boxes: 8-connected component labelling of the binarised 518^2 / 296^2 mask (union-find in global memory,
+//     atomicMin linking), per-component area / bounding box / OpenCV ordering key, then the reference's box logic
+//     (`process_preds` :366-384, `expand_bbox` :399-417) in IEEE fp64 with explicit round-to-nearest ops so that
+//     `int()` truncations match CPython bit for bit.  OpenCV numbers components by their first 2x2 block in
+//     block-raster order; that key is reproduced so ties in the final stable sort fall the same way.
+//  2. roi_crop_resize: PIL `crop` + torchvision `Resize` (= Pillow ImagingResample, antialiased triangle filter):
+//     fp64 coefficients -> 22-bit fixed point, horizontal pass then vertical pass, uint8 rounding after each.
+//  3. paste_bicubic: `ToPILImage` + `Image.resize` (Pillow default BICUBIC, a=-0.5) of the second-pass 37^2 mask and
+//     `paste` into the full-size mask, boxes applied in the reference's order.
+// All three are HBM-/latency-bound integer work: coalesced row-major passes, warp-aggregated atomics.
+#include "looktwice.cuh"
+
+#include "prof.cuh"
+
+namespace ucod {
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// union-find connected components
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int uf_find(const int* L, int i) {
+    const volatile int* V = L;
+    while (true) {
+        const int p = V[i];
+        if (p == i) return i;
+        i = p;
+    }
+}
+__device__ __forceinline__ void uf_union(int* L, int a, int b) {
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&L[a], b);  // link larger root under the smaller one
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ L, int n_img, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    L[i] = mask[i] ? (int)(i % n_img) : -1;
+}
+
+__global__ void ccl_merge_kernel(int* __restrict__ L, int H, int W, int B) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int b = blockIdx.z;
+    if (x >= W) return;
+    int* Lb = L + (size_t)b * H * W;
+    const int i = y * W + x;
+    if (Lb[i] < 0) return;
+    if (x > 0 && Lb[i - 1] >= 0) uf_union(Lb, i, i - 1);
+    if (y > 0) {
+        const int u = i - W;
+        if (Lb[u] >= 0) uf_union(Lb, i, u);
+        if (x > 0 && Lb[u - 1] >= 0) uf_union(Lb, i, u - 1);
+        if (x + 1 < W && Lb[u + 1] >= 0) uf_union(Lb, i, u + 1);
+    }
+}
+
+// final root per pixel + per-root area (warp-aggregated atomics)
+__global__ void ccl_flatten_area_kernel(int* __restrict__ L, int* __restrict__ area, int n_img, size_t total) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int root = -1;
+    size_t base = 0;
+    if (i < total) {
+        base = (i / n_img) * (size_t)n_img;
+        const int l = L[i];
+        if (l >= 0) {
+            root = uf_find(L + base, (int)(i - base));
+            L[i] = root;
+        }
+    }
+    // key must distinguish images: a warp may straddle an image boundary
+    const long long key = root < 0 ? -1ll : (long long)(base + root);
+    const unsigned grp = __match_any_sync(0xffffffffu, key);
+    if (root >= 0) {
+        const int leader = __ffs(grp) - 1;
+        if ((int)(threadIdx.x & 31) == leader) atomicAdd(&area[base + root], __popc(grp));
+    }
+}
+
+constexpr int LT_MAXBIG = 128;  // components with area fraction > 0.01: at most 99
+
+struct ImgSummary {
+    int n_comp;
+    int max_area;
+    int n_big;
+    int pad;
+};
+
+// roots: count components, track the largest, register the "big" ones (p > 0.01) in a compact table
+__global__ void ccl_roots_kernel(const int* __restrict__ L, int* __restrict__ area, ImgSummary* __restrict__ summ,
+                                 int* __restrict__ big_root, int* __restrict__ big_area, int n_img, size_t total,
+                                 double inv_gate /* p > 0.01 test uses area / n_img in fp64 */) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int b = (int)(i / n_img);
+    const int li = (int)(i - (size_t)b * n_img);
+    if (L[i] != li) return;
+    const int a = area[i];
+    atomicAdd(&summ[b].n_comp, 1);
+    atomicMax(&summ[b].max_area, a);
+    const double p = __ddiv_rn((double)a, (double)n_img);
+    if (p > inv_gate) {
+        const int slot = atomicAdd(&summ[b].n_big, 1);
+        if (slot < LT_MAXBIG) {
+            big_root[b * LT_MAXBIG + slot] = li;
+            big_area[b * LT_MAXBIG + slot] = a;
+            area[i] = -(slot + 1);  // pixels find their slot through their root
+        }
+    }
+}
+
+struct BigStats {
+    int x0, x1, y0, y1, key;
+};
+
+__global__ void ccl_bbox_kernel(const int* __restrict__ L, const int* __restrict__ area, BigStats* __restrict__ st,
+                                int H, int W, int B) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y, b = blockIdx.z;
+    int slot = -1;
+    if (x < W) {
+        const size_t base = (size_t)b * H * W;
+        const int r = L[base + (size_t)y * W + x];
+        if (r >= 0) {
+            const int a = area[base + r];
+            if (a < 0) slot = -a - 1;
+        }
+    }
+    const unsigned grp = __match_any_sync(0xffffffffu, slot);
+    if (slot >= 0) {
+        // all lanes of a warp share y and b: reduce x over the group, one set of atomics per group
+        const int xmin = __reduce_min_sync(grp, x);
+        const int xmax = __reduce_max_sync(grp, x);
+        if ((int)(threadIdx.x & 31) == __ffs(grp) - 1) {
+            BigStats* s = st + b * LT_MAXBIG + slot;
+            atomicMin(&s->x0, xmin);
+            atomicMax(&s->x1, xmax);
+            atomicMin(&s->y0, y);
+            atomicMax(&s->y1, y);
+            atomicMin(&s->key, (y >> 1) * ((W + 1) >> 1) + (xmin >> 1));
+        }
+    }
+}
+
+__global__ void lt_init_stats_kernel(BigStats* st, int n, int H, int W) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    st[i].x0 = W, st[i].x1 = -1, st[i].y0 = H, st[i].y1 = -1, st[i].key = 0x7fffffff;
+}
+
+// One thread per image: process_preds' branchy tail + expand_bbox in exact fp64.
+__global__ void lt_boxes_kernel(const ImgSummary* __restrict__ summ, const int* __restrict__ big_area,
+                                const BigStats* __restrict__ st, int* __restrict__ boxes, int* __restrict__ nbox,
+                                int* __restrict__ status, int B, int H, int W, double look_twice_th, int dynamic,
+                                double const_scale) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    int* out = boxes + (size_t)b * LT_MAXBIG * 4;
+    status[b] = 0;
+    const ImgSummary s = summ[b];
+    if (s.n_comp == 0) {  // loop_UCOD_DPL.py:369-370
+        out[0] = 129, out[1] = 129, out[2] = 259, out[3] = 259;
+        nbox[b] = 1;
+        return;
+    }
+    const double hw = (double)((long long)H * W);
+    const double p_max = __ddiv_rn((double)s.max_area, hw);
+    if (!(p_max < look_twice_th)) {  // :372 else-branch -> None
+        nbox[b] = -1;
+        return;
+    }
+    int n = s.n_big < LT_MAXBIG ? s.n_big : LT_MAXBIG;
+    if (s.n_big > LT_MAXBIG) status[b] |= 2;
+    // order slots by OpenCV label order (first-block key), insertion sort on a local index array
+    int order[LT_MAXBIG];
+    for (int i = 0; i < n; ++i) {
+        int j = i;
+        const int k = st[b * LT_MAXBIG + i].key;
+        while (j > 0 && st[b * LT_MAXBIG + order[j - 1]].key > k) {
+            order[j] = order[j - 1];
+            --j;
+        }
+        order[j] = i;
+    }
+    int bx[LT_MAXBIG][4];
+    for (int t = 0; t < n; ++t) {
+        const int slot = order[t];
+        const BigStats g = st[b * LT_MAXBIG + slot];
+        const int x = g.x0, y = g.y0, w = g.x1 - g.x0 + 1, h = g.y1 - g.y0 + 1;
+        double scale = const_scale;
+        if (dynamic) {
+            const double fr = __ddiv_rn((double)big_area[b * LT_MAXBIG + slot], (double)(h * w));
+            const double br = __ddiv_rn((double)(h * y), hw);  // (sic) h*y, loop_UCOD_DPL.py:404
+            const double arg = __dadd_rn(__dsub_rn(1.0, __ddiv_rn(br, fr)), 1.0);
+            if (arg < 0.0) {  // math.sqrt raises ValueError in the reference
+                status[b] |= 1;
+                nbox[b] = -2;
+                return;
+            }
+            scale = __dsqrt_rn(arg);
+        }
+        const double new_w = __dmul_rn((double)w, scale);
+        const double new_h = __dmul_rn((double)h, scale);
+        double new_x = __dsub_rn((double)x, __ddiv_rn(__dsub_rn(new_w, (double)w), 2.0));
+        double new_y = __dsub_rn((double)y, __ddiv_rn(__dsub_rn(new_h, (double)h), 2.0));
+        new_x = new_x > 0.0 ? new_x : 0.0;  // max(0, new_x)
+        if (__dadd_rn(new_x, new_w) > (double)H) new_x = __dsub_rn((double)H, new_w);  // img_width := h (:379)
+        new_y = new_y > 0.0 ? new_y : 0.0;
+        if (__dadd_rn(new_y, new_h) > (double)W) new_y = __dsub_rn((double)W, new_h);  // img_height := w
+        bx[t][0] = (int)new_x, bx[t][1] = (int)new_y, bx[t][2] = (int)new_w, bx[t][3] = (int)new_h;
+    }
+    // stable sort by -w*h
+    int ord2[LT_MAXBIG];
+    for (int i = 0; i < n; ++i) {
+        int j = i;
+        const long long k = -(long long)bx[i][2] * bx[i][3];
+        while (j > 0 && -(long long)bx[ord2[j - 1]][2] * bx[ord2[j - 1]][3] > k) {
+            ord2[j] = ord2[j - 1];
+            --j;
+        }
+        ord2[j] = i;
+    }
+    for (int i = 0; i < n; ++i)
+        for (int c = 0; c < 4; ++c) out[i * 4 + c] = bx[ord2[i]][c];
+    nbox[b] = n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pillow ImagingResample (8 bpc): coefficient tables
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_KMAX = 40;          // max taps per output sample (support scale up to ~19x for bilinear)
+constexpr int RS_PRECISION_BITS = 22;
+
+__device__ __forceinline__ double filt_bilinear(double x) {
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return __dsub_rn(1.0, x);
+    return 0.0;
+}
+__device__ __forceinline__ double filt_bicubic(double x) {
+    const double a = -0.5;
+    if (x < 0.0) x = -x;
+    if (x < 1.0) {
+        // ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        double t = __dsub_rn(__dmul_rn(a + 2.0, x), a + 3.0);
+        t = __dmul_rn(__dmul_rn(t, x), x);
+        return __dadd_rn(t, 1.0);
+    }
+    if (x < 2.0) {
+        // (((x - 5) * x + 8) * x - 4) * a
+        double t = __dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0);
+        t = __dsub_rn(__dmul_rn(t, x), 4.0);
+        return __dmul_rn(t, a);
+    }
+    return 0.0;
+}
+
+// job geometry for one axis: in_size source samples -> out_size samples (box = whole source)
+// bounds[(job*2+axis)*out_cap + xx] = {xmin, count} ; coef[((job*2+axis)*out_cap + xx)*RS_KMAX + k]
+__global__ void resample_coeffs_kernel(const int* __restrict__ in_sizes /*[njobs,2] (w,h)*/,
+                                       const int* __restrict__ out_sizes /*[njobs,2] (w,h)*/, int njobs, int out_cap,
+                                       int bicubic, int2* __restrict__ bounds, int* __restrict__ coef,
+                                       int* __restrict__ err) {
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int axis = blockIdx.y, job = blockIdx.z;
+    const int in_size = in_sizes[job * 2 + axis], out_size = out_sizes[job * 2 + axis];
+    if (xx >= out_size || xx >= out_cap || in_size <= 0) return;
+    const double fsupport = bicubic ? 2.0 : 1.0;
+    const double scale = __ddiv_rn((double)(float)in_size, (double)out_size);
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = __dmul_rn(fsupport, filterscale);
+    const int ksize = (int)ceil(support) * 2 + 1;
+    if (ksize > RS_KMAX) {
+        atomicOr(err, 1);
+        return;
+    }
+    const double center = __dadd_rn(0.0, __dmul_rn((double)xx + 0.5, scale));
+    const double ss = __ddiv_rn(1.0, filterscale);
+    int xmin = (int)__dadd_rn(__dsub_rn(center, support), 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
+    if (xmax > in_size) xmax = in_size;
+    const int n = xmax - xmin;
+    double w[RS_KMAX];
+    double ww = 0.0;
+    for (int x = 0; x < n; ++x) {
+        const double arg = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+        const double v = bicubic ? filt_bicubic(arg) : filt_bilinear(arg);
+        w[x] = v;
+        ww = __dadd_rn(ww, v);
+    }
+    const size_t o = ((size_t)job * 2 + axis) * out_cap + xx;
+    bounds[o] = make_int2(xmin, n);
+    int* kk = coef + o * RS_KMAX;
+    for (int x = 0; x < n; ++x) {
+        double k = w[x];
+        if (ww != 0.0) k = __ddiv_rn(k, ww);
+        const double f = __dmul_rn(k, (double)(1 << RS_PRECISION_BITS));
+        kk[x] = k < 0 ? (int)__dadd_rn(-0.5, f) : (int)__dadd_rn(0.5, f);
+    }
+    for (int x = n; x < RS_KMAX; ++x) kk[x] = 0;
+}
+
+__device__ __forceinline__ uint8_t clip8(int v) {
+    v >>= RS_PRECISION_BITS;
+    return (uint8_t)(v < 0 ? 0 : (v > 255 ? 255 : v));
+}
+
+// ---- crop + horizontal pass: tmp[job][c][r][xx], r over source rows y_first..y_last-1 of the crop ----
+__global__ void crop_hpass_kernel(const uint8_t* __restrict__ images, int H0, int W0, long long img_stride,
+                                  long long ch_stride, long long row_stride, long long px_stride,
+                                  const int* __restrict__ jobs /*[n,5] img,x,y,w,h*/, const int2* __restrict__ bounds,
+                                  const int* __restrict__ coef, uint8_t* __restrict__ tmp, int out_cap, int out_w,
+                                  int out_h, int tmp_rows) {
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int job = blockIdx.z;
+    const int c = blockIdx.y % 3, r = blockIdx.y / 3;
+    const int* jb = jobs + job * 5;
+    const int cw = jb[3], chh = jb[4];
+    if (cw <= 0 || chh <= 0 || xx >= out_w) return;
+    const size_t vb = ((size_t)job * 2 + 1) * out_cap;
+    const int y_first = bounds[vb].x;
+    const int y_last = bounds[vb + out_h - 1].x + bounds[vb + out_h - 1].y;
+    if (r >= y_last - y_first || r >= tmp_rows) return;
+    const int sy = jb[2] + y_first + r;  // source row in the original image
+    const size_t hb = ((size_t)job * 2 + 0) * out_cap + xx;
+    const int2 bd = bounds[hb];
+    const int* kk = coef + hb * RS_KMAX;
+    int acc = 1 << (RS_PRECISION_BITS - 1);
+    if (sy >= 0 && sy < H0) {
+        const uint8_t* row = images + (size_t)jb[0] * img_stride + (size_t)c * ch_stride + (size_t)sy * row_stride;
+        for (int k = 0; k < bd.y; ++k) {
+            const int sx = jb[1] + bd.x + k;
+            const int px = (sx >= 0 && sx < W0) ? row[(size_t)sx * px_stride] : 0;
+            acc += px * kk[k];
+        }
+    }
+    tmp[(((size_t)job * 3 + c) * tmp_rows + r) * out_w + xx] = clip8(acc);
+}
+
+// ---- vertical pass: out[job][c][yy][xx] (planar u8) ----
+__global__ void crop_vpass_kernel(const uint8_t* __restrict__ tmp, const int* __restrict__ jobs,
+                                  const int2* __restrict__ bounds, const int* __restrict__ coef,
+                                  uint8_t* __restrict__ out, int out_cap, int out_w, int out_h, int tmp_rows) {
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int job = blockIdx.z;
+    const int c = blockIdx.y % 3, yy = blockIdx.y / 3;
+    const int* jb = jobs + job * 5;
+    if (xx >= out_w) return;
+    uint8_t* dst = out + (((size_t)job * 3 + c) * out_h + yy) * out_w + xx;
+    if (jb[3] <= 0 || jb[4] <= 0) {
+        *dst = 0;
+        return;
+    }
+    const size_t vb = ((size_t)job * 2 + 1) * out_cap;
+    const int y_first = bounds[vb].x;
+    const int2 bd = bounds[vb + yy];
+    const int* kk = coef + (vb + yy) * RS_KMAX;
+    const uint8_t* src = tmp + ((size_t)job * 3 + c) * tmp_rows * out_w + xx;
+    int acc = 1 << (RS_PRECISION_BITS - 1);
+    for (int k = 0; k < bd.y; ++k) acc += (int)src[(size_t)(bd.x - y_first + k) * out_w] * kk[k];
+    *dst = clip8(acc);
+}
+
+// ---- paste: horizontal pass over the binarised g x g prediction ----
+__global__ void paste_hpass_kernel(const float* __restrict__ logits, int g_h, int g_w,
+                                   const int* __restrict__ jobs /*[n,6] img,x,y,w,h,rank*/,
+                                   const int2* __restrict__ bounds, const int* __restrict__ coef,
+                                   uint8_t* __restrict__ tmp, int out_cap) {
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y, job = blockIdx.z;
+    const int* jb = jobs + job * 6;
+    const int w = jb[3], h = jb[4];
+    if (w <= 0 || h <= 0 || xx >= w || xx >= out_cap) return;
+    const size_t hb = ((size_t)job * 2 + 0) * out_cap + xx;
+    const int2 bd = bounds[hb];
+    const int* kk = coef + hb * RS_KMAX;
+    const float* row = logits + ((size_t)job * g_h + r) * g_w;
+    int acc = 1 << (RS_PRECISION_BITS - 1);
+    for (int k = 0; k < bd.y; ++k) acc += (row[bd.x + k] > 0x1.8p-24f ? 255 : 0) * kk[k];
+    tmp[((size_t)job * g_h + r) * out_cap + xx] = clip8(acc);
+}
+
+// ---- paste: vertical pass, written straight into the full-size mask (only jobs of the given rank) ----
+__global__ void paste_vpass_kernel(const uint8_t* __restrict__ tmp, int g_h, const int* __restrict__ jobs,
+                                   const int2* __restrict__ bounds, const int* __restrict__ coef,
+                                   uint8_t* __restrict__ mask, int S_h, int S_w, int out_cap, int rank) {
+    const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int yy = blockIdx.y, job = blockIdx.z;
+    const int* jb = jobs + job * 6;
+    if (jb[5] != rank) return;
+    const int w = jb[3], h = jb[4];
+    if (w <= 0 || h <= 0 || xx >= w || yy >= h || xx >= out_cap || yy >= out_cap) return;
+    const int dx = jb[1] + xx, dy = jb[2] + yy;
+    if (dx < 0 || dx >= S_w || dy < 0 || dy >= S_h) return;  // Image.paste clips
+    const size_t vb = ((size_t)job * 2 + 1) * out_cap + yy;
+    const int2 bd = bounds[vb];
+    const int* kk = coef + vb * RS_KMAX;
+    // the horizontal pass covered source rows y_first.. ; for an un-cropped source y_first is bounds[0].xmin
+    const uint8_t* src = tmp + (size_t)job * g_h * out_cap + xx;
+    int acc = 1 << (RS_PRECISION_BITS - 1);
+    for (int k = 0; k < bd.y; ++k) acc += (int)src[(size_t)(bd.x + k) * out_cap] * kk[k];
+    mask[((size_t)jb[0] * S_h + dy) * S_w + dx] = clip8(acc);
+}
+
+__global__ void mask_scale_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, int mul) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] ? (uint8_t)mul : 0;
+}
+
+__global__ void fill_crop_sizes_kernel(const int* jobs, int* sizes, int njobs, int out_w, int out_h) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    sizes[j * 2 + 0] = jobs[j * 5 + 3];
+    sizes[j * 2 + 1] = jobs[j * 5 + 4];
+    sizes[njobs * 2 + j * 2 + 0] = out_w;
+    sizes[njobs * 2 + j * 2 + 1] = out_h;
+}
+__global__ void fill_paste_sizes_kernel(const int* jobs, int* sizes, int njobs, int g_w, int g_h) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= njobs) return;
+    sizes[j * 2 + 0] = g_w;
+    sizes[j * 2 + 1] = g_h;
+    sizes[njobs * 2 + j * 2 + 0] = jobs[j * 6 + 3];
+    sizes[njobs * 2 + j * 2 + 1] = jobs[j * 6 + 4];
+}
+
+size_t align256(size_t v) { return (v + 255) / 256 * 256; }
+
+}  // namespace
+
+// ================================================================================================
+size_t lt_boxes_workspace_bytes(int B, int H, int W) {
+    const size_t n = (size_t)B * H * W;
+    return align256(n * 4) * 2 + align256((size_t)B * sizeof(ImgSummary)) + align256((size_t)B * LT_MAXBIG * 4) * 2 +
+           align256((size_t)B * LT_MAXBIG * sizeof(BigStats)) + 1024;
+}
+
+int lt_boxes(const uint8_t* mask, int B, int H, int W, double look_twice_th, int dynamic, double const_scale,
+             int* boxes, int* nbox, int* status, int* labels_out, void* workspace, size_t ws_bytes,
+             cudaStream_t stream) {
+    UCOD_REQUIRE(mask && boxes && nbox && status && workspace, "lt_boxes: null argument");
+    UCOD_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "lt_boxes: bad geometry");
+    UCOD_REQUIRE(ws_bytes >= lt_boxes_workspace_bytes(B, H, W), "lt_boxes: workspace too small");
+    const int n_img = H * W;
+    const size_t total = (size_t)B * n_img;
+    uint8_t* p = static_cast<uint8_t*>(workspace);
+    int* L = reinterpret_cast<int*>(p);
+    p += align256(total * 4);
+    int* area = reinterpret_cast<int*>(p);
+    p += align256(total * 4);
+    ImgSummary* summ = reinterpret_cast<ImgSummary*>(p);
+    p += align256((size_t)B * sizeof(ImgSummary));
+    int* big_root = reinterpret_cast<int*>(p);
+    p += align256((size_t)B * LT_MAXBIG * 4);
+    int* big_area = reinterpret_cast<int*>(p);
+    p += align256((size_t)B * LT_MAXBIG * 4);
+    BigStats* st = reinterpret_cast<BigStats*>(p);
+
+    UCOD_CHECK_CUDA(cudaMemsetAsync(area, 0, total * 4, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(summ, 0, (size_t)B * sizeof(ImgSummary), stream));
+    const int T = 256;
+    const unsigned lin = (unsigned)((total + T - 1) / T);
+    dim3 g2(ceil_div(W, 128), H, B);
+    {
+        ProfScope ps(KC_CCL, stream, (double)total * 5);
+        ccl_init_kernel<<<lin, T, 0, stream>>>(mask, L, n_img, total);
+    }
+    {
+        ProfScope ps(KC_CCL, stream, (double)total * 8);
+        ccl_merge_kernel<<<g2, 128, 0, stream>>>(L, H, W, B);
+    }
+    {
+        ProfScope ps(KC_CCL, stream, (double)total * 8);
+        ccl_flatten_area_kernel<<<lin, T, 0, stream>>>(L, area, n_img, total);
+    }
+    lt_init_stats_kernel<<<ceil_div(B * LT_MAXBIG, T), T, 0, stream>>>(st, B * LT_MAXBIG, H, W);
+    {
+        ProfScope ps(KC_CCL, stream, (double)total * 8);
+        ccl_roots_kernel<<<lin, T, 0, stream>>>(L, area, summ, big_root, big_area, n_img, total, 0.01);
+    }
+    {
+        ProfScope ps(KC_CCL, stream, (double)total * 8);
+        ccl_bbox_kernel<<<g2, 128, 0, stream>>>(L, area, st, H, W, B);
+    }
+    {
+        ProfScope ps(KC_CCL, stream, (double)B * LT_MAXBIG * 40);
+        lt_boxes_kernel<<<ceil_div(B, 32), 32, 0, stream>>>(summ, big_area, st, boxes, nbox, status, B, H, W,
+                                                           look_twice_th, dynamic, const_scale);
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    if (labels_out) UCOD_CHECK_CUDA(cudaMemcpyAsync(labels_out, L, total * 4, cudaMemcpyDeviceToDevice, stream));
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t roi_crop_resize_workspace_bytes(int njobs, int max_crop_h, int out_h, int out_w) {
+    const int cap = out_h > out_w ? out_h : out_w;
+    return align256((size_t)njobs * 2 * cap * sizeof(int2)) + align256((size_t)njobs * 2 * cap * RS_KMAX * 4) +
+           align256((size_t)njobs * 3 * max_crop_h * out_w) + align256((size_t)njobs * 4 * 4) + 1024;
+}
+
+int roi_crop_resize(const uint8_t* images, int n_img, int H0, int W0, long long img_stride, long long ch_stride,
+                    long long row_stride, long long px_stride, const int* jobs, int njobs, int max_crop_h,
+                    uint8_t* out, int out_h, int out_w, void* workspace, size_t ws_bytes, int* err_flag,
+                    cudaStream_t stream) {
+    UCOD_REQUIRE(images && jobs && out && workspace && err_flag, "roi_crop_resize: null argument");
+    UCOD_REQUIRE(njobs > 0 && out_h > 0 && out_w > 0 && max_crop_h > 0 && n_img > 0, "roi_crop_resize: bad geometry");
+    UCOD_REQUIRE(ws_bytes >= roi_crop_resize_workspace_bytes(njobs, max_crop_h, out_h, out_w),
+                 "roi_crop_resize: workspace too small");
+    const int cap = out_h > out_w ? out_h : out_w;
+    uint8_t* p = static_cast<uint8_t*>(workspace);
+    int2* bounds = reinterpret_cast<int2*>(p);
+    p += align256((size_t)njobs * 2 * cap * sizeof(int2));
+    int* coef = reinterpret_cast<int*>(p);
+    p += align256((size_t)njobs * 2 * cap * RS_KMAX * 4);
+    uint8_t* tmp = p;
+    p += align256((size_t)njobs * 3 * max_crop_h * out_w);
+    int* sizes = reinterpret_cast<int*>(p);  // [njobs,2] in (w,h) then [njobs,2] out (w,h)
+
+    // in/out size tables from the job list (device-side, no host round trip)
+    fill_crop_sizes_kernel<<<ceil_div(njobs, 128), 128, 0, stream>>>(jobs, sizes, njobs, out_w, out_h);
+    {
+        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * 2 * cap * RS_KMAX * 4);
+        dim3 g(ceil_div(cap, 128), 2, njobs);
+        resample_coeffs_kernel<<<g, 128, 0, stream>>>(sizes, sizes + njobs * 2, njobs, cap, 0, bounds, coef, err_flag);
+    }
+    {
+        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * 3 * max_crop_h * (out_w + W0));
+        dim3 g(ceil_div(out_w, 128), 3 * max_crop_h, njobs);
+        crop_hpass_kernel<<<g, 128, 0, stream>>>(images, H0, W0, img_stride, ch_stride, row_stride, px_stride, jobs,
+                                                 bounds, coef, tmp, cap, out_w, out_h, max_crop_h);
+    }
+    {
+        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * 3 * out_h * out_w * 3);
+        dim3 g(ceil_div(out_w, 128), 3 * out_h, njobs);
+        crop_vpass_kernel<<<g, 128, 0, stream>>>(tmp, jobs, bounds, coef, out, cap, out_w, out_h, max_crop_h);
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+size_t paste_bicubic_workspace_bytes(int njobs, int g_h, int out_cap) {
+    return align256((size_t)njobs * 2 * out_cap * sizeof(int2)) + align256((size_t)njobs * 2 * out_cap * RS_KMAX * 4) +
+           align256((size_t)njobs * g_h * out_cap) + align256((size_t)njobs * 4 * 4) + 1024;
+}
+
+int paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const int* jobs, int max_rank, uint8_t* mask,
+                  int n_img, int S_h, int S_w, int out_cap, void* workspace, size_t ws_bytes, int* err_flag,
+                  cudaStream_t stream) {
+    UCOD_REQUIRE(logits && jobs && mask && workspace && err_flag, "paste_bicubic: null argument");
+    UCOD_REQUIRE(njobs > 0 && g_h > 0 && g_w > 0 && out_cap > 0 && max_rank >= 0, "paste_bicubic: bad geometry");
+    UCOD_REQUIRE(ws_bytes >= paste_bicubic_workspace_bytes(njobs, g_h, out_cap), "paste_bicubic: workspace too small");
+    uint8_t* p = static_cast<uint8_t*>(workspace);
+    int2* bounds = reinterpret_cast<int2*>(p);
+    p += align256((size_t)njobs * 2 * out_cap * sizeof(int2));
+    int* coef = reinterpret_cast<int*>(p);
+    p += align256((size_t)njobs * 2 * out_cap * RS_KMAX * 4);
+    uint8_t* tmp = p;
+    p += align256((size_t)njobs * g_h * out_cap);
+    int* sizes = reinterpret_cast<int*>(p);
+    fill_paste_sizes_kernel<<<ceil_div(njobs, 128), 128, 0, stream>>>(jobs, sizes, njobs, g_w, g_h);
+    {
+        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * 2 * out_cap * RS_KMAX * 4);
+        dim3 g(ceil_div(out_cap, 128), 2, njobs);
+        resample_coeffs_kernel<<<g, 128, 0, stream>>>(sizes, sizes + njobs * 2, njobs, out_cap, 1, bounds, coef,
+                                                      err_flag);
+    }
+    {
+        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * g_h * (out_cap + g_w * 4));
+        dim3 g(ceil_div(out_cap, 128), g_h, njobs);
+        paste_hpass_kernel<<<g, 128, 0, stream>>>(logits, g_h, g_w, jobs, bounds, coef, tmp, out_cap);
+    }
+    for (int r = 0; r <= max_rank; ++r) {
+        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * out_cap * out_cap / (max_rank + 1));
+        dim3 g(ceil_div(out_cap, 128), out_cap, njobs);
+        paste_vpass_kernel<<<g, 128, 0, stream>>>(tmp, g_h, jobs, bounds, coef, mask, S_h, S_w, out_cap, r);
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    (void)n_img;
+    return 0;
+}
+
+int mask_scale_u8(const uint8_t* in, uint8_t* out, size_t n, int mul, cudaStream_t stream) {
+    UCOD_REQUIRE(in && out, "mask_scale_u8: null argument");
+    if (n == 0) return 0;
+    ProfScope ps(KC_RESAMPLE, stream, (double)n * 2);
+    mask_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(in, out, n, mul);
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ucod

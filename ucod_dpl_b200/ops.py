@@ -115,3 +115,92 @@ def refine_small_components(mask_u8: torch.Tensor, area_threshold: int = 4) -> t
     with torch.cuda.device(m.device):
         _lib.call("ucod_refine_small_components", ptr(m), ptr(out), B, h, w, int(area_threshold), stream_ptr(m.device))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+LT_MAX_BOXES = 128
+
+
+def lt_boxes(mask_u8: torch.Tensor, look_twice_th: float, expand_type: str = "dynamic", const_scale: float = 1.3,
+             want_labels: bool = False):
+    """mask uint8 [B,H,W] -> (boxes int32 [B,128,4], nbox int32 [B], status int32 [B], labels int32 [B,H,W] | None)."""
+    _lib.require_cuda(mask_u8)
+    m = mask_u8.to(torch.uint8).contiguous()
+    B, H, W = m.shape
+    dev = m.device
+    boxes = torch.zeros(B, LT_MAX_BOXES, 4, device=dev, dtype=torch.int32)
+    nbox = torch.empty(B, device=dev, dtype=torch.int32)
+    status = torch.empty(B, device=dev, dtype=torch.int32)
+    labels = torch.empty(B, H, W, device=dev, dtype=torch.int32) if want_labels else None
+    lib = _lib.load()
+    lib.ucod_lt_boxes_workspace_bytes.restype = _u64
+    ws = _ws(lib.ucod_lt_boxes_workspace_bytes(B, H, W), dev)
+    wp, wn = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_lt_boxes", ptr(m), B, H, W, ctypes.c_double(look_twice_th),
+                  1 if expand_type == "dynamic" else 0, ctypes.c_double(const_scale), ptr(boxes), ptr(nbox),
+                  ptr(status), ptr(labels), wp, wn, stream_ptr(dev))
+    return boxes, nbox, status, labels
+
+
+def roi_crop_resize(images_u8: torch.Tensor, jobs: torch.Tensor, out_size, layout: str = "CHW") -> torch.Tensor:
+    """images uint8 [N,3,H0,W0] (layout 'CHW') or [N,H0,W0,3] ('HWC'); jobs int32 [n,5] (img,x,y,w,h) on the same
+    device -> uint8 [n,3,out_h,out_w] = PIL crop + antialiased bilinear Resize."""
+    _lib.require_cuda(images_u8, jobs)
+    if images_u8.dtype != torch.uint8:
+        raise UcodError("roi_crop_resize expects uint8 images")
+    if layout == "CHW":
+        N, _, H0, W0 = images_u8.shape
+        s_img, s_ch, s_row, s_px = images_u8.stride()
+    else:
+        N, H0, W0, _ = images_u8.shape
+        s_img, s_row, s_px, s_ch = images_u8.stride()
+    jobs = jobs.to(torch.int32).contiguous()
+    n = jobs.shape[0]
+    oh, ow = out_size
+    dev = images_u8.device
+    out = torch.empty(n, 3, oh, ow, device=dev, dtype=torch.uint8)
+    if n == 0:
+        return out
+    max_h = max(int(jobs[:, 4].max().item()), 1)
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    lib = _lib.load()
+    lib.ucod_roi_crop_resize_workspace_bytes.restype = _u64
+    ws = _ws(lib.ucod_roi_crop_resize_workspace_bytes(n, max_h, oh, ow), dev)
+    wp, wn = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_roi_crop_resize", ptr(images_u8), N, H0, W0, _i64(s_img), _i64(s_ch), _i64(s_row), _i64(s_px),
+                  ptr(jobs), n, max_h, ptr(out), oh, ow, wp, wn, ptr(err), stream_ptr(dev))
+    return out
+
+
+def paste_bicubic(logits: torch.Tensor, jobs: torch.Tensor, mask_u8: torch.Tensor) -> None:
+    """logits fp32 [n,g,g]; jobs int32 [n,6] (img,x,y,w,h,rank); mask uint8 [N,S,S] with values 0..255, updated
+    in place (binarise -> PIL bicubic resize -> paste, rank order per image)."""
+    _lib.require_cuda(logits, jobs, mask_u8)
+    logits = logits.float().contiguous()
+    jobs = jobs.to(torch.int32).contiguous()
+    n, gh, gw = logits.shape
+    if n == 0:
+        return
+    N, Sh, Sw = mask_u8.shape
+    cap = max(int(jobs[:, 3:5].max().item()), 1)
+    max_rank = int(jobs[:, 5].max().item())
+    dev = logits.device
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    lib = _lib.load()
+    lib.ucod_paste_bicubic_workspace_bytes.restype = _u64
+    ws = _ws(lib.ucod_paste_bicubic_workspace_bytes(n, gh, cap), dev)
+    wp, wn = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_paste_bicubic", ptr(logits), n, gh, gw, ptr(jobs), max_rank, ptr(mask_u8), N, Sh, Sw, cap, wp,
+                  wn, ptr(err), stream_ptr(dev))
+
+
+def mask_scale_u8(mask_u8: torch.Tensor, mul: int = 255) -> torch.Tensor:
+    _lib.require_cuda(mask_u8)
+    m = mask_u8.contiguous()
+    out = torch.empty_like(m)
+    with torch.cuda.device(m.device):
+        _lib.call("ucod_mask_scale_u8", ptr(m), ptr(out), _u64(m.numel()), int(mul), stream_ptr(m.device))
+    return out
