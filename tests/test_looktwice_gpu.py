@@ -37,7 +37,7 @@ def test_boxes_bit_exact(S, th):
     logits = [blob_logits(int(rng.integers(0, 6)), seed=t, size=(0.03, 0.2) if t % 2 else (0.02, 0.08))
               for t in range(24)]
     logits.append(blob_logits(0, seed=99))                          # empty mask -> hard-coded default box
-    logits.append(blob_logits(1, seed=98, size=(0.45, 0.5)))        # one huge component -> None
+    logits.append(torch.full((1, 1, 68, 68), 4.0))                   # one image-filling component -> None
     lg = torch.cat(logits, 0)
     mask = ops.upsample_bilinear(lg[:, 0].cuda(), (S, S), binarize=True)
     boxes, nbox, status, _ = ops.lt_boxes(mask, th, "dynamic")
