@@ -170,6 +170,29 @@ int ucod_paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const i
 /* out[i] = in[i] ? mul : 0  ({0,1} mask -> {0,255} canvas, loop_UCOD_DPL.py:330). */
 int ucod_mask_scale_u8(const uint8_t* in, uint8_t* out, uint64_t n, int mul, void* stream);
 
+/* ---- APM: discriminator + pseudo-label fusion -----------------------------------------------------
+ * `Discriminator.forward` (models/discriminator.py:86-95, dis_use_features = False): mask fp32 [batch,1,fs,fs]
+ * -> prob fp32 [batch].  Weight pointers follow the reference state_dict: maskConv.layers.{0,1}, convs.{0,1}.layers.{0,1},
+ * linear.  bn_train != 0: BatchNorm uses batch statistics (the reference never calls .eval() on it) and, if
+ * update_running != 0, also updates running_mean/var (momentum 0.1, unbiased variance) like nn.BatchNorm2d. */
+typedef struct ucod_disc_weights {
+    const float* conv1; const float* bn1_w; const float* bn1_b; float* bn1_mean; float* bn1_var;
+    const float* conv2; const float* bn2_w; const float* bn2_b; float* bn2_mean; float* bn2_var;
+    const float* conv3; const float* bn3_w; const float* bn3_b; float* bn3_mean; float* bn3_var;
+    const float* lin_w; const float* lin_b;
+} ucod_disc_weights;
+uint64_t ucod_discriminator_workspace_bytes(int batch, int fs);
+int ucod_discriminator_fwd(const float* mask, int batch, int fs, const ucod_disc_weights* w, int bn_train,
+                           int update_running, float* prob, void* workspace, uint64_t workspace_bytes, void* stream);
+/* `TrainLoop.merge_pseudo_label` (engine/runner/loop_UCOD_DPL.py:257-272), split around the two discriminator calls:
+ * binarize: s_mask = sigmoid(student) > 0.5, t_mask = sigmoid(teacher) > 0.5, p_mask = pl > 0.5 (fp32 {0,1}, n elements)
+ * merge:    w_b = clamp(0.5*(1+cos(pi*|p_s-p_p|)) + epoch_term, 0, 1); merged = pl*(1-w_b) + t_mask*w_b;
+ *           weight[b] = w_b; dis_loss (optional device scalar) = BCE(p_s, 0). */
+int ucod_apm_binarize(const float* student, const float* teacher, const float* pl, float* s_mask, float* t_mask,
+                      float* p_mask, uint64_t n, void* stream);
+int ucod_apm_merge(const float* pl, const float* t_mask, const float* p_s, const float* p_p, float epoch_term,
+                   float* merged, float* weight, float* dis_loss, int batch, int pixels, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
 #include "prof.cuh"
 #include "pseudo_label.cuh"
 #include "looktwice.cuh"
+#include "discriminator.cuh"
 
 using namespace ucod;
 
@@ -126,6 +127,28 @@ int ucod_paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const i
 }
 int ucod_mask_scale_u8(const uint8_t* in, uint8_t* out, uint64_t n, int mul, void* stream) {
     return mask_scale_u8(in, out, (size_t)n, mul, reinterpret_cast<cudaStream_t>(stream));
+}
+
+uint64_t ucod_discriminator_workspace_bytes(int batch, int fs) {
+    return (uint64_t)discriminator_workspace_bytes(batch, fs);
+}
+int ucod_discriminator_fwd(const float* mask, int batch, int fs, const ucod_disc_weights* w, int bn_train,
+                           int update_running, float* prob, void* workspace, uint64_t workspace_bytes, void* stream) {
+    UCOD_REQUIRE(w != nullptr, "ucod_discriminator_fwd: null weights");
+    DiscWeights d{w->conv1, w->bn1_w, w->bn1_b, w->bn1_mean, w->bn1_var, w->conv2, w->bn2_w, w->bn2_b, w->bn2_mean,
+                  w->bn2_var, w->conv3, w->bn3_w, w->bn3_b, w->bn3_mean, w->bn3_var, w->lin_w, w->lin_b};
+    return discriminator_forward(mask, batch, fs, d, bn_train, update_running, prob, workspace,
+                                 (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_apm_binarize(const float* student, const float* teacher, const float* pl, float* s_mask, float* t_mask,
+                      float* p_mask, uint64_t n, void* stream) {
+    return apm_binarize(student, teacher, pl, s_mask, t_mask, p_mask, (size_t)n,
+                        reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_apm_merge(const float* pl, const float* t_mask, const float* p_s, const float* p_p, float epoch_term,
+                   float* merged, float* weight, float* dis_loss, int batch, int pixels, void* stream) {
+    return apm_merge(pl, t_mask, p_s, p_p, epoch_term, merged, weight, dis_loss, batch, pixels,
+                     reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

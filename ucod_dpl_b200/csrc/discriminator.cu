@@ -1,0 +1,260 @@
+// APM scorer (`Discriminator`, models/discriminator.py:73-95, dis_use_features=False) and the Adaptive
+// Pseudo-label Module fusion (`TrainLoop.merge_pseudo_label`, engine/runner/loop_UCOD_DPL.py:257-272).
+//
+// Discriminator: mask [B,1,fs,fs] -> conv3x3(1->32)+BN+LReLU(0.1) -> conv3x3 s2 (32->16)+BN+LReLU ->
+// conv3x3 s2 (16->8)+BN+LReLU -> Linear(8*((fs+3)/4)^2 -> 1) -> sigmoid.  The reference never puts the
+// discriminator in eval mode, so BatchNorm normally runs with BATCH statistics (and updates its running
+// buffers): each conv kernel writes raw outputs + per-channel sum / sum-of-squares, and the NEXT kernel
+// normalises on load.  8 473 parameters: everything but the activations lives in shared memory / L2.
+#include "discriminator.cuh"
+
+#include "prof.cuh"
+
+namespace ucod {
+
+namespace {
+
+constexpr float LRELU = 0.1f;
+
+struct BnParams {
+    const float* gamma;
+    const float* beta;
+    float* running_mean;
+    float* running_var;
+};
+
+// scale/shift for channel c from either batch sums (train) or running buffers (eval)
+__device__ __forceinline__ void bn_affine(int c, const double* sums, double count, const BnParams& bn, int train,
+                                          float eps, float& scale, float& shift) {
+    float mean, var;
+    if (train) {
+        const double m = sums[2 * c] / count;
+        double v = sums[2 * c + 1] / count - m * m;
+        if (v < 0) v = 0;
+        mean = (float)m, var = (float)v;
+    } else {
+        mean = bn.running_mean[c], var = bn.running_var[c];
+    }
+    const float inv = rsqrtf(var + eps);
+    scale = bn.gamma[c] * inv;
+    shift = bn.beta[c] - mean * scale;
+}
+
+__device__ __forceinline__ void bn_update_running(int c, const double* sums, double count, const BnParams& bn,
+                                                  float momentum) {
+    const double m = sums[2 * c] / count;
+    double v = sums[2 * c + 1] / count - m * m;
+    if (v < 0) v = 0;
+    const double unbiased = count > 1 ? v * count / (count - 1) : v;
+    bn.running_mean[c] = (1.f - momentum) * bn.running_mean[c] + momentum * (float)m;
+    bn.running_var[c] = (1.f - momentum) * bn.running_var[c] + momentum * (float)unbiased;
+}
+
+// Direct 3x3 convolution, pad 1, stride STRIDE, no bias.  One thread = one output pixel, all COUT channels.
+// IN_BN: input is the previous layer's RAW conv output; BatchNorm + LeakyReLU are applied on load.
+template <int CIN, int COUT, int STRIDE, bool IN_BN>
+__global__ void __launch_bounds__(128)
+    disc_conv_kernel(const float* __restrict__ in, const float* __restrict__ weight /*[COUT,CIN,3,3]*/,
+                     float* __restrict__ out, double* __restrict__ out_sums /*[COUT,2]*/,
+                     const double* __restrict__ in_sums, BnParams in_bn, int bn_train, int update_running,
+                     float eps, float momentum, int B, int Hin, int Win, int Hout, int Wout) {
+    __shared__ float s_w[COUT * CIN * 9];
+    __shared__ float s_scale[CIN], s_shift[CIN];
+    __shared__ float s_red[COUT * 2];
+    for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) s_w[i] = weight[i];
+    if (IN_BN) {
+        const double count = (double)B * Hin * Win;
+        for (int c = threadIdx.x; c < CIN; c += blockDim.x) {
+            bn_affine(c, in_sums, count, in_bn, bn_train, eps, s_scale[c], s_shift[c]);
+            if (bn_train && update_running && blockIdx.x == 0 && blockIdx.y == 0)
+                bn_update_running(c, in_sums, count, in_bn, momentum);
+        }
+    }
+    for (int i = threadIdx.x; i < COUT * 2; i += blockDim.x) s_red[i] = 0.f;
+    __syncthreads();
+
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = pix < Hout * Wout;
+    float acc[COUT];
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    if (active) {
+        const int oy = pix / Wout, ox = pix - oy * Wout;
+        const float* img = in + (size_t)b * CIN * Hin * Win;
+        for (int c = 0; c < CIN; ++c) {
+            float v[9];
+#pragma unroll
+            for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                for (int kx = 0; kx < 3; ++kx) {
+                    const int iy = oy * STRIDE + ky - 1, ix = ox * STRIDE + kx - 1;
+                    float t = 0.f;  // zero padding applies AFTER BN + LeakyReLU of the previous block
+                    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
+                        t = img[((size_t)c * Hin + iy) * Win + ix];
+                        if (IN_BN) {
+                            t = t * s_scale[c] + s_shift[c];
+                            t = t > 0.f ? t : LRELU * t;
+                        }
+                    }
+                    v[ky * 3 + kx] = t;
+                }
+#pragma unroll
+            for (int o = 0; o < COUT; ++o) {
+                const float* w = s_w + (o * CIN + c) * 9;
+                float a = acc[o];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) a += v[k] * w[k];
+                acc[o] = a;
+            }
+        }
+        float* dst = out + (size_t)b * COUT * Hout * Wout + pix;
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) dst[(size_t)o * Hout * Wout] = acc[o];
+    }
+    // per-channel sum / sum of squares of the raw outputs (for the next BatchNorm)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o) {
+        float s = active ? acc[o] : 0.f, q = s * s;
+        s = warp_sum(s);
+        q = warp_sum(q);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(&s_red[2 * o], s);
+            atomicAdd(&s_red[2 * o + 1], q);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < COUT * 2; i += blockDim.x) atomicAdd(&out_sums[i], (double)s_red[i]);
+}
+
+// BN3 + LeakyReLU + flatten + Linear + sigmoid: one CTA per image
+template <int C>
+__global__ void __launch_bounds__(256)
+    disc_head_kernel(const float* __restrict__ in /*[B,C,H,W] raw*/, const double* __restrict__ in_sums, BnParams bn,
+                     int bn_train, int update_running, float eps, float momentum,
+                     const float* __restrict__ lin_w /*[C*H*W]*/, const float* __restrict__ lin_b,
+                     float* __restrict__ prob /*[B]*/, int B, int H, int W) {
+    __shared__ float s_scale[C], s_shift[C];
+    __shared__ float red[8];
+    const double count = (double)B * H * W;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        bn_affine(c, in_sums, count, bn, bn_train, eps, s_scale[c], s_shift[c]);
+        if (bn_train && update_running && blockIdx.x == 0) bn_update_running(c, in_sums, count, bn, momentum);
+    }
+    __syncthreads();
+    const int b = blockIdx.x;
+    const int n = C * H * W, hw = H * W;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = i / hw;
+        float t = in[(size_t)b * n + i] * s_scale[c] + s_shift[c];
+        t = t > 0.f ? t : LRELU * t;
+        acc += t * lin_w[i];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = lin_b[0];
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+        prob[b] = 1.f / (1.f + expf(-t));
+    }
+}
+
+// APM step 1: hard masks for the discriminator.  student/teacher: sigmoid(x) > 0.5 ; pseudo-label: pl > 0.5
+__global__ void apm_binarize_kernel(const float* __restrict__ student, const float* __restrict__ teacher,
+                                    const float* __restrict__ pl, float* __restrict__ s_mask,
+                                    float* __restrict__ t_mask, float* __restrict__ p_mask, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    s_mask[i] = student[i] > 0x1.8p-24f ? 1.f : 0.f;
+    t_mask[i] = teacher[i] > 0x1.8p-24f ? 1.f : 0.f;
+    p_mask[i] = pl[i] > 0.5f ? 1.f : 0.f;
+}
+
+// APM step 2: w_b = clamp(0.5*(1+cos(pi*|p_s-p_p|)) + epoch_term, 0, 1); merged = pl*(1-w) + T*w;
+// dis_loss = mean_b BCE(p_s, 0) = mean_b -max(log(1-p_s), -100)   (torch BCELoss clamps log at -100)
+__global__ void apm_merge_kernel(const float* __restrict__ pl, const float* __restrict__ t_mask,
+                                 const float* __restrict__ p_s, const float* __restrict__ p_p, float epoch_term,
+                                 float* __restrict__ merged, float* __restrict__ weight, float* __restrict__ dis_loss,
+                                 int B, int npix) {
+    const int b = blockIdx.y;
+    const float d = fabsf(p_s[b] - p_p[b]);
+    float w = 0.5f * (1.f + cosf(d * 3.14159265358979323846f)) + epoch_term;
+    w = fminf(fmaxf(w, 0.f), 1.f);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < npix) {
+        const size_t o = (size_t)b * npix + i;
+        merged[o] = pl[o] * (1.f - w) + t_mask[o] * w;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        weight[b] = w;
+        if (b == 0 && dis_loss != nullptr) {
+            float acc = 0.f;
+            for (int k = 0; k < B; ++k) acc += -fmaxf(logf(1.f - p_s[k]), -100.f);
+            dis_loss[0] = acc / (float)B;
+        }
+    }
+}
+
+}  // namespace
+
+size_t discriminator_workspace_bytes(int B, int fs) {
+    const int h2 = (fs + 1) / 2, h3 = (h2 + 1) / 2;
+    return ((size_t)B * 32 * fs * fs + (size_t)B * 16 * h2 * h2 + (size_t)B * 8 * h3 * h3) * 4 + (32 + 16 + 8) * 2 * 8 +
+           1024;
+}
+
+int discriminator_forward(const float* mask, int B, int fs, const DiscWeights& w, int bn_train, int update_running,
+                          float* prob, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    UCOD_REQUIRE(mask && prob && workspace, "discriminator_forward: null argument");
+    UCOD_REQUIRE(B > 0 && fs > 0, "discriminator_forward: bad geometry");
+    UCOD_REQUIRE(ws_bytes >= discriminator_workspace_bytes(B, fs), "discriminator_forward: workspace too small");
+    const int h1 = fs, h2 = (fs + 2 - 3) / 2 + 1, h3 = (h2 + 2 - 3) / 2 + 1;
+    uint8_t* p = static_cast<uint8_t*>(workspace);
+    double* sums = reinterpret_cast<double*>(p);  // [32+16+8][2]
+    p += (32 + 16 + 8) * 2 * 8;
+    float* a1 = reinterpret_cast<float*>(p);
+    p += (size_t)B * 32 * h1 * h1 * 4;
+    float* a2 = reinterpret_cast<float*>(p);
+    p += (size_t)B * 16 * h2 * h2 * 4;
+    float* a3 = reinterpret_cast<float*>(p);
+    double *s1 = sums, *s2 = sums + 64, *s3 = sums + 96;
+    UCOD_CHECK_CUDA(cudaMemsetAsync(sums, 0, (32 + 16 + 8) * 2 * 8, stream));
+    const float eps = 1e-5f, mom = 0.1f;
+    BnParams bn1{w.bn1_w, w.bn1_b, w.bn1_mean, w.bn1_var}, bn2{w.bn2_w, w.bn2_b, w.bn2_mean, w.bn2_var},
+        bn3{w.bn3_w, w.bn3_b, w.bn3_mean, w.bn3_var}, none{nullptr, nullptr, nullptr, nullptr};
+    ProfScope ps(KC_OTHER, stream, (double)B * (32 * h1 * h1 + 16 * h2 * h2 + 8 * h3 * h3) * 8);
+    disc_conv_kernel<1, 32, 1, false><<<dim3(ceil_div(h1 * h1, 128), B), 128, 0, stream>>>(
+        mask, w.conv1, a1, s1, nullptr, none, 0, 0, eps, mom, B, fs, fs, h1, h1);
+    disc_conv_kernel<32, 16, 2, true><<<dim3(ceil_div(h2 * h2, 128), B), 128, 0, stream>>>(
+        a1, w.conv2, a2, s2, s1, bn1, bn_train, update_running, eps, mom, B, h1, h1, h2, h2);
+    disc_conv_kernel<16, 8, 2, true><<<dim3(ceil_div(h3 * h3, 128), B), 128, 0, stream>>>(
+        a2, w.conv3, a3, s3, s2, bn2, bn_train, update_running, eps, mom, B, h2, h2, h3, h3);
+    disc_head_kernel<8><<<B, 256, 0, stream>>>(a3, s3, bn3, bn_train, update_running, eps, mom, w.lin_w, w.lin_b, prob,
+                                               B, h3, h3);
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int apm_binarize(const float* student, const float* teacher, const float* pl, float* s_mask, float* t_mask,
+                 float* p_mask, size_t n, cudaStream_t stream) {
+    UCOD_REQUIRE(student && teacher && pl && s_mask && t_mask && p_mask, "apm_binarize: null argument");
+    ProfScope ps(KC_OTHER, stream, (double)n * 24);
+    apm_binarize_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(student, teacher, pl, s_mask, t_mask, p_mask,
+                                                                        n);
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int apm_merge(const float* pl, const float* t_mask, const float* p_s, const float* p_p, float epoch_term,
+              float* merged, float* weight, float* dis_loss, int B, int npix, cudaStream_t stream) {
+    UCOD_REQUIRE(pl && t_mask && p_s && p_p && merged && weight, "apm_merge: null argument");
+    ProfScope ps(KC_OTHER, stream, (double)B * npix * 12);
+    apm_merge_kernel<<<dim3(ceil_div(npix, 256), B), 256, 0, stream>>>(pl, t_mask, p_s, p_p, epoch_term, merged, weight,
+                                                                      dis_loss, B, npix);
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace ucod

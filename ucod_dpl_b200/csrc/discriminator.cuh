@@ -1,0 +1,29 @@
+// Discriminator forward + APM fusion (see discriminator.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ucod {
+
+struct DiscWeights {
+    const float* conv1;  // [32,1,3,3]
+    const float *bn1_w, *bn1_b;
+    float *bn1_mean, *bn1_var;
+    const float* conv2;  // [16,32,3,3]
+    const float *bn2_w, *bn2_b;
+    float *bn2_mean, *bn2_var;
+    const float* conv3;  // [8,16,3,3]
+    const float *bn3_w, *bn3_b;
+    float *bn3_mean, *bn3_var;
+    const float* lin_w;  // [1, 8*h3*h3]
+    const float* lin_b;  // [1]
+};
+
+size_t discriminator_workspace_bytes(int B, int fs);
+int discriminator_forward(const float* mask, int B, int fs, const DiscWeights& w, int bn_train, int update_running,
+                          float* prob, void* workspace, size_t ws_bytes, cudaStream_t stream);
+int apm_binarize(const float* student, const float* teacher, const float* pl, float* s_mask, float* t_mask,
+                 float* p_mask, size_t n, cudaStream_t stream);
+int apm_merge(const float* pl, const float* t_mask, const float* p_s, const float* p_p, float epoch_term,
+              float* merged, float* weight, float* dis_loss, int B, int npix, cudaStream_t stream);
+
+}  // namespace ucod

@@ -204,3 +204,57 @@ def mask_scale_u8(mask_u8: torch.Tensor, mul: int = 255) -> torch.Tensor:
     with torch.cuda.device(m.device):
         _lib.call("ucod_mask_scale_u8", ptr(m), ptr(out), _u64(m.numel()), int(mul), stream_ptr(m.device))
     return out
+
+
+# ------------------------------------------------------------------------------------------------
+class _DiscW(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "conv1", "bn1_w", "bn1_b", "bn1_mean", "bn1_var", "conv2", "bn2_w", "bn2_b", "bn2_mean", "bn2_var",
+        "conv3", "bn3_w", "bn3_b", "bn3_mean", "bn3_var", "lin_w", "lin_b")]
+
+
+def discriminator_forward(mask: torch.Tensor, tensors: dict, bn_train: bool = True,
+                          update_running: bool = True) -> torch.Tensor:
+    """mask fp32 [B,1,fs,fs]; `tensors`: fp32 CUDA tensors keyed by the _DiscW field names -> prob [B,1]."""
+    _lib.require_cuda(mask)
+    m = mask.float().contiguous()
+    B, _, fs, fs2 = m.shape
+    if fs != fs2:
+        raise UcodError("discriminator_forward expects square masks")
+    dev = m.device
+    w = _DiscW(*[tensors[n].data_ptr() for n, _ in _DiscW._fields_])
+    prob = torch.empty(B, 1, device=dev, dtype=torch.float32)
+    lib = _lib.load()
+    lib.ucod_discriminator_workspace_bytes.restype = _u64
+    ws = _ws(lib.ucod_discriminator_workspace_bytes(B, fs), dev)
+    wp, wn = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_discriminator_fwd", ptr(m), B, fs, ctypes.byref(w), 1 if bn_train else 0,
+                  1 if update_running else 0, ptr(prob), wp, wn, stream_ptr(dev))
+    return prob
+
+
+def apm_binarize(student: torch.Tensor, teacher: torch.Tensor, pl: torch.Tensor):
+    _lib.require_cuda(student, teacher, pl)
+    s, t, p = student.float().contiguous(), teacher.float().contiguous(), pl.float().contiguous()
+    sm, tm, pm = torch.empty_like(s), torch.empty_like(t), torch.empty_like(p)
+    with torch.cuda.device(s.device):
+        _lib.call("ucod_apm_binarize", ptr(s), ptr(t), ptr(p), ptr(sm), ptr(tm), ptr(pm), _u64(s.numel()),
+                  stream_ptr(s.device))
+    return sm, tm, pm
+
+
+def apm_merge(pl: torch.Tensor, t_mask: torch.Tensor, p_s: torch.Tensor, p_p: torch.Tensor, epoch_term: float):
+    """-> (merged like pl, weight [B,1], dis_loss scalar tensor)."""
+    _lib.require_cuda(pl, t_mask, p_s, p_p)
+    pl = pl.float().contiguous()
+    B = pl.shape[0]
+    npix = pl.numel() // B
+    merged = torch.empty_like(pl)
+    weight = torch.empty(B, 1, device=pl.device, dtype=torch.float32)
+    loss = torch.empty((), device=pl.device, dtype=torch.float32)
+    with torch.cuda.device(pl.device):
+        _lib.call("ucod_apm_merge", ptr(pl), ptr(t_mask.contiguous()), ptr(p_s.float().contiguous()),
+                  ptr(p_p.float().contiguous()), c_float(epoch_term), ptr(merged), ptr(weight), ptr(loss), B, npix,
+                  stream_ptr(pl.device))
+    return merged, weight, loss
