@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UCOD_B200_ABI_VERSION 1
+#define UCOD_B200_ABI_VERSION 2
 
 /* Last error message of the calling thread ("" if none). */
 const char* ucod_last_error(void);
@@ -43,13 +43,16 @@ long long ucod_launch_count(void);
 int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n, int k, int epi_mode,
                    const float* bias, const float* scale, void* out, int ld_out, void* stream);
 
-/* Fused softmax(q k^T * scale) v, head_dim 64, non-causal (tcgen05 flash-attention forward).
- * q,k: [batch*heads, tokens, 64] bf16 ; vt: [batch*heads, 64, tokens_pad] bf16 (V transposed, pad columns zero,
- * tokens_pad % 8 == 0) ; ctx: [batch, tokens, heads*64] bf16.
+/* Fused softmax(q k^T * scale) v, non-causal (tcgen05 flash-attention forward), head_dim 64 or 128.
+ * q: [batch, tokens_q, ld_q] bf16 ; k, v: [batch, tokens_kv, ld_kv] bf16 ; head h lives in columns
+ * [h*head_dim, (h+1)*head_dim) of each pointer, so q/k/v may point at the three column blocks of one fused QKV
+ * projection output (nothing is transposed in memory).  ctx: [batch, tokens_q, ld_ctx] bf16, same head layout.
+ * Row pitches are in elements (multiples of 8), pointers 16-byte aligned.
  * Replaces: HF Dinov2SelfAttention/ViTSelfAttention (modeling_dinov2.py:153-235) under
- * data/utils/feature_extractor.py:49-59. */
-int ucod_attention_d64(const void* q, const void* k, const void* vt, void* ctx, int batch, int heads, int tokens,
-                       int tokens_pad, float scale, void* stream);
+ * data/utils/feature_extractor.py:49-59, and nn.MultiheadAttention of models/modules/mlp.py:134-148
+ * (head_dim 96 zero-padded to 128). */
+int ucod_attention(const void* q, int ld_q, const void* k, const void* v, int ld_kv, void* ctx, int ld_ctx, int batch,
+                   int heads, int head_dim, int tokens_q, int tokens_kv, float scale, void* stream);
 
 /* ---- frozen ViT-B backbone: last-layer key tokens ---------------------------------------------
  * Replaces `backbone.__init__/forward` (data/utils/feature_extractor.py:31-59) and the hook + attentions of

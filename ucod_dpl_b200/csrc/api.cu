@@ -36,11 +36,15 @@ int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n,
     return launch_gemm_bf16(a, lda, w, ldw, m, n, k, ep, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int ucod_attention_d64(const void* q, const void* k, const void* vt, void* ctx, int batch, int heads, int tokens,
-                       int tokens_pad, float scale, void* stream) {
-    UCOD_REQUIRE(q && k && vt && ctx, "ucod_attention_d64: null pointer");
-    return launch_attention_d64(q, k, vt, ctx, batch, heads, tokens, tokens_pad, scale,
-                                reinterpret_cast<cudaStream_t>(stream));
+int ucod_attention(const void* q, int ld_q, const void* k, const void* v, int ld_kv, void* ctx, int ld_ctx, int batch,
+                   int heads, int head_dim, int tokens_q, int tokens_kv, float scale, void* stream) {
+    AttentionArgs a;
+    a.q = q, a.k = k, a.v = v, a.ctx = ctx;
+    a.batch = batch, a.heads = heads, a.tokens_q = tokens_q, a.tokens_kv = tokens_kv;
+    a.head_dim = head_dim, a.head_dim_real = head_dim;
+    a.ld_q = ld_q, a.ld_kv = ld_kv, a.ld_ctx = ld_ctx;
+    a.scale = scale;
+    return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int ucod_vit_create(void** handle, const ucod_vit_cfg* cfg, const void* patch_w, const float* patch_b,

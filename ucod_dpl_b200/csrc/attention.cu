@@ -1,19 +1,29 @@
-// Fused multi-head attention forward (non-causal, head_dim 64) on tcgen05 / TMEM.
+// Fused multi-head attention forward (non-causal) on tcgen05 / TMEM, head_dim 64 (ViT-B) or 128 (CORAL CSF,
+// head_dim 96 zero-padded).
 //
-//   ctx[b, t, h*64:(h+1)*64] = softmax_j(q[b,h,t,:] . k[b,h,j,:] * scale) @ v[b,h,j,:]
+//   ctx[b, t, h*D:(h+1)*D] = softmax_j(q[b,t,h,:] . k[b,j,h,:] * scale) @ v[b,j,h,:]
 //
-// One CTA = one (batch*head, 128-query tile).  Warp 0: TMA producer (Q once; K_j and V^T_j double
-// buffered).  Warp 1: single-thread MMA issuer: S = Q K_j^T (128x128x64) into TMEM cols [0,128),
-// O += P_j V_j (128x64x128) into TMEM cols [128,192).  Warps 2..5: one thread per query row —
-// online softmax straight out of TMEM (no cross-thread shuffles), P written as bf16 into a
-// 128B-swizzled smem tile that the second MMA consumes, O rescaled in TMEM only when the row max moved.
-// S_{j+1} is issued before P_j V_j so the tensor pipe works while the softmax warps run; two CTAs fit per SM.
+// Q, K, V are read in place from token-major activations ([batch, tokens, ld] bf16, head h at columns h*D —
+// e.g. the three column blocks of the fused QKV GEMM output) through 3-D TMA maps; nothing is transposed or
+// re-laid-out in HBM.  One CTA = one (batch, head, 128-query tile); two CTAs are resident per SM (D = 64) so one
+// CTA's softmax overlaps the other's MMAs.
 //
-// V is consumed as V^T [bh, 64, Tpad] (written by the QKV GEMM epilogue) so that both MMAs read
-// K-major operands.  Keys >= T in the last tile are masked to -inf (their V^T columns are zero).
+// CTA = 256 threads = two warpgroups:
+//   WG0: warp 0 = TMA producer (Q once; K_j / V_j double buffered, separately released), warp 1 = single-thread
+//        MMA issuer (+ TMEM allocator); registers trimmed with setmaxnreg.dec.
+//   WG1: 4 softmax warps, one thread per query row (= TMEM lane), registers raised with setmaxnreg.inc so the
+//        whole 128-wide S row lives in registers (S is read from TMEM exactly once).
+// TMEM: S fp32 [0,128) | P bf16-packed [128,192) | O fp32 [192,192+D).
+//   S_j  = Q K_j^T                (SS MMA, both operands K-major SW128 tiles)
+//   P_j  = exp2(S_j*c - m_ref)    (written back to TMEM as packed bf16; never touches shared memory)
+//   O   += P_j V_j                (TS MMA: A = P from TMEM, B = V tile consumed MN-major straight from [keys, D])
+// Online softmax with a lazily updated reference maximum: O / l are rescaled only when the row maximum grows by
+// more than 2^8 (exact result after the final O / l normalisation; rescales become rare after the first tiles).
+// S_{j+1} is issued as soon as the softmax warps have pulled S_j into registers, so the tensor pipe computes the
+// next scores while the exponentials of the current tile are evaluated.
 //
-// Replaces: HF Dinov2SelfAttention / ViTSelfAttention eager+sdpa paths (transformers
-// modeling_dinov2.py:153-235) reached from data/utils/feature_extractor.py:49-59.
+// Replaces: HF Dinov2SelfAttention / ViTSelfAttention eager+sdpa paths (transformers modeling_dinov2.py:153-235)
+// reached from data/utils/feature_extractor.py:49-59, and nn.MultiheadAttention in models/modules/mlp.py:134-148.
 #include "attention.cuh"
 #include "prof.cuh"
 
@@ -21,199 +31,260 @@ namespace ucod {
 
 namespace {
 
-constexpr int ATT_BM = 128;   // queries per CTA
-constexpr int ATT_BN = 128;   // keys per tile
-constexpr int ATT_D = 64;     // head dim
-constexpr int SQ_BYTES = ATT_BM * ATT_D * 2;        // 16 KB
-constexpr int SK_BYTES = ATT_BN * ATT_D * 2;        // 16 KB
-constexpr int SV_BYTES = ATT_D * ATT_BN * 2;        // 16 KB (two [64 x 64] K-blocks)
-constexpr int SP_BYTES = ATT_BM * ATT_BN * 2;       // 32 KB (two [128 x 64] K-blocks)
-constexpr int ATT_SMEM = SQ_BYTES + 2 * SK_BYTES + 2 * SV_BYTES + SP_BYTES + 256 + 1024;
-constexpr int ATT_TMEM_COLS = 256;                  // S: [0,128)  O: [128,192)
-constexpr int ATT_THREADS = 192;
+template <int D>
+struct AttCfg {
+    static constexpr int BM = 128;      // queries per CTA
+    static constexpr int BN = 128;      // keys per tile
+    static constexpr int NKB = D / 64;  // 64-column (128-byte) blocks per head
+    static constexpr int BLK_BYTES = 128 * 64 * 2;  // one [128 x 64] bf16 TMA box
+    static constexpr int SQ_BYTES = NKB * BLK_BYTES;
+    static constexpr int SK_BYTES = NKB * BLK_BYTES;
+    static constexpr int SV_BYTES = NKB * BLK_BYTES;
+    static constexpr int STAGES = 2;
+    static constexpr int SMEM = SQ_BYTES + STAGES * (SK_BYTES + SV_BYTES) + 256 + 1024;
+    static constexpr int TM_S = 0, TM_P = 128, TM_O = 192;
+    static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;
+    static constexpr int THREADS = 256;
+    static constexpr int CTAS_PER_SM = (D == 64) ? 2 : 1;
+};
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+// MN-major operand tile, 128-byte swizzle: rows (k index) are 128 B = 64 consecutive MN elements, 8 rows form one
+// 1024 B swizzle atom (SBO), further 64-element MN chunks are `lbo_bytes` apart.
+__device__ __forceinline__ uint64_t umma_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+template <int N>
+__device__ __forceinline__ void reg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N>
+__device__ __forceinline__ void reg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+template <int D>
+__global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                         const __grid_constant__ CUtensorMap tm_vt, __nv_bfloat16* __restrict__ ctx, int T, int H,
-                         float scale_log2e) {
+                         const __grid_constant__ CUtensorMap tm_v, __nv_bfloat16* __restrict__ ctx, int Tq, int Tk,
+                         int H, int ld_ctx, float scale_log2e) {
+    using C = AttCfg<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sQ = smem;
-    uint8_t* sK = sQ + SQ_BYTES;
-    uint8_t* sV = sK + 2 * SK_BYTES;
-    uint8_t* sP = sV + 2 * SV_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sP + SP_BYTES);
-    uint64_t* bar_q = bars;            // 1
-    uint64_t* bar_kv_full = bars + 1;  // 2
-    uint64_t* bar_kv_empty = bars + 3; // 2
-    uint64_t* bar_s = bars + 5;        // S tile ready in TMEM
-    uint64_t* bar_p = bars + 6;        // P tile ready in smem (128 arrivals)
-    uint64_t* bar_pv = bars + 7;       // P V MMA retired
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint8_t* sK = sQ + C::SQ_BYTES;
+    uint8_t* sV = sK + C::STAGES * C::SK_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + C::STAGES * C::SV_BYTES);
+    uint64_t* bar_q = bars;           // Q tile landed
+    uint64_t* bar_kfull = bars + 1;   // [2]
+    uint64_t* bar_kempty = bars + 3;  // [2]
+    uint64_t* bar_vfull = bars + 5;   // [2]
+    uint64_t* bar_vempty = bars + 7;  // [2]
+    uint64_t* bar_s = bars + 9;       // S_j complete in TMEM
+    uint64_t* bar_sfree = bars + 10;  // S_j pulled into registers by all 128 rows
+    uint64_t* bar_p = bars + 11;      // P_j published in TMEM (128 arrivals)
+    uint64_t* bar_pv = bars + 12;     // P_j V_j retired
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int q0 = blockIdx.x * ATT_BM;
-    const int bh = blockIdx.y;
-    const int n_tiles = (T + ATT_BN - 1) / ATT_BN;
+    const int q0 = blockIdx.x * C::BM;
+    const int b = blockIdx.y / H, h = blockIdx.y - b * H;
+    const int col0 = h * D;
+    const int n_tiles = (Tk + C::BN - 1) / C::BN;
 
     if (threadIdx.x == 0) {
         mbar_init(bar_q, 1);
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_kv_full[i], 1);
-            mbar_init(&bar_kv_empty[i], 1);
+            mbar_init(&bar_kfull[i], 1);
+            mbar_init(&bar_kempty[i], 1);
+            mbar_init(&bar_vfull[i], 1);
+            mbar_init(&bar_vempty[i], 1);
         }
         mbar_init(bar_s, 1);
+        mbar_init(bar_sfree, 128);
         mbar_init(bar_p, 128);
         mbar_init(bar_pv, 1);
         fence_mbar_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, ATT_TMEM_COLS);
+        tmem_alloc(tmem_slot, C::TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base;
-    const uint32_t tmem_o = tmem_base + 128;
+    const uint32_t tmem_s = tmem_base + C::TM_S;
+    const uint32_t tmem_p = tmem_base + C::TM_P;
+    const uint32_t tmem_o = tmem_base + C::TM_O;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+    if (warp < 4) {
+        reg_dec<48>();
+        if (warp == 0 && lane == 0) {
+            // ===================== TMA producer =====================
             tma_prefetch_desc(&tm_q);
             tma_prefetch_desc(&tm_k);
-            tma_prefetch_desc(&tm_vt);
-            mbar_arrive_expect_tx(bar_q, SQ_BYTES);
-            tma_load_3d(sQ, &tm_q, bar_q, 0, q0, bh);
+            tma_prefetch_desc(&tm_v);
+            mbar_arrive_expect_tx(bar_q, C::SQ_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < C::NKB; ++kb)
+                tma_load_3d(sQ + kb * C::BLK_BYTES, &tm_q, bar_q, col0 + kb * 64, q0, b);
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j & 1;
-                const uint32_t use = (uint32_t)(j >> 1);
-                mbar_wait(&bar_kv_empty[st], (use & 1) ^ 1);
-                mbar_arrive_expect_tx(&bar_kv_full[st], SK_BYTES + SV_BYTES);
-                tma_load_3d(sK + st * SK_BYTES, &tm_k, &bar_kv_full[st], 0, j * ATT_BN, bh);
-                tma_load_3d(sV + st * SV_BYTES, &tm_vt, &bar_kv_full[st], j * ATT_BN, 0, bh);
-                tma_load_3d(sV + st * SV_BYTES + SV_BYTES / 2, &tm_vt, &bar_kv_full[st], j * ATT_BN + 64, 0, bh);
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc_s = umma_idesc_bf16(ATT_BM, ATT_BN);
-            constexpr uint32_t idesc_o = umma_idesc_bf16(ATT_BM, ATT_D);
-            const uint32_t q_addr = smem_u32(sQ);
-            const uint32_t p_addr = smem_u32(sP);
-            auto issue_s = [&](int j) {
-                const uint32_t k_addr = smem_u32(sK + (j & 1) * SK_BYTES);
+                const uint32_t ph = ((uint32_t)(j >> 1) & 1) ^ 1;
+                mbar_wait(&bar_kempty[st], ph);
+                mbar_arrive_expect_tx(&bar_kfull[st], C::SK_BYTES);
 #pragma unroll
-                for (int k = 0; k < ATT_D / 16; ++k)
-                    umma_bf16_ss(tmem_s, umma_desc_kmajor_sw128(q_addr + k * 32),
-                                 umma_desc_kmajor_sw128(k_addr + k * 32), idesc_s, k != 0);
+                for (int kb = 0; kb < C::NKB; ++kb)
+                    tma_load_3d(sK + st * C::SK_BYTES + kb * C::BLK_BYTES, &tm_k, &bar_kfull[st], col0 + kb * 64,
+                                j * C::BN, b);
+                mbar_wait(&bar_vempty[st], ph);
+                mbar_arrive_expect_tx(&bar_vfull[st], C::SV_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < C::NKB; ++kb)
+                    tma_load_3d(sV + st * C::SV_BYTES + kb * C::BLK_BYTES, &tm_v, &bar_vfull[st], col0 + kb * 64,
+                                j * C::BN, b);
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ===================== MMA issuer =====================
+            constexpr uint32_t idesc_s = umma_idesc_bf16(C::BM, C::BN);
+            constexpr uint32_t idesc_o = umma_idesc_bf16(C::BM, D) | (1u << 16);  // B operand MN-major
+            const uint32_t q_addr = smem_u32(sQ);
+            auto issue_s = [&](int j) {
+                const uint32_t k_addr = smem_u32(sK + (j & 1) * C::SK_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < C::NKB; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16_ss(tmem_s, umma_desc_kmajor_sw128(q_addr + kb * C::BLK_BYTES + k * 32),
+                                     umma_desc_kmajor_sw128(k_addr + kb * C::BLK_BYTES + k * 32), idesc_s,
+                                     (kb | k) != 0);
+                umma_commit(&bar_kempty[j & 1]);
                 umma_commit(bar_s);
             };
             mbar_wait(bar_q, 0);
-            mbar_wait(&bar_kv_full[0], 0);
+            mbar_wait(&bar_kfull[0], 0);
             tc_fence_after();
             issue_s(0);
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j & 1;
-                mbar_wait(bar_p, j & 1);  // softmax has consumed S_j and published P_j
-                tc_fence_after();
                 if (j + 1 < n_tiles) {
-                    mbar_wait(&bar_kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    mbar_wait(&bar_kfull[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    mbar_wait(bar_sfree, j & 1);  // S_j is in the softmax warps' registers
                     tc_fence_after();
                     issue_s(j + 1);
                 }
-                const uint32_t v_addr = smem_u32(sV + st * SV_BYTES);
+                mbar_wait(&bar_vfull[st], (j >> 1) & 1);
+                mbar_wait(bar_p, j & 1);  // P_j published
+                tc_fence_after();
+                const uint32_t v_addr = smem_u32(sV + st * C::SV_BYTES);
 #pragma unroll
-                for (int kb = 0; kb < 2; ++kb) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        umma_bf16_ss(tmem_o, umma_desc_kmajor_sw128(p_addr + kb * (SP_BYTES / 2) + k * 32),
-                                     umma_desc_kmajor_sw128(v_addr + kb * (SV_BYTES / 2) + k * 32), idesc_o,
-                                     (j | kb | k) != 0);
-                }
-                umma_commit(&bar_kv_empty[st]);
+                for (int k = 0; k < C::BN / 16; ++k)
+                    umma_bf16_ts(tmem_o, tmem_p + k * 8, umma_desc_mnmajor_sw128(v_addr + k * 2048, C::BLK_BYTES),
+                                 idesc_o, (j | k) != 0);
+                umma_commit(&bar_vempty[st]);
                 umma_commit(bar_pv);
             }
         }
     } else {
         // ===================== softmax / correction / epilogue: one thread per query row ==============
+        reg_inc<208>();
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        uint8_t* p_row = sP + (r >> 3) * 1024 + (r & 7) * 128;
-        const int rx = r & 7;
-        float m_run = -INFINITY, l_run = 0.f;
+        float m_ref = 0.f, l_run = 0.f;
 
         for (int j = 0; j < n_tiles; ++j) {
             mbar_wait(bar_s, j & 1);
             tc_fence_after();
-            const int valid = T - j * ATT_BN;  // keys valid in this tile (>= 1)
-            // ---- pass 1: row max ----
-            float m_tile = -INFINITY;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t u[32];
-                tmem_ld32(tmem_s + lane_off + c * 32, u);
-                tmem_wait_ld();
+            uint32_t u[128];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float s = (c * 32 + i < valid) ? __uint_as_float(u[i]) : -INFINITY;
-                    m_tile = fmaxf(m_tile, s);
-                }
+            for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + lane_off + c * 32, reinterpret_cast<uint32_t(&)[32]>(u[32 * c]));
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_sfree);
+            const int valid = Tk - j * C::BN;  // keys valid in this tile (>= 1)
+            if (valid < C::BN) {
+#pragma unroll
+                for (int i = 0; i < 128; ++i)
+                    if (i >= valid) u[i] = 0xff800000u;  // -inf
             }
-            const float m_new = fmaxf(m_run, m_tile);
-            const float alpha = exp2f((m_run - m_new) * scale_log2e);  // 0 when m_run = -inf
-            const float m_scaled = m_new * scale_log2e;
-
-            // previous P V must have retired before P is overwritten / O is rescaled
-            if (j > 0) {
+            // ---- row maximum (4 independent chains) ----
+            float mx[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                mx[c] = __uint_as_float(u[32 * c]);
+#pragma unroll
+                for (int i = 1; i < 32; i += 2)
+                    mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(u[32 * c + i]),
+                                               __uint_as_float(u[32 * c + (i + 1 < 32 ? i + 1 : i)])));
+            }
+            const float ms = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2e;
+            float alpha = 1.f;
+            bool grow = false;
+            if (j == 0) {
+                m_ref = ms;
+            } else {
+                if (ms > m_ref + 8.f) {
+                    alpha = ex2_approx(m_ref - ms);
+                    m_ref = ms;
+                    grow = true;
+                }
+                // previous P V must have retired before P is overwritten / O is rescaled
                 mbar_wait(bar_pv, (j - 1) & 1);
                 tc_fence_after();
-                if (__any_sync(0xffffffffu, m_new > m_run)) {
+                if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t u[32];
-                        tmem_ld32(tmem_o + lane_off + c * 32, u);
+                    for (int c = 0; c < D / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_o + lane_off + c * 32, o);
                         tmem_wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) u[i] = __float_as_uint(__uint_as_float(u[i]) * alpha);
-                        tmem_st32(tmem_o + lane_off + c * 32, u);
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tmem_o + lane_off + c * 32, o);
                     }
-                    tmem_wait_st();
+                    l_run *= alpha;
                 }
             }
-            // ---- pass 2: probabilities -> bf16 -> swizzled smem ----
-            float l_tile = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t u[32];
-                tmem_ld32(tmem_s + lane_off + c * 32, u);
-                tmem_wait_ld();
-                float p[32];
+            // ---- probabilities -> packed bf16 -> TMEM ----
+            const float neg_m = -m_ref;
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t pk[32];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    const float s = __uint_as_float(u[i]);
-                    const float e = exp2f(fmaf(s, scale_log2e, -m_scaled));
-                    p[i] = (c * 32 + i < valid) ? e : 0.f;
-                    l_tile += p[i];
+                    const float p0 = ex2_approx(fmaf(__uint_as_float(u[64 * half + 2 * i]), scale_log2e, neg_m));
+                    const float p1 = ex2_approx(fmaf(__uint_as_float(u[64 * half + 2 * i + 1]), scale_log2e, neg_m));
+                    ls[i & 3] += p0 + p1;
+                    pk[i] = pack_bf16x2(p0, p1);
                 }
-                uint8_t* dst = p_row + (c >> 1) * (SP_BYTES / 2);
-#pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int ci = (c & 1) * 4 + g;  // 16-byte chunk index inside the 128-byte row
-                    uint4 t;
-                    t.x = pack_bf16x2(p[8 * g + 0], p[8 * g + 1]);
-                    t.y = pack_bf16x2(p[8 * g + 2], p[8 * g + 3]);
-                    t.z = pack_bf16x2(p[8 * g + 4], p[8 * g + 5]);
-                    t.w = pack_bf16x2(p[8 * g + 6], p[8 * g + 7]);
-                    *reinterpret_cast<uint4*>(dst + ((ci ^ rx) << 4)) = t;
-                }
+                tmem_st32(tmem_p + lane_off + half * 32, pk);
             }
-            l_run = l_run * alpha + l_tile;
-            m_run = m_new;
-            fence_proxy_async_smem();
+            l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar_p);
         }
@@ -223,21 +294,20 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
         tc_fence_after();
         const float inv_l = 1.0f / l_run;
         const int t = q0 + r;
-        const int b = bh / H, h = bh - b * H;
-        __nv_bfloat16* out = ctx + ((size_t)b * T + t) * (size_t)(H * ATT_D) + h * ATT_D;
+        __nv_bfloat16* out = ctx + ((size_t)b * Tq + t) * (size_t)ld_ctx + h * D;
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-            uint32_t u[32];
-            tmem_ld32(tmem_o + lane_off + c * 32, u);
+        for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_o + lane_off + c * 32, o);
             tmem_wait_ld();
-            if (t < T) {
+            if (t < Tq) {
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {
                     uint4 v;
-                    v.x = pack_bf16x2(__uint_as_float(u[8 * g + 0]) * inv_l, __uint_as_float(u[8 * g + 1]) * inv_l);
-                    v.y = pack_bf16x2(__uint_as_float(u[8 * g + 2]) * inv_l, __uint_as_float(u[8 * g + 3]) * inv_l);
-                    v.z = pack_bf16x2(__uint_as_float(u[8 * g + 4]) * inv_l, __uint_as_float(u[8 * g + 5]) * inv_l);
-                    v.w = pack_bf16x2(__uint_as_float(u[8 * g + 6]) * inv_l, __uint_as_float(u[8 * g + 7]) * inv_l);
+                    v.x = pack_bf16x2(__uint_as_float(o[8 * g + 0]) * inv_l, __uint_as_float(o[8 * g + 1]) * inv_l);
+                    v.y = pack_bf16x2(__uint_as_float(o[8 * g + 2]) * inv_l, __uint_as_float(o[8 * g + 3]) * inv_l);
+                    v.z = pack_bf16x2(__uint_as_float(o[8 * g + 4]) * inv_l, __uint_as_float(o[8 * g + 5]) * inv_l);
+                    v.w = pack_bf16x2(__uint_as_float(o[8 * g + 6]) * inv_l, __uint_as_float(o[8 * g + 7]) * inv_l);
                     reinterpret_cast<uint4*>(out + c * 32)[g] = v;
                 }
             }
@@ -246,35 +316,52 @@ __global__ void __launch_bounds__(ATT_THREADS, 2)
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, ATT_TMEM_COLS);
+    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+template <int D>
+int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
+    using C = AttCfg<D>;
+    CUtensorMap tq, tk, tv;
+    const uint64_t cols = (uint64_t)a.heads * D;
+    if (int rc = make_tmap_3d_bf16(&tq, a.q, (uint64_t)a.batch, (uint64_t)a.tokens_q, cols, (uint64_t)a.ld_q,
+                                   (uint64_t)a.tokens_q * a.ld_q, C::BM, 64))
+        return rc;
+    if (int rc = make_tmap_3d_bf16(&tk, a.k, (uint64_t)a.batch, (uint64_t)a.tokens_kv, cols, (uint64_t)a.ld_kv,
+                                   (uint64_t)a.tokens_kv * a.ld_kv, C::BN, 64))
+        return rc;
+    if (int rc = make_tmap_3d_bf16(&tv, a.v, (uint64_t)a.batch, (uint64_t)a.tokens_kv, cols, (uint64_t)a.ld_kv,
+                                   (uint64_t)a.tokens_kv * a.ld_kv, C::BN, 64))
+        return rc;
+    auto kern = attention_fwd_kernel<D>;
+    static bool configured = false;
+    if (!configured) {
+        UCOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
+        configured = true;
+    }
+    dim3 grid((unsigned)ceil_div(a.tokens_q, C::BM), (unsigned)(a.batch * a.heads));
+    {
+        ProfScope ps(KC_ATTENTION, stream, 4.0 * a.batch * a.heads * (double)a.tokens_q * a.tokens_kv * a.head_dim_real);
+        kern<<<grid, C::THREADS, C::SMEM, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(a.ctx), a.tokens_q,
+                                                     a.tokens_kv, a.heads, a.ld_ctx, a.scale * 1.4426950408889634f);
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 }  // namespace
 
-int launch_attention_d64(const void* q, const void* k, const void* vt, void* ctx, int B, int H, int T, int Tpad,
-                         float scale, cudaStream_t stream) {
-    UCOD_REQUIRE(B > 0 && H > 0 && T > 0 && Tpad >= T && Tpad % 8 == 0, "attention: bad geometry B=%d H=%d T=%d Tpad=%d",
-                 B, H, T, Tpad);
-    const uint64_t BH = (uint64_t)B * H;
-    CUtensorMap tq, tk, tv;
-    if (int rc = make_tmap_3d_bf16(&tq, q, BH, (uint64_t)T, 64, 64, (uint64_t)T * 64, ATT_BM, 64)) return rc;
-    if (int rc = make_tmap_3d_bf16(&tk, k, BH, (uint64_t)T, 64, 64, (uint64_t)T * 64, ATT_BN, 64)) return rc;
-    if (int rc = make_tmap_3d_bf16(&tv, vt, BH, 64, (uint64_t)Tpad, (uint64_t)Tpad, (uint64_t)Tpad * 64, 64, 64))
-        return rc;
-    static bool configured = false;
-    if (!configured) {
-        UCOD_CHECK_CUDA(
-            cudaFuncSetAttribute(attention_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
-        configured = true;
-    }
-    dim3 grid((unsigned)ceil_div(T, ATT_BM), (unsigned)BH);
-    {
-        ProfScope ps(KC_ATTENTION, stream, 4.0 * B * H * (double)T * T * ATT_D);
-        attention_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, stream>>>(
-            tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(ctx), T, H, scale * 1.4426950408889634f);
-    }
-    UCOD_CHECK_CUDA(cudaGetLastError());
-    return 0;
+int launch_attention(const AttentionArgs& a, cudaStream_t stream) {
+    UCOD_REQUIRE(a.q && a.k && a.v && a.ctx, "attention: null pointer");
+    UCOD_REQUIRE(a.batch > 0 && a.heads > 0 && a.tokens_q > 0 && a.tokens_kv > 0,
+                 "attention: bad geometry batch=%d heads=%d Tq=%d Tk=%d", a.batch, a.heads, a.tokens_q, a.tokens_kv);
+    UCOD_REQUIRE(a.head_dim == 64 || a.head_dim == 128, "attention: head_dim %d not supported (64 or 128)", a.head_dim);
+    UCOD_REQUIRE(a.ld_q % 8 == 0 && a.ld_kv % 8 == 0 && a.ld_ctx % 8 == 0 && a.ld_q >= a.heads * a.head_dim &&
+                     a.ld_kv >= a.heads * a.head_dim && a.ld_ctx >= a.heads * a.head_dim,
+                 "attention: row pitches must be multiples of 8 and cover heads*head_dim");
+    UCOD_REQUIRE(((uintptr_t)a.q | (uintptr_t)a.k | (uintptr_t)a.v | (uintptr_t)a.ctx) % 16 == 0,
+                 "attention: pointers must be 16-byte aligned");
+    return a.head_dim == 64 ? launch_inst<64>(a, stream) : launch_inst<128>(a, stream);
 }
 
 }  // namespace ucod

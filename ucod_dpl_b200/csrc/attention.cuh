@@ -4,9 +4,20 @@
 
 namespace ucod {
 
-// q, k: [B*H, T, 64] bf16 ; vt: [B*H, 64, Tpad] bf16 (columns >= T must be finite, normally zero) ;
-// ctx: [B, T, H*64] bf16.  scale = 1/sqrt(head_dim).
-int launch_attention_d64(const void* q, const void* k, const void* vt, void* ctx, int B, int H, int T, int Tpad,
-                         float scale, cudaStream_t stream);
+// q: [batch, tokens_q, ld_q] bf16, k / v: [batch, tokens_kv, ld_kv] bf16 — head h occupies columns
+// [h*head_dim, (h+1)*head_dim) of each pointer (so the three pointers may address the Q / K / V column blocks of one
+// fused projection output).  ctx: [batch, tokens_q, ld_ctx] bf16, same head layout.  head_dim 64 or 128;
+// head_dim_real (<= head_dim) only feeds the FLOP accounting when the operands are zero-padded.
+struct AttentionArgs {
+    const void* q = nullptr;
+    const void* k = nullptr;
+    const void* v = nullptr;
+    void* ctx = nullptr;
+    int batch = 0, heads = 0, tokens_q = 0, tokens_kv = 0;
+    int head_dim = 64, head_dim_real = 64;
+    int ld_q = 0, ld_kv = 0, ld_ctx = 0;
+    float scale = 0.125f;
+};
+int launch_attention(const AttentionArgs& args, cudaStream_t stream);
 
 }  // namespace ucod

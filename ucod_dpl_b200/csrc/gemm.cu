@@ -101,22 +101,6 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, int m, int n0,
         const size_t row = (size_t)b * (T - ep.skip) + (t - ep.skip);
         if (ep.out != nullptr) store32_f32(reinterpret_cast<float*>(ep.out) + row * ep.ld_out + n0, v);
         if (ep.out2 != nullptr) store32_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out2) + row * ep.ld_out + n0, v);
-    } else if constexpr (MODE == EPI_QKV) {
-        const int T = ep.tokens, H = ep.heads;
-        const int D = N / 3;
-        const int b = m / T, t = m - b * T;
-        const int which = n0 / D;
-        const int within = n0 - which * D;
-        const int h = within >> 6, d0 = within & 63;
-        if (which < 2) {
-            __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? ep.out : ep.out2);
-            store32_bf16(base + (((size_t)b * H + h) * T + t) * 64 + d0, v);
-        } else {
-            __nv_bfloat16* vt = reinterpret_cast<__nv_bfloat16*>(ep.out3) +
-                                (((size_t)b * H + h) * 64 + d0) * ep.tokens_pad + t;
-#pragma unroll
-            for (int i = 0; i < 32; ++i) vt[(size_t)i * ep.tokens_pad] = __float2bfloat16_rn(v[i]);
-        }
     }
 }
 
@@ -281,7 +265,6 @@ static int launch_mode(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
         case EPI_BIAS_BF16: return launch_inst<BN, EPI_BIAS_BF16>(ta, tb, M, N, K, ep, s);
         case EPI_BIAS_GELU_BF16: return launch_inst<BN, EPI_BIAS_GELU_BF16>(ta, tb, M, N, K, ep, s);
         case EPI_RESID_F32: return launch_inst<BN, EPI_RESID_F32>(ta, tb, M, N, K, ep, s);
-        case EPI_QKV: return launch_inst<BN, EPI_QKV>(ta, tb, M, N, K, ep, s);
         case EPI_PATCH: return launch_inst<BN, EPI_PATCH>(ta, tb, M, N, K, ep, s);
         case EPI_BIAS_F32: return launch_inst<BN, EPI_BIAS_F32>(ta, tb, M, N, K, ep, s);
         case EPI_KEYS: return launch_inst<BN, EPI_KEYS>(ta, tb, M, N, K, ep, s);
@@ -294,9 +277,6 @@ int launch_gemm_bf16(const void* A, int lda, const void* W, int ldw, int M, int 
     UCOD_REQUIRE(M > 0 && N > 0 && K > 0, "gemm: empty problem M=%d N=%d K=%d", M, N, K);
     UCOD_REQUIRE(N % 128 == 0, "gemm: N=%d must be a multiple of 128", N);
     UCOD_REQUIRE(lda % 8 == 0 && ldw % 8 == 0 && K % 8 == 0, "gemm: lda/ldw/K must be multiples of 8");
-    if (ep.mode == EPI_QKV)
-        UCOD_REQUIRE(N % 3 == 0 && (N / 3) % 64 == 0 && ep.tokens > 0 && ep.heads * 64 == N / 3,
-                     "gemm: bad QKV epilogue geometry");
     const int BN = (N % 256 == 0) ? 256 : 128;
     CUtensorMap ta, tb;
     if (int rc = make_tmap_2d_bf16(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 128, 64)) return rc;

@@ -9,7 +9,6 @@ enum GemmEpiMode : int {
     EPI_BIAS_BF16 = 0,       // out_bf16[m,n] = acc + bias[n]
     EPI_BIAS_GELU_BF16 = 1,  // out_bf16[m,n] = gelu_erf(acc + bias[n])
     EPI_RESID_F32 = 2,       // x_f32[m,n] += scale[n] * (acc + bias[n])            (scale may be null -> 1)
-    EPI_QKV = 3,             // scatter: q,k -> [B,heads,T,64] bf16 ; v -> vT [B,heads,64,Tpad] bf16
     EPI_PATCH = 4,           // x_f32[b*(P+1)+1+p, n] = acc + bias[n] + pos[1+p, n]   (m = b*P + p)
     EPI_BIAS_F32 = 5,        // out_f32[m,n] = acc + bias[n]
     EPI_KEYS = 6,            // last-layer key projection: drop `skip` leading tokens per image, write
@@ -23,11 +22,8 @@ struct GemmEpi {
     const float* pos = nullptr;    // [T, N] (EPI_PATCH)
     void* out = nullptr;
     void* out2 = nullptr;
-    void* out3 = nullptr;
     int ld_out = 0;      // row pitch of out/out2 in elements
-    int tokens = 0;      // T  (EPI_QKV / EPI_KEYS) or P (EPI_PATCH)
-    int tokens_pad = 0;  // Tpad (EPI_QKV)
-    int heads = 0;       // EPI_QKV
+    int tokens = 0;      // T (EPI_KEYS) or P (EPI_PATCH)
     int skip = 0;        // EPI_KEYS
 };
 

@@ -6,7 +6,7 @@
 // The pseudo-label variant additionally returns the last layer's CLS->patch attention row
 // (generate_pseudo_label.py:76-81, data/utils/found_bkg_mask.py:24).
 //
-// Per layer: LN (warp/row, fp32 stats) -> QKV GEMM (tcgen05, epilogue scatters Q,K,[V^T]) -> fused attention
+// Per layer: LN (warp/row, fp32 stats) -> fused QKV GEMM (tcgen05, [M,3D] bf16) -> fused attention reading Q/K/V in place
 // (tcgen05) -> out-proj GEMM (+bias, LayerScale, residual, fp32 stream) -> LN -> fc1 GEMM (+bias, erf-GELU)
 // -> fc2 GEMM (+bias, LayerScale, residual).
 #include "vit.cuh"
@@ -162,12 +162,12 @@ static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct VitWorkspace {
     float* x;
-    __nv_bfloat16 *xn, *q, *k, *vt, *ctx, *h, *patches;
+    __nv_bfloat16 *xn, *qkv, *ctx, *h, *patches;
     float* keys_all;
     size_t bytes;
 };
 
-static VitWorkspace carve(const ucod_vit_cfg& c, int B, int T, int Tpad, int P, void* base) {
+static VitWorkspace carve(const ucod_vit_cfg& c, int B, int T, int P, void* base) {
     VitWorkspace w{};
     size_t off = 0;
     auto take = [&](size_t n) {
@@ -178,9 +178,7 @@ static VitWorkspace carve(const ucod_vit_cfg& c, int B, int T, int Tpad, int P, 
     const size_t M = (size_t)B * T, D = c.hidden;
     w.x = static_cast<float*>(take(M * D * 4));
     w.xn = static_cast<__nv_bfloat16*>(take(M * D * 2));
-    w.q = static_cast<__nv_bfloat16*>(take(M * D * 2));
-    w.k = static_cast<__nv_bfloat16*>(take(M * D * 2));
-    w.vt = static_cast<__nv_bfloat16*>(take((size_t)B * D * Tpad * 2));
+    w.qkv = static_cast<__nv_bfloat16*>(take(M * 3 * D * 2));  // fused projection output [M, 3D]: Q | K | V
     w.ctx = static_cast<__nv_bfloat16*>(take(M * D * 2));
     const size_t hbytes = M * (size_t)c.mlp_dim * 2;
     const size_t pbytes = (size_t)B * P * c.patch_kpad * 2;
@@ -226,8 +224,8 @@ int vit_workspace_bytes(void* handle, int B, int img_h, int img_w, size_t* out) 
     VitModel* m = static_cast<VitModel*>(handle);
     const int p = m->cfg.patch;
     UCOD_REQUIRE(B > 0 && img_h >= p && img_w >= p, "ucod_vit_workspace_bytes: bad geometry");
-    const int P = (img_h / p) * (img_w / p), T = P + 1, Tpad = (T + 7) / 8 * 8;
-    *out = carve(m->cfg, B, T, Tpad, P, nullptr).bytes;
+    const int P = (img_h / p) * (img_w / p), T = P + 1;
+    *out = carve(m->cfg, B, T, P, nullptr).bytes;
     return 0;
 }
 
@@ -250,9 +248,9 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
     UCOD_REQUIRE(B > 0 && img_h >= p && img_w >= p, "ucod_vit_keys: bad geometry");
     UCOD_REQUIRE(image_dtype == 0 || image_dtype == 1, "ucod_vit_keys: image_dtype must be 0 (f32) or 1 (u8)");
     UCOD_REQUIRE(keys_f32 || keys_bf16 || cls_attn, "ucod_vit_keys: no output requested");
-    const int gh = img_h / p, gw = img_w / p, P = gh * gw, T = P + 1, Tpad = (T + 7) / 8 * 8;
+    const int gh = img_h / p, gw = img_w / p, P = gh * gw, T = P + 1;
     const int M = B * T;
-    VitWorkspace w = carve(c, B, T, Tpad, P, workspace);
+    VitWorkspace w = carve(c, B, T, P, workspace);
     UCOD_REQUIRE(ws_bytes >= w.bytes, "ucod_vit_keys: workspace too small (%zu < %zu bytes)", ws_bytes, w.bytes);
     UCOD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "ucod_vit_keys: workspace must be 1 KiB aligned");
 
@@ -286,7 +284,6 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
         cls_init_kernel<<<B, 256, 0, stream>>>(w.x, m->cls, pos_emb, T, D);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
-    UCOD_CHECK_CUDA(cudaMemsetAsync(w.vt, 0, (size_t)B * D * Tpad * 2, stream));
 
     // ---- layers 0 .. L-2 in full ----
     const float scale = 0.125f;  // 1/sqrt(64)
@@ -295,17 +292,20 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
         if (int rc = layernorm(w.x, L.ln1_w, L.ln1_b, w.xn, M, c.ln_eps, stream)) return rc;
         {
             GemmEpi ep;
-            ep.mode = EPI_QKV;
+            ep.mode = EPI_BIAS_BF16;
             ep.bias = L.b_qkv;
-            ep.out = w.q;
-            ep.out2 = w.k;
-            ep.out3 = w.vt;
-            ep.tokens = T;
-            ep.tokens_pad = Tpad;
-            ep.heads = H;
+            ep.out = w.qkv;
+            ep.ld_out = 3 * D;
             if (int rc = launch_gemm_bf16(w.xn, D, L.w_qkv, D, M, 3 * D, D, ep, stream)) return rc;
         }
-        if (int rc = launch_attention_d64(w.q, w.k, w.vt, w.ctx, B, H, T, Tpad, scale, stream)) return rc;
+        {
+            AttentionArgs a;
+            a.q = w.qkv, a.k = w.qkv + D, a.v = w.qkv + 2 * D, a.ctx = w.ctx;
+            a.batch = B, a.heads = H, a.tokens_q = T, a.tokens_kv = T;
+            a.ld_q = 3 * D, a.ld_kv = 3 * D, a.ld_ctx = D;
+            a.scale = scale;
+            if (int rc = launch_attention(a, stream)) return rc;
+        }
         {
             GemmEpi ep;
             ep.mode = EPI_RESID_F32;
