@@ -36,12 +36,12 @@ long long ucod_launch_count(void);
 
 /* ---- dense building block -------------------------------------------------------------------
  * out[M,N] = epilogue(A[M,K] * W[N,K]^T) ; A, W bf16 row-major (K contiguous), fp32 accumulate (tcgen05).
- * epi_mode: 0 = bf16 out, +bias ; 1 = bf16 out, gelu(+bias) ; 2 = fp32 in-place residual
- *           out += scale*(acc+bias) ; 5 = fp32 out, +bias.   bias/scale may be NULL.
+ * epi_mode: 0 = bf16 out, +bias ; 1 = bf16 out, erf-gelu(+bias) ; 2 = fp32 in-place residual
+ *           out += acc+bias (TMA reduce-add) ; 5 = fp32 out, +bias.   bias may be NULL.  ld_out in elements.
  * Replaces: torch.nn.Linear / 1x1 Conv2d library GEMMs on the path (HF modeling_dinov2.py:153-235,348-387;
  * models/modules/DBA.py:13,35). */
 int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n, int k, int epi_mode,
-                   const float* bias, const float* scale, void* out, int ld_out, void* stream);
+                   const float* bias, void* out, int ld_out, void* stream);
 
 /* Fused softmax(q k^T * scale) v, non-causal (tcgen05 flash-attention forward), head_dim 64 or 128.
  * q: [batch, tokens_q, ld_q] bf16 ; k, v: [batch, tokens_kv, ld_kv] bf16 ; head h lives in columns
@@ -71,12 +71,10 @@ typedef struct ucod_vit_cfg {
 typedef struct ucod_vit_layer {
     const float* ln1_w; const float* ln1_b;
     const void* w_qkv;  const float* b_qkv;   /* bf16 [3*hidden, hidden] = [Wq;Wk;Wv], fp32 [3*hidden] */
-    const void* w_o;    const float* b_o;     /* bf16 [hidden, hidden] */
-    const float* ls1;                         /* LayerScale lambda1 [hidden] or NULL */
+    const void* w_o;    const float* b_o;     /* bf16 [hidden, hidden]; LayerScale lambda1 folded in (rows, bias) */
     const float* ln2_w; const float* ln2_b;
     const void* w_fc1;  const float* b_fc1;   /* bf16 [mlp_dim, hidden] */
-    const void* w_fc2;  const float* b_fc2;   /* bf16 [hidden, mlp_dim] */
-    const float* ls2;                         /* LayerScale lambda2 [hidden] or NULL */
+    const void* w_fc2;  const float* b_fc2;   /* bf16 [hidden, mlp_dim]; LayerScale lambda2 folded in */
 } ucod_vit_layer;
 
 /* patch_w: bf16 [hidden, patch_kpad] (conv weight flattened c-major, zero padded), patch_b fp32 [hidden],

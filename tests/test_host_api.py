@@ -161,6 +161,6 @@ def test_argument_errors_do_not_need_a_gpu():
     from ucod_dpl_b200 import _lib
     lib = _lib.load()
     lib.ucod_gemm_bf16.restype = ctypes.c_int
-    rc = lib.ucod_gemm_bf16(None, 8, None, 8, 0, 128, 64, 0, None, None, None, 128, None)
+    rc = lib.ucod_gemm_bf16(None, 8, None, 8, 0, 128, 64, 0, None, None, 128, None)
     assert rc != 0
     assert b"gemm" in lib.ucod_last_error()

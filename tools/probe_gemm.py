@@ -13,7 +13,7 @@ def run(M, N, K, mode, iters=20):
     w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
     bias = torch.randn(N, device="cuda")
     out = torch.empty(M, N, device="cuda", dtype=torch.float32 if mode in (2, 5) else torch.bfloat16)
-    args = (_lib.ptr(a), K, _lib.ptr(w), K, M, N, K, mode, _lib.ptr(bias), _lib.ptr(None), _lib.ptr(out), N,
+    args = (_lib.ptr(a), K, _lib.ptr(w), K, M, N, K, mode, _lib.ptr(bias), _lib.ptr(out), N,
             _lib.stream_ptr())
     for _ in range(3):
         _lib.call("ucod_gemm_bf16", *args)

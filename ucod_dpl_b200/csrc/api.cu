@@ -22,7 +22,7 @@ int ucod_prof_collect(double* ms, double* work, long long* launches) { return pr
 long long ucod_launch_count(void) { return launch_count_total(); }
 
 int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n, int k, int epi_mode,
-                   const float* bias, const float* scale, void* out, int ld_out, void* stream) {
+                   const float* bias, void* out, int ld_out, void* stream) {
     UCOD_REQUIRE(a && w && out, "ucod_gemm_bf16: null pointer");
     UCOD_REQUIRE(epi_mode == EPI_BIAS_BF16 || epi_mode == EPI_BIAS_GELU_BF16 || epi_mode == EPI_RESID_F32 ||
                      epi_mode == EPI_BIAS_F32,
@@ -30,7 +30,6 @@ int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n,
     GemmEpi ep;
     ep.mode = epi_mode;
     ep.bias = bias;
-    ep.scale = scale;
     ep.out = out;
     ep.ld_out = ld_out;
     return launch_gemm_bf16(a, lda, w, ldw, m, n, k, ep, reinterpret_cast<cudaStream_t>(stream));

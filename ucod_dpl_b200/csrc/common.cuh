@@ -229,6 +229,9 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // 2-D bf16 row-major [rows, cols] (cols contiguous), box = {box_cols (=64), box_rows}, 128 B swizzle.
 int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint64_t row_stride_elems,
                       uint32_t box_rows, uint32_t box_cols);
+// 2-D row-major [rows, cols] of 2-byte (bf16) or 4-byte (fp32) elements; box rows are 128 B wide, 128 B swizzle.
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                 uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols);
 // 3-D bf16 [batch, rows, cols]; box = {box_cols, box_rows, 1}.
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,
                       uint64_t row_stride_elems, uint64_t batch_stride_elems, uint32_t box_rows, uint32_t box_cols);

@@ -6,12 +6,17 @@
 // Tile 128 x BN x 64, STAGES-deep smem ring (mbarrier full/empty), two TMEM accumulator stages so the
 // epilogue of tile i overlaps the main loop of tile i+1. One CTA per SM, static tile striding with the
 // N index fastest so that CTAs running concurrently share the same A row-block through L2.
+// Epilogue: TMEM -> registers (+bias from a shared-memory tile, GELU) -> 128B-swizzled staging box in shared
+// memory -> TMA bulk tensor store (bf16 outputs) or TMA reduce-add (fp32 residual stream: x += acc + bias is
+// performed by the L2, the SM never reads x).  Patch-embed / key / decoder outputs use direct row stores.
 //
 // Replaces (reference, all library-dispatched): HF Dinov2/ViT `nn.Linear` query/key/value/dense/fc1/fc2
 // (transformers modeling_dinov2.py:153-235,348-387), patch-embed Conv2d (:38-117), the decoder's
 // `decoupling` 1x1 conv (models/modules/DBA.py:13,35) and the CORAL CSF projections (models/modules/mlp.py:116-148).
 #include "gemm.cuh"
 #include "prof.cuh"
+
+#include <string.h>
 
 namespace ucod {
 
@@ -23,21 +28,39 @@ struct GemmCfg {
     static constexpr int A_BYTES = BM * BK * 2;
     static constexpr int B_BYTES = BN * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual alignment slack
-    static constexpr int TMEM_COLS = 2 * BN;                                    // two accumulator stages
+    static constexpr int OUT_BYTES = BM * 128;  // one staged output box: 128 rows x 128 B (64 bf16 or 32 fp32 columns)
+    static constexpr int BIAS_BYTES = BN * 4;
+    static constexpr int BAR_BYTES = 128;
+    // +1024: manual alignment slack
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+    static constexpr int TMEM_COLS = 2 * BN;  // two accumulator stages
     static constexpr int THREADS = 192;
 };
+static_assert(GemmCfg<256>::SMEM_BYTES <= 227 * 1024, "GEMM shared memory budget exceeded");
+
+// Modes whose output tile is staged in shared memory and written with TMA (bulk tensor store / reduce-add).
+__host__ __device__ constexpr bool epi_uses_tma(int mode) {
+    return mode == EPI_BIAS_BF16 || mode == EPI_BIAS_GELU_BF16 || mode == EPI_RESID_F32;
+}
+__host__ __device__ constexpr int epi_box_cols(int mode) { return mode == EPI_RESID_F32 ? 32 : 64; }
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue: one thread owns one accumulator row; called per 32-column chunk.
+// Epilogue helpers
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load32(const float* p, float (&v)[32]) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
-        v[4 * i + 0] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
-    }
+// erf-GELU through erfc: 0.5*erfc(a) = 2^q(a) on a = |x|/sqrt(2) in [0, 4.2] (degree-5 fit, |gelu error| < 1e-6,
+// far below the bf16 output resolution); x > 0: x - x*e, x <= 0: x*e.  One MUFU + 9 FMA-pipe instructions.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float a = fminf(fabsf(x) * 0.70710678118654752440f, 4.2f);
+    float q = -0.0027778262738138437f;
+    q = fmaf(q, a, 0.028876738622784615f);
+    q = fmaf(q, a, -0.14762860536575317f);
+    q = fmaf(q, a, -0.9191074371337891f);
+    q = fmaf(q, a, -1.6277707815170288f);
+    q = fmaf(q, a, -1.0000038146972656f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(q));
+    const float r = x * e;
+    return x > 0.f ? x - r : r;
 }
 __device__ __forceinline__ void store32_bf16(__nv_bfloat16* dst, const float (&v)[32]) {
 #pragma unroll
@@ -55,37 +78,47 @@ __device__ __forceinline__ void store32_f32(float* dst, const float (&v)[32]) {
     for (int i = 0; i < 8; ++i)
         reinterpret_cast<float4*>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
-
-template <int MODE>
-__device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, int m, int n0, int N, float (&v)[32]) {
-    if (ep.bias != nullptr) {
-        float b[32];
-        load32(ep.bias + n0, b);
+__device__ __forceinline__ void load32(const float* p, float (&v)[32]) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] += b[i];
+    for (int i = 0; i < 8; ++i) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p) + i);
+        v[4 * i + 0] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
     }
-    if constexpr (MODE == EPI_BIAS_BF16) {
-        store32_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)m * ep.ld_out + n0, v);
-    } else if constexpr (MODE == EPI_BIAS_GELU_BF16) {
+}
+// acc += bias (bias tile lives in shared memory; every thread reads the same address -> broadcast)
+__device__ __forceinline__ void add_bias32(const float* sbias, float (&v)[32]) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
-        store32_bf16(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)m * ep.ld_out + n0, v);
-    } else if constexpr (MODE == EPI_BIAS_F32) {
+    for (int i = 0; i < 8; ++i) {
+        const float4 t = reinterpret_cast<const float4*>(sbias)[i];
+        v[4 * i + 0] += t.x, v[4 * i + 1] += t.y, v[4 * i + 2] += t.z, v[4 * i + 3] += t.w;
+    }
+}
+// TMA store / reduce-add of one staged [128 rows x 128 B] box (shared -> global), bulk-group completion.
+__device__ __forceinline__ void tma_store_2d(const void* desc, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const void* desc, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+// direct (non-TMA) output modes: one thread owns one row, 32 consecutive columns per call
+template <int MODE>
+__device__ __forceinline__ void epilogue_direct(const GemmEpi& ep, int m, int n0, int N, float (&v)[32]) {
+    if constexpr (MODE == EPI_BIAS_F32) {
         store32_f32(reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ld_out + n0, v);
-    } else if constexpr (MODE == EPI_RESID_F32) {
-        float* x = reinterpret_cast<float*>(ep.out) + (size_t)m * ep.ld_out + n0;
-        if (ep.scale != nullptr) {
-            float s[32];
-            load32(ep.scale + n0, s);
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] *= s[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            float4 t = reinterpret_cast<const float4*>(x)[i];
-            v[4 * i] += t.x, v[4 * i + 1] += t.y, v[4 * i + 2] += t.z, v[4 * i + 3] += t.w;
-        }
-        store32_f32(x, v);
     } else if constexpr (MODE == EPI_PATCH) {
         const int P = ep.tokens;
         const int b = m / P, p = m - b * P;
@@ -110,7 +143,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmEpi& ep, int m, int n0,
 template <int BN, int MODE>
 __global__ void __launch_bounds__(192, 1)
     gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                             int M, int N, int K, const GemmEpi ep) {
+                             const __grid_constant__ CUtensorMap tmap_out, int M, int N, int K, const GemmEpi ep) {
     using Cfg = GemmCfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
 
@@ -118,7 +151,9 @@ __global__ void __launch_bounds__(192, 1)
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint8_t* sOut = smem + STAGES * Cfg::STAGE_BYTES;  // 2 x OUT_BYTES, 1024-aligned
+    float* sBias = reinterpret_cast<float*>(sOut + 2 * Cfg::OUT_BYTES);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
     uint64_t* bar_empty = bar_full + STAGES;
     uint64_t* bar_tfull = bar_empty + STAGES;
     uint64_t* bar_tempty = bar_tfull + 2;
@@ -201,33 +236,102 @@ __global__ void __launch_bounds__(192, 1)
             }
         }
     } else {
-        // ===================== Epilogue warps (TMEM -> regs -> global) =====================
+        // ===================== Epilogue warps: TMEM -> registers -> (smem -> TMA) | global =====================
         const int q = warp & 3;  // TMEM lane quarter this warp may touch
+        const int row = q * 32 + lane;
+        const int et = threadIdx.x - 64;  // 0..127
+        const bool leader = (et == 0);
+        if (leader && epi_uses_tma(MODE)) tma_prefetch_desc(&tmap_out);
+        uint32_t sub_count = 0;
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
             const int m0 = (tile / n_tiles) * Cfg::BM;
             const int n0 = (tile % n_tiles) * BN;
+            // bias tile -> shared (the previous tile's readers are all past their last barrier)
+            for (int i = et; i < BN; i += 128) sBias[i] = ep.bias != nullptr ? __ldg(ep.bias + n0 + i) : 0.f;
             mbar_wait(&bar_tfull[as], aphase);
             tc_fence_after();
-            const int m = m0 + q * 32 + lane;
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+            if constexpr (epi_uses_tma(MODE)) {
+                constexpr int BOX = epi_box_cols(MODE);  // columns per staged box
+                constexpr int NSUB = BN / BOX;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t r[32];
-                tmem_ld32(taddr + c * 32, r);
-                tmem_wait_ld();
-                if (m < M) {
-                    float v[32];
+                for (int sidx = 0; sidx < NSUB; ++sidx, ++sub_count) {
+                    uint8_t* stage_out = sOut + (sub_count & 1) * Cfg::OUT_BYTES;
+                    if (leader) bulk_wait_read<1>();  // the store that last used this buffer has read it
+                    epi_bar_sync();                   // buffer free for everyone (+ bias tile visible)
+                    uint8_t* srow = stage_out + row * 128;
+                    const int rx = row & 7;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    epilogue_chunk<MODE>(ep, m, n0 + c * 32, N, v);
+                    for (int c = 0; c < BOX / 32; ++c) {
+                        uint32_t r[32];
+                        tmem_ld32(taddr + sidx * BOX + c * 32, r);
+                        tmem_wait_ld();
+                        if (sidx == NSUB - 1 && c == BOX / 32 - 1) {  // accumulator stage fully read
+                            tc_fence_before();
+                            mbar_arrive(&bar_tempty[as]);
+                        }
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        add_bias32(sBias + sidx * BOX + c * 32, v);
+                        if constexpr (MODE == EPI_RESID_F32) {
+#pragma unroll
+                            for (int g = 0; g < 8; ++g)
+                                *reinterpret_cast<float4*>(srow + ((g ^ rx) << 4)) =
+                                    make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        } else {
+                            if constexpr (MODE == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+                            }
+#pragma unroll
+                            for (int g = 0; g < 4; ++g) {
+                                uint4 t;
+                                t.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+                                t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                                t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+                                t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                                *reinterpret_cast<uint4*>(srow + (((c * 4 + g) ^ rx) << 4)) = t;
+                            }
+                        }
+                    }
+                    fence_proxy_async_smem();
+                    epi_bar_sync();
+                    if (leader) {
+                        if constexpr (MODE == EPI_RESID_F32)
+                            tma_reduce_add_2d(&tmap_out, stage_out, n0 + sidx * BOX, m0);
+                        else
+                            tma_store_2d(&tmap_out, stage_out, n0 + sidx * BOX, m0);
+                        bulk_commit();
+                    }
                 }
+            } else {
+                epi_bar_sync();  // bias tile visible
+                const int m = m0 + row;
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_wait_ld();
+                    if (c == BN / 32 - 1) {
+                        tc_fence_before();
+                        mbar_arrive(&bar_tempty[as]);
+                    }
+                    if (m < M) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        add_bias32(sBias + c * 32, v);
+                        epilogue_direct<MODE>(ep, m, n0 + c * 32, N, v);
+                    }
+                }
+                epi_bar_sync();  // everyone is done with the bias tile before the next one is written
             }
-            tc_fence_before();
-            mbar_arrive(&bar_tempty[as]);
         }
+        if (leader && epi_uses_tma(MODE)) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -241,6 +345,16 @@ __global__ void __launch_bounds__(192, 1)
 template <int BN, int MODE>
 static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const GemmEpi& ep,
                        cudaStream_t stream) {
+    CUtensorMap tout;
+    memset(&tout, 0, sizeof(tout));
+    if (epi_uses_tma(MODE)) {
+        UCOD_REQUIRE(ep.out != nullptr && ep.ld_out >= N, "gemm: output pointer / pitch missing");
+        const int esz = MODE == EPI_RESID_F32 ? 4 : 2;
+        UCOD_REQUIRE(((size_t)ep.ld_out * esz) % 16 == 0, "gemm: output row pitch must be a multiple of 16 bytes");
+        if (int rc = make_tmap_2d(&tout, ep.out, esz, (uint64_t)M, (uint64_t)N, (uint64_t)ep.ld_out, 128,
+                                  (uint32_t)epi_box_cols(MODE)))
+            return rc;
+    }
     using Cfg = GemmCfg<BN>;
     auto kern = gemm_bf16_tcgen05_kernel<BN, MODE>;
     static bool configured = false;
@@ -252,7 +366,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
     {
         ProfScope ps(KC_GEMM, stream, 2.0 * M * N * K);
-        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, M, N, K, ep);
+        kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, M, N, K, ep);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;

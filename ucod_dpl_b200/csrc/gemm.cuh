@@ -8,7 +8,7 @@ namespace ucod {
 enum GemmEpiMode : int {
     EPI_BIAS_BF16 = 0,       // out_bf16[m,n] = acc + bias[n]
     EPI_BIAS_GELU_BF16 = 1,  // out_bf16[m,n] = gelu_erf(acc + bias[n])
-    EPI_RESID_F32 = 2,       // x_f32[m,n] += scale[n] * (acc + bias[n])            (scale may be null -> 1)
+    EPI_RESID_F32 = 2,       // x_f32[m,n] += acc + bias[n]   (TMA reduce-add; LayerScale is folded into W, bias)
     EPI_PATCH = 4,           // x_f32[b*(P+1)+1+p, n] = acc + bias[n] + pos[1+p, n]   (m = b*P + p)
     EPI_BIAS_F32 = 5,        // out_f32[m,n] = acc + bias[n]
     EPI_KEYS = 6,            // last-layer key projection: drop `skip` leading tokens per image, write
@@ -18,7 +18,6 @@ enum GemmEpiMode : int {
 struct GemmEpi {
     int mode = EPI_BIAS_BF16;
     const float* bias = nullptr;   // [N]
-    const float* scale = nullptr;  // [N]
     const float* pos = nullptr;    // [T, N] (EPI_PATCH)
     void* out = nullptr;
     void* out2 = nullptr;

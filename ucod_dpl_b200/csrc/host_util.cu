@@ -46,7 +46,7 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 }
 
 static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-                  const cuuint32_t* box) {
+                  const cuuint32_t* box, CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
     PFN_tmapEncodeTiled fn = get_encode_fn();
     UCOD_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
     UCOD_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base pointer must be 16-byte aligned");
@@ -54,7 +54,7 @@ static int encode(CUtensorMap* out, const void* base, int rank, const cuuint64_t
         UCOD_REQUIRE((strides_bytes[i] & 15) == 0, "TMA stride %d (%llu B) must be a multiple of 16", i,
                      (unsigned long long)strides_bytes[i]);
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims,
+    CUresult r = fn(out, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims,
                     strides_bytes, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     UCOD_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -67,6 +67,16 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     cuuint64_t strides[1] = {row_stride_elems * 2};
     cuuint32_t box[2] = {box_cols, box_rows};
     return encode(out, base, 2, dims, strides, box);
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t rows, uint64_t cols,
+                 uint64_t row_stride_elems, uint32_t box_rows, uint32_t box_cols) {
+    UCOD_REQUIRE(elem_bytes == 2 || elem_bytes == 4, "make_tmap_2d: element size %d not supported", elem_bytes);
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_stride_elems * (uint64_t)elem_bytes};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    return encode(out, base, 2, dims, strides, box,
+                  elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
 }
 
 int make_tmap_3d_bf16(CUtensorMap* out, const void* base, uint64_t batch, uint64_t rows, uint64_t cols,

@@ -7,7 +7,7 @@
 // (generate_pseudo_label.py:76-81, data/utils/found_bkg_mask.py:24).
 //
 // Per layer: LN (warp/row, fp32 stats) -> fused QKV GEMM (tcgen05, [M,3D] bf16) -> fused attention reading Q/K/V in place
-// (tcgen05) -> out-proj GEMM (+bias, LayerScale, residual, fp32 stream) -> LN -> fc1 GEMM (+bias, erf-GELU)
+// (tcgen05) -> out-proj GEMM (+bias, residual reduce-add into the fp32 stream; LayerScale folded into the weights) -> LN -> fc1 GEMM (+bias, erf-GELU)
 // -> fc2 GEMM (+bias, LayerScale, residual).
 #include "vit.cuh"
 
@@ -310,7 +310,6 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
             GemmEpi ep;
             ep.mode = EPI_RESID_F32;
             ep.bias = L.b_o;
-            ep.scale = L.ls1;
             ep.out = w.x;
             ep.ld_out = D;
             if (int rc = launch_gemm_bf16(w.ctx, D, L.w_o, D, M, D, D, ep, stream)) return rc;
@@ -328,7 +327,6 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
             GemmEpi ep;
             ep.mode = EPI_RESID_F32;
             ep.bias = L.b_fc2;
-            ep.scale = L.ls2;
             ep.out = w.x;
             ep.ld_out = D;
             if (int rc = launch_gemm_bf16(w.h, c.mlp_dim, L.w_fc2, c.mlp_dim, M, D, c.mlp_dim, ep, stream)) return rc;

@@ -43,8 +43,7 @@ class _Cfg(ctypes.Structure):
 
 class _Layer(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
-        "ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ls1", "ln2_w", "ln2_b", "w_fc1", "b_fc1", "w_fc2",
-        "b_fc2", "ls2")]
+        "ln1_w", "ln1_b", "w_qkv", "b_qkv", "w_o", "b_o", "ln2_w", "ln2_b", "w_fc1", "b_fc1", "w_fc2", "b_fc2")]
 
 
 def _layer_keys(spec: VitSpec, i: int) -> dict:
@@ -107,16 +106,23 @@ class VitKeyExtractor:
             L.ln1_b = f32(sd[k["ln1"] + ".bias"]).data_ptr()
             L.w_qkv = bf16(wqkv).data_ptr()
             L.b_qkv = f32(bqkv).data_ptr()
-            L.w_o = bf16(sd[k["o"] + ".weight"]).data_ptr()
-            L.b_o = f32(sd[k["o"] + ".bias"]).data_ptr()
-            L.ls1 = f32(sd[k["ls1"]]).data_ptr() if k["ls1"] else None
+            # LayerScale (DINOv2) is folded into the projection that precedes it: ls * (W x + b) = (ls W) x + ls b
+            ls1 = sd[k["ls1"]].detach().float() if k["ls1"] else None
+            ls2 = sd[k["ls2"]].detach().float() if k["ls2"] else None
+            w_o, b_o = sd[k["o"] + ".weight"].detach().float(), sd[k["o"] + ".bias"].detach().float()
+            w_2, b_2 = sd[k["fc2"] + ".weight"].detach().float(), sd[k["fc2"] + ".bias"].detach().float()
+            if ls1 is not None:
+                w_o, b_o = w_o * ls1[:, None], b_o * ls1
+            if ls2 is not None:
+                w_2, b_2 = w_2 * ls2[:, None], b_2 * ls2
+            L.w_o = bf16(w_o).data_ptr()
+            L.b_o = f32(b_o).data_ptr()
             L.ln2_w = f32(sd[k["ln2"] + ".weight"]).data_ptr()
             L.ln2_b = f32(sd[k["ln2"] + ".bias"]).data_ptr()
             L.w_fc1 = bf16(sd[k["fc1"] + ".weight"]).data_ptr()
             L.b_fc1 = f32(sd[k["fc1"] + ".bias"]).data_ptr()
-            L.w_fc2 = bf16(sd[k["fc2"] + ".weight"]).data_ptr()
-            L.b_fc2 = f32(sd[k["fc2"] + ".bias"]).data_ptr()
-            L.ls2 = f32(sd[k["ls2"]]).data_ptr() if k["ls2"] else None
+            L.w_fc2 = bf16(w_2).data_ptr()
+            L.b_fc2 = f32(b_2).data_ptr()
         cfg = _Cfg(spec.hidden, spec.layers, spec.heads, spec.mlp_dim, spec.patch, self.kpad, spec.ln_eps)
         self._handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
