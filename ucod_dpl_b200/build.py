@@ -46,7 +46,7 @@ def _compile_one(src: Path, force: bool, hdr_mtime: float) -> tuple[Path, str]:
     if (not force and obj.exists() and obj.stat().st_mtime >= src.stat().st_mtime
             and obj.stat().st_mtime >= hdr_mtime):
         return obj, ""
-    cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+    cmd = [_nvcc(), *NVCC_FLAGS, *os.environ.get("UCOD_NVCC_EXTRA", "").split(), "-c", str(src), "-o", str(obj)]
     p = subprocess.run(cmd, capture_output=True, text=True)
     if p.returncode != 0:
         raise RuntimeError(f"nvcc failed for {src.name}:\n{p.stdout}\n{p.stderr}")

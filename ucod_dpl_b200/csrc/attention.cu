@@ -10,9 +10,12 @@
 //
 // CTA = 256 threads = two warpgroups:
 //   WG0: warp 0 = TMA producer (Q once; K_j / V_j double buffered, separately released), warp 1 = single-thread
-//        MMA issuer (+ TMEM allocator); registers trimmed with setmaxnreg.dec.
-//   WG1: 4 softmax warps, one thread per query row (= TMEM lane), registers raised with setmaxnreg.inc so the
-//        whole 128-wide S row lives in registers (S is read from TMEM exactly once).
+//        MMA issuer (+ TMEM allocator); registers trimmed with setmaxnreg.dec (80: no spills in the issue loop).
+//   WG1: 4 softmax warps, one thread per query row (= TMEM lane), registers raised with setmaxnreg.inc (176) so
+//        the whole 128-wide S row lives in registers (S is read from TMEM exactly once).
+// Measured on B200 (tools/att_timeline.py, tools/ubench/mma_rate.cu): the softmax warps are busy ~85 % of a tile
+// period (exp phase bound by the 16/clk/SM MUFU rate shared by the two resident CTAs); dependent N=64 P.V MMAs
+// retire every ~74 clk (latency-bound chain), S MMAs every 67 clk.
 // TMEM: S fp32 [0,128) | P bf16-packed [128,192) | O fp32 [192,192+D).
 //   S_j  = Q K_j^T                (SS MMA, both operands K-major SW128 tiles)
 //   P_j  = exp2(S_j*c - m_ref)    (written back to TMEM as packed bf16; never touches shared memory)
@@ -28,6 +31,13 @@
 #include "prof.cuh"
 
 namespace ucod {
+
+#ifdef UCOD_ATT_TIMELINE
+__device__ long long g_att_tl[3][16][8];
+#define TL(role, j, slot) do { if (tl_on && (j) < 16) g_att_tl[role][j][slot] = clock64() - tl_t0; } while (0)
+#else
+#define TL(role, j, slot) do {} while (0)
+#endif
 
 namespace {
 
@@ -113,6 +123,10 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     const int b = blockIdx.y / H, h = blockIdx.y - b * H;
     const int col0 = h * D;
     const int n_tiles = (Tk + C::BN - 1) / C::BN;
+#ifdef UCOD_ATT_TIMELINE
+    const bool tl_on = (blockIdx.x == 5 && blockIdx.y == 300) && (lane == 0);
+    const long long tl_t0 = clock64();
+#endif
 
     if (threadIdx.x == 0) {
         mbar_init(bar_q, 1);
@@ -141,7 +155,7 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     const uint32_t tmem_o = tmem_base + C::TM_O;
 
     if (warp < 4) {
-        reg_dec<48>();
+        reg_dec<80>();
         if (warp == 0 && lane == 0) {
             // ===================== TMA producer =====================
             tma_prefetch_desc(&tm_q);
@@ -155,12 +169,14 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                 const int st = j & 1;
                 const uint32_t ph = ((uint32_t)(j >> 1) & 1) ^ 1;
                 mbar_wait(&bar_kempty[st], ph);
+                TL(0, j, 0);
                 mbar_arrive_expect_tx(&bar_kfull[st], C::SK_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < C::NKB; ++kb)
                     tma_load_3d(sK + st * C::SK_BYTES + kb * C::BLK_BYTES, &tm_k, &bar_kfull[st], col0 + kb * 64,
                                 j * C::BN, b);
                 mbar_wait(&bar_vempty[st], ph);
+                TL(0, j, 1);
                 mbar_arrive_expect_tx(&bar_vfull[st], C::SV_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < C::NKB; ++kb)
@@ -192,12 +208,17 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                 const int st = j & 1;
                 if (j + 1 < n_tiles) {
                     mbar_wait(&bar_kfull[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    TL(1, j, 0);
                     mbar_wait(bar_sfree, j & 1);  // S_j is in the softmax warps' registers
+                    TL(1, j, 1);
                     tc_fence_after();
                     issue_s(j + 1);
+                    TL(1, j, 2);
                 }
                 mbar_wait(&bar_vfull[st], (j >> 1) & 1);
+                TL(1, j, 3);
                 mbar_wait(bar_p, j & 1);  // P_j published
+                TL(1, j, 4);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sV + st * C::SV_BYTES);
 #pragma unroll
@@ -206,23 +227,27 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                                  idesc_o, (j | k) != 0);
                 umma_commit(&bar_vempty[st]);
                 umma_commit(bar_pv);
+                TL(1, j, 5);
             }
         }
     } else {
         // ===================== softmax / correction / epilogue: one thread per query row ==============
-        reg_inc<208>();
+        reg_inc<176>();
         const int quarter = warp & 3;
         const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         float m_ref = 0.f, l_run = 0.f;
 
         for (int j = 0; j < n_tiles; ++j) {
+            TL(2, j, 0);
             mbar_wait(bar_s, j & 1);
+            TL(2, j, 1);
             tc_fence_after();
             uint32_t u[128];
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_ld32(tmem_s + lane_off + c * 32, reinterpret_cast<uint32_t(&)[32]>(u[32 * c]));
             tmem_wait_ld();
+            TL(2, j, 2);
             tc_fence_before();
             mbar_arrive(bar_sfree);
             const int valid = Tk - j * C::BN;  // keys valid in this tile (>= 1)
@@ -253,7 +278,9 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                     grow = true;
                 }
                 // previous P V must have retired before P is overwritten / O is rescaled
+                TL(2, j, 3);
                 mbar_wait(bar_pv, (j - 1) & 1);
+                TL(2, j, 4);
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, grow)) {
 #pragma unroll 1
@@ -284,9 +311,11 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                 tmem_st32(tmem_p + lane_off + half * 32, pk);
             }
             l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            TL(2, j, 5);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar_p);
+            TL(2, j, 6);
         }
 
         // ---- epilogue: O / l -> bf16 ctx ----
@@ -350,6 +379,12 @@ int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
 }
 
 }  // namespace
+
+#ifdef UCOD_ATT_TIMELINE
+extern "C" int ucod_debug_att_timeline(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_att_tl, sizeof(long long) * 3 * 16 * 8);
+}
+#endif
 
 int launch_attention(const AttentionArgs& a, cudaStream_t stream) {
     UCOD_REQUIRE(a.q && a.k && a.v && a.ctx, "attention: null pointer");

@@ -118,6 +118,18 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const void* desc, ui
         "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// L2 prefetch of a tensor-map box (no shared-memory destination): hides DRAM latency beyond the smem ring depth
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* desc, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(desc)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_3d(const void* desc, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(
+                     reinterpret_cast<uint64_t>(desc)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
 // generic-proxy smem writes -> visible to the async proxy (UMMA / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
