@@ -79,3 +79,53 @@ def random_vit_state_dict(spec, seed: int = 0, layerscale_init: float = 1.0) -> 
             sd[k["ls1"]] = layerscale_init * (1.0 + rn(D, std=0.1))
             sd[k["ls2"]] = layerscale_init * (1.0 + rn(D, std=0.1))
     return sd
+
+
+def random_refiner_state_dict(seed: int = 0, dim: int = 768) -> dict:
+    """Seeded random weights for the CORAL `SparseRefiner` under the reference's state_dict names
+    (weights/CORAL_dinov{1,2}.safetensors are not shipped — .MISSING_LARGE_BLOBS).  Scales keep activations O(1)."""
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=0.02):
+        return torch.randn(*shape, generator=g) * std
+
+    p = "HRE.CSF."
+    sd = {}
+    for n in ("norm_q", "norm_kv", "norm_mlp"):
+        sd[f"{p}attn.{n}.weight"] = 1.0 + rn(dim, std=0.1)
+        sd[f"{p}attn.{n}.bias"] = rn(dim, std=0.05)
+    sd[p + "attn.attn.in_proj_weight"] = rn(3 * dim, dim, std=0.04)
+    sd[p + "attn.attn.in_proj_bias"] = rn(3 * dim, std=0.05)
+    sd[p + "attn.attn.out_proj.weight"] = rn(dim, dim, std=0.04)
+    sd[p + "attn.attn.out_proj.bias"] = rn(dim, std=0.05)
+    sd[p + "attn.mlp.0.weight"] = rn(4 * dim, dim, std=0.03)
+    sd[p + "attn.mlp.0.bias"] = rn(4 * dim, std=0.05)
+    sd[p + "attn.mlp.2.weight"] = rn(dim, 4 * dim, std=0.02)
+    sd[p + "attn.mlp.2.bias"] = rn(dim, std=0.05)
+    sd[p + "depthwise_conv.weight"] = rn(dim, 1, 7, 7, std=0.1)
+    sd[p + "depthwise_conv.bias"] = rn(dim, std=0.05)
+    sd[p + "mask_dec.weight"] = rn(1, dim, 1, 1, std=0.05)
+    sd[p + "mask_dec.bias"] = rn(1, std=0.1)
+    sd["GE.alpha"] = torch.tensor(0.5)
+    sd["GE.fuser.0.weight"] = rn(64, 1, 1, 1, std=0.5)
+    sd["GE.fuser.0.bias"] = rn(64, std=0.3)
+    sd["GE.fuser.2.weight"] = rn(1, 64, 1, 1, std=0.3)
+    sd["GE.fuser.2.bias"] = rn(1, std=0.1)
+    return sd
+
+
+def synth_coral_inputs(seed: int, batch: int = 1, grid: int = 56, dim: int = 768, windows: int = 3,
+                       uncertain=((0, 1), (1, 1), (2, 0))):
+    """Seeded CORAL refiner inputs: l features [B,dim,g,g], h features [B,w*w,dim,g,g] and coarse logits [B,1,g,g]
+    that are confident (|logit| = 12) everywhere except inside the listed (row, col) windows, where they are
+    uncertain (|logit| < 1.5) — so the entropy selector picks exactly those windows."""
+    g = torch.Generator().manual_seed(seed)
+    l = torch.randn(batch, dim, grid, grid, generator=g)
+    h = torch.randn(batch, windows * windows, dim, grid, grid, generator=g)
+    preds = torch.full((batch, 1, grid, grid), -12.0)
+    preds[:, :, : grid // 2, : grid // 3] = 12.0
+    edges = [(i * grid) // windows for i in range(windows + 1)]
+    for (r, c) in uncertain:
+        y0, y1, x0, x1 = edges[r] + 1, edges[r + 1] - 1, edges[c] + 1, edges[c + 1] - 1
+        preds[:, :, y0:y1, x0:x1] = 1.5 * torch.randn(batch, 1, y1 - y0, x1 - x0, generator=g).clamp(-1, 1)
+    return l, h, preds
