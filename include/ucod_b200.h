@@ -54,6 +54,14 @@ int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n,
 int ucod_attention(const void* q, int ld_q, const void* k, const void* v, int ld_kv, void* ctx, int ld_ctx, int batch,
                    int heads, int head_dim, int tokens_q, int tokens_kv, float scale, void* stream);
 
+/* Same kernel with K/V shared between q batches: q batch b attends to K/V batch kv_batch_map[b] (device int32
+ * [batch], values < kv_batch).  head_dim_real <= head_dim documents zero-padded heads (FLOP accounting only).
+ * Used by the CORAL CSF block, where every selected window of an image attends to that image's low-res tokens
+ * (`repeat_interleave` of models/modules/ASR.py:24 without materialising the copies). */
+int ucod_attention_shared_kv(const void* q, int ld_q, const void* k, const void* v, int ld_kv, void* ctx, int ld_ctx,
+                             int batch, int heads, int head_dim, int head_dim_real, int tokens_q, int tokens_kv,
+                             float scale, const int32_t* kv_batch_map, int kv_batch, void* stream);
+
 /* ---- frozen ViT-B backbone: last-layer key tokens ---------------------------------------------
  * Replaces `backbone.__init__/forward` (data/utils/feature_extractor.py:31-59) and the hook + attentions of
  * generate_pseudo_label.py:24-27,76-81,111-112.  Weights are device pointers owned by the caller
@@ -193,6 +201,43 @@ int ucod_apm_binarize(const float* student, const float* teacher, const float* p
                       float* p_mask, uint64_t n, void* stream);
 int ucod_apm_merge(const float* pl, const float* t_mask, const float* p_s, const float* p_p, float epoch_term,
                    float* merged, float* weight, float* dis_loss, int batch, int pixels, void* stream);
+
+/* ---- CORAL second stage (SparseRefiner, eval) ----------------------------------------------------------
+ * The dense part of the CSF block (models/modules/CSF.py:38-43, mlp.py:134-148) is assembled by the host from
+ * ucod_layernorm_bf16 + ucod_gemm_bf16 + ucod_attention_shared_kv; the functions below are the remaining stages.
+ *
+ * `EntropySelector.forward` (models/modules/ASR.py:41-51): preds fp32 [batch,size,size] (logits, or probabilities
+ * when every value of the call lies in [0,1]); entropy fp32 [batch,size,size]; scores fp32 and mask uint8
+ * [batch, window_size^2] (adaptive average pool > threshold); scratch: 4 device bytes. */
+int ucod_coral_entropy_select(const float* preds, int batch, int size, int window_size, float threshold,
+                              float* entropy, float* scores, uint8_t* mask, void* scratch, void* stream);
+/* CSF tail (CSF.py:41-42): depthwise 7x7 (pad 3) + 1x1 mask_dec folded into 49 taps per token.
+ * taps fp32 [n_windows*grid*grid, ld_taps] (column ky*7+kx = sum_c mask_dec.w[c]*dw.w[c,ky,kx]*x[token,c]);
+ * out fp32 [n_windows, grid, grid] = bias_const + zero-padded 7x7 gather-sum. */
+int ucod_coral_window_head(const float* taps, int ld_taps, int n_windows, int grid, float bias_const, float* out,
+                           void* stream);
+/* `HRE.concate_windows` (models/modules/HRE.py:18-39): slot_of_cell int32 [batch, window_size^2] = index of the
+ * cell's window in window_preds [n,grid,grid] or -1; out fp32 [batch, window_size*grid, window_size*grid]. */
+int ucod_coral_scatter_windows(const float* window_preds, const int32_t* slot_of_cell, int batch, int window_size,
+                               int grid, float* out, void* stream);
+/* `GatedEnsembler.forward` (models/modules/GE_pix_level.py:16-26): preds fp32 [batch,preds_size,preds_size] coarse
+ * logits, h_preds fp32 [batch,size,size]; fuser weights w0[64], b0[64], w2[64], b2[1];
+ * out / weight fp32 [batch,size,size] (the entropy maximum is taken over the whole call, as in the reference). */
+uint64_t ucod_coral_gated_ensemble_workspace_bytes(int batch, int size);
+int ucod_coral_gated_ensemble(const float* preds, int preds_size, const float* h_preds, int batch, int size,
+                              const float* w0, const float* b0, const float* w2, const float* b2, float* out,
+                              float* weight, void* workspace, uint64_t workspace_bytes, void* stream);
+/* nn.LayerNorm over the last dim (dim % 128 == 0, <= 1024): x fp32 [rows,dim] -> y bf16 [rows,dim]. */
+int ucod_layernorm_bf16(const float* x, const float* weight, const float* bias, void* y, int rows, int dim, float eps,
+                        void* stream);
+int ucod_cast_f32_bf16(const float* in, void* out, uint64_t n, void* stream);
+/* NCHW-style [batch, channels, pixels] fp32 (element strides sb, sc, sp) -> token-major fp32 [batch, pixels, channels]. */
+int ucod_features_to_tokens_f32(const float* in, float* out, int batch, int channels, int pixels, int64_t sb,
+                                int64_t sc, int64_t sp, void* stream);
+/* F.interpolate(mode='bilinear') of token-major maps (engine/runner/loop_CORAL.py:224-227, loop_UCOD_DPL.py:305):
+ * in fp32 [n, gin_h*gin_w, channels] -> out_f32 and/or out_bf16 [n, gout_h*gout_w, channels] (either may be NULL). */
+int ucod_resize_tokens_bilinear(const float* in, float* out_f32, void* out_bf16, int n, int gin_h, int gin_w,
+                                int gout_h, int gout_w, int channels, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,98 @@
+"""CORAL SparseRefiner (CUDA) vs. the CPU oracle and the reference-generated golden vectors."""
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import coral as oc
+from ucod_dpl_b200 import ops
+from ucod_dpl_b200.models.UDLR import SparseRefiner
+from ucod_dpl_b200.synth import random_refiner_state_dict, synth_coral_inputs
+
+pytestmark = pytest.mark.gpu
+GOLD = Path(__file__).resolve().parents[1] / "tests" / "golden"
+
+
+@pytest.fixture(scope="module")
+def refiner():
+    r = SparseRefiner.from_config(SimpleNamespace(window_size=3, threshold=0.0015))
+    r.load_state_dict(random_refiner_state_dict(0), strict=True)
+    return r.cuda().eval()
+
+
+@pytest.mark.parametrize("P", [56, 102])
+def test_entropy_select_matches_oracle(P):
+    g = torch.Generator().manual_seed(P)
+    preds = torch.randn(3, 1, P, P, generator=g) * 6
+    preds[1] = 14.0
+    for x in (preds, preds.sigmoid()):   # logits and probabilities take different branches (ASR.py:42-45)
+        ent, scores, mask = ops.coral_entropy_select(x.cuda(), 0.0015, 3)
+        _, _, rmask, _, rent, rscores = oc.entropy_select(torch.zeros(3, 1, 1, 1), torch.zeros(3, 9, 1, 1, 1), x,
+                                                          0.0015, 3)
+        np.testing.assert_allclose(ent.cpu().numpy(), rent.numpy(), atol=2e-6)
+        np.testing.assert_allclose(scores.cpu().numpy(), rscores.numpy(), rtol=1e-4, atol=1e-7)
+        far = (rscores - 0.0015).abs() > 1e-5     # selection is exact wherever the score is not within rounding of the threshold
+        assert torch.equal(mask.cpu()[far], rmask[far])
+
+
+def test_gated_ensemble_and_scatter_match_oracle(refiner):
+    sd = random_refiner_state_dict(0)
+    g = torch.Generator().manual_seed(3)
+    preds = torch.randn(2, 1, 56, 56, generator=g) * 3
+    wins = torch.randn(3, 1, 56, 56, generator=g)
+    mask = torch.zeros(2, 1, 3, 3, dtype=torch.bool)
+    mask[0, 0, 0, 2] = mask[0, 0, 2, 1] = mask[1, 0, 1, 1] = True
+    coords = torch.tensor([[0, 2], [2, 1], [1, 1]])
+    ref_h = oc.concate_windows(wins, coords, mask, 3)
+    h = refiner.HRE.concate_windows(wins.cuda(), coords.cuda(), mask.cuda())
+    np.testing.assert_allclose(h.cpu().numpy(), ref_h.numpy(), atol=1e-6)
+    assert (h.cpu()[1, 0, :56] == 0).all()                      # unselected cells are exactly zero
+    ref_out, ref_w = oc.gated_ensembler(sd, preds, ref_h)
+    out, w = refiner.GE(preds.cuda(), h)
+    np.testing.assert_allclose(w.cpu().numpy(), ref_w.numpy(), atol=2e-5)
+    np.testing.assert_allclose(out.cpu().numpy(), ref_out.numpy(), atol=2e-4, rtol=1e-4)
+
+
+@pytest.mark.parametrize("tag,seed,batch,unc", [("a", 5, 1, ((0, 1), (1, 1), (2, 0))), ("b", 6, 2, ((1, 2),))])
+def test_sparse_refiner_matches_reference_golden(refiner, tag, seed, batch, unc):
+    gold = np.load(GOLD / "coral.npz")
+    l, h, preds = synth_coral_inputs(seed, batch=batch, uncertain=unc)
+    if tag == "b":
+        preds[1] = -12.0
+    out, ex_loss, opt = refiner(l.cuda(), h.cuda(), preds.cuda())
+    assert ex_loss == 0
+    assert np.array_equal(opt["mask"].cpu().numpy(), gold[tag + "_mask"])            # selection: bit-exact
+    assert np.array_equal(opt["coords_list"].cpu().numpy(), gold[tag + "_coords"])
+    wp, ref_wp = opt["window_preds"].cpu().numpy(), gold[tag + "_window_preds"]
+    assert wp.shape == ref_wp.shape
+    # bf16 tensor-core path vs fp32 reference: logits of O(1..10); tolerance 3e-2 * max|ref|
+    tol = 3e-2 * np.abs(ref_wp).max()
+    assert np.abs(wp - ref_wp).max() < tol, (np.abs(wp - ref_wp).max(), tol)
+    assert np.abs(out.cpu().numpy() - gold[tag + "_out"]).max() < 3e-2 * max(1.0, np.abs(gold[tag + "_out"]).max())
+    np.testing.assert_allclose(opt["GE_w"].cpu().numpy(), gold[tag + "_ge_w"], atol=2e-5)
+    # final masks (sigmoid > 0.5 of the refined logits) agree on >= 99.9 % of pixels
+    agree = ((out.cpu().numpy() > 0) == (gold[tag + "_out"] > 0)).mean()
+    assert agree >= 0.999, agree
+
+
+def test_token_entry_matches_nchw_entry(refiner):
+    l, h, preds = synth_coral_inputs(11, batch=1, uncertain=((0, 0), (2, 2)))
+    out1, _, _ = refiner(l.cuda(), h.cuda(), preds.cuda())
+    lt = ops.features_to_tokens_f32(l.cuda())
+    ht = ops.features_to_tokens_f32(h.cuda().flatten(0, 1)).reshape(1, 9, 56 * 56, 768)
+    out2, _, _ = refiner.forward_tokens(lt, ht, preds.cuda(), 56)
+    # identical up to the order of the atomically accumulated global sums in the gated ensemble
+    assert (out1 - out2).abs().max().item() < 1e-4
+
+
+def test_resize_tokens_matches_interpolate():
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(2, 768, 37, 37, generator=g)
+    ref = torch.nn.functional.interpolate(x, size=(56, 56), mode="bilinear")
+    tok = ops.features_to_tokens_f32(x.cuda())
+    o32, o16 = ops.resize_tokens_bilinear(tok, (37, 37), (56, 56), want_f32=True, want_bf16=True)
+    got = o32.reshape(2, 56, 56, 768).permute(0, 3, 1, 2).cpu()
+    np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-5)
+    assert (o16.float().cpu() - o32.cpu()).abs().max() < 0.04

@@ -61,7 +61,7 @@ def test_cfgnode_semantics(tmp_path):
 def test_registries_are_populated():
     import ucod_dpl_b200.dropin  # noqa: F401  (imports every hot-path module so that it registers itself)
     from ucod_dpl_b200.engine.registry import BACKBONE_REGISTRY, DATASET_REGISTRY, HOOK_REGISTRY, MODULE_REGISTRY, Registry
-    for n in ("baseline", "RevDecoder", "Discriminator"):
+    for n in ("baseline", "RevDecoder", "Discriminator", "SparseRefiner"):
         assert n in MODULE_REGISTRY
     assert "backbone" in BACKBONE_REGISTRY
     assert len(DATASET_REGISTRY) == 0 and len(HOOK_REGISTRY) == 0
@@ -103,6 +103,16 @@ def test_discriminator_layout():
     assert d.linear.in_features == 2312
 
 
+def test_refiner_state_dict_layout():
+    import numpy as np
+    from ucod_dpl_b200.models.UDLR import SparseRefiner
+    from ucod_dpl_b200.synth import random_refiner_state_dict
+    r = SparseRefiner.from_config(SimpleNamespace(window_size=3, threshold=0.0015))
+    want = list(np.load(GOLD / "coral.npz")["state_dict_keys"])   # keys of the reference module
+    assert sorted(r.state_dict().keys()) == want
+    r.load_state_dict(random_refiner_state_dict(0), strict=True)
+
+
 def test_reference_module_paths_alias():
     """`ucod_dpl_b200.dropin.install()` makes the reference's import paths resolve to this package."""
     import sys
@@ -112,6 +122,8 @@ def test_reference_module_paths_alias():
         dropin.install()
         from models.uscod import baseline  # noqa
         from models.discriminator import Discriminator  # noqa
+        from models.UDLR import SparseRefiner  # noqa
+        from models.modules.CSF import CSF  # noqa
         from data.utils.feature_extractor import backbone  # noqa
         from data.utils.found_bkg_mask import compute_img_bkg_seg  # noqa
         from engine.config import CfgNode  # noqa

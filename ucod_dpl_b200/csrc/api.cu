@@ -2,6 +2,7 @@
 #include "../../include/ucod_b200.h"
 #include "gemm.cuh"
 #include "attention.cuh"
+#include "coral.cuh"
 #include "vit.cuh"
 #include "decoder.cuh"
 #include "prof.cuh"
@@ -37,12 +38,20 @@ int ucod_gemm_bf16(const void* a, int lda, const void* w, int ldw, int m, int n,
 
 int ucod_attention(const void* q, int ld_q, const void* k, const void* v, int ld_kv, void* ctx, int ld_ctx, int batch,
                    int heads, int head_dim, int tokens_q, int tokens_kv, float scale, void* stream) {
+    return ucod_attention_shared_kv(q, ld_q, k, v, ld_kv, ctx, ld_ctx, batch, heads, head_dim, head_dim, tokens_q,
+                                    tokens_kv, scale, nullptr, 0, stream);
+}
+int ucod_attention_shared_kv(const void* q, int ld_q, const void* k, const void* v, int ld_kv, void* ctx, int ld_ctx,
+                             int batch, int heads, int head_dim, int head_dim_real, int tokens_q, int tokens_kv,
+                             float scale, const int32_t* kv_batch_map, int kv_batch, void* stream) {
     AttentionArgs a;
     a.q = q, a.k = k, a.v = v, a.ctx = ctx;
     a.batch = batch, a.heads = heads, a.tokens_q = tokens_q, a.tokens_kv = tokens_kv;
-    a.head_dim = head_dim, a.head_dim_real = head_dim;
+    a.head_dim = head_dim, a.head_dim_real = head_dim_real;
     a.ld_q = ld_q, a.ld_kv = ld_kv, a.ld_ctx = ld_ctx;
     a.scale = scale;
+    a.kv_batch_map = kv_batch_map;
+    a.kv_batch = kv_batch;
     return launch_attention(a, reinterpret_cast<cudaStream_t>(stream));
 }
 
@@ -152,6 +161,48 @@ int ucod_apm_merge(const float* pl, const float* t_mask, const float* p_s, const
                    float* merged, float* weight, float* dis_loss, int batch, int pixels, void* stream) {
     return apm_merge(pl, t_mask, p_s, p_p, epoch_term, merged, weight, dis_loss, batch, pixels,
                      reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- CORAL second stage ----
+int ucod_coral_entropy_select(const float* preds, int batch, int size, int window_size, float threshold,
+                              float* entropy, float* scores, uint8_t* mask, void* scratch, void* stream) {
+    return coral_entropy_select(preds, batch, size, window_size, threshold, entropy, scores, mask,
+                                static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_coral_window_head(const float* taps, int ld_taps, int n_windows, int grid, float bias_const, float* out,
+                           void* stream) {
+    return coral_window_head(taps, ld_taps, n_windows, grid, bias_const, out, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_coral_scatter_windows(const float* window_preds, const int32_t* slot_of_cell, int batch, int window_size,
+                               int grid, float* out, void* stream) {
+    return coral_scatter_windows(window_preds, slot_of_cell, batch, window_size, grid, out,
+                                 reinterpret_cast<cudaStream_t>(stream));
+}
+uint64_t ucod_coral_gated_ensemble_workspace_bytes(int batch, int size) {
+    return (uint64_t)coral_gated_ensemble_workspace_bytes(batch, size);
+}
+int ucod_coral_gated_ensemble(const float* preds, int preds_size, const float* h_preds, int batch, int size,
+                              const float* w0, const float* b0, const float* w2, const float* b2, float* out,
+                              float* weight, void* workspace, uint64_t workspace_bytes, void* stream) {
+    return coral_gated_ensemble(preds, preds_size, h_preds, batch, size, w0, b0, w2, b2, out, weight, workspace,
+                                (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_layernorm_bf16(const float* x, const float* weight, const float* bias, void* y, int rows, int dim, float eps,
+                        void* stream) {
+    return layernorm_rows_bf16(x, weight, bias, y, rows, dim, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_cast_f32_bf16(const float* in, void* out, uint64_t n, void* stream) {
+    return cast_f32_to_bf16(in, out, (size_t)n, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_features_to_tokens_f32(const float* in, float* out, int batch, int channels, int pixels, int64_t sb,
+                                int64_t sc, int64_t sp, void* stream) {
+    return features_to_tokens_f32(in, out, batch, channels, pixels, sb, sc, sp,
+                                  reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_resize_tokens_bilinear(const float* in, float* out_f32, void* out_bf16, int n, int gin_h, int gin_w,
+                                int gout_h, int gout_w, int channels, void* stream) {
+    return resize_tokens_bilinear(in, out_f32, out_bf16, n, gin_h, gin_w, gout_h, gout_w, channels,
+                                  reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

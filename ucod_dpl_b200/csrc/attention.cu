@@ -99,7 +99,7 @@ template <int D>
 __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                          const __grid_constant__ CUtensorMap tm_v, __nv_bfloat16* __restrict__ ctx, int Tq, int Tk,
-                         int H, int ld_ctx, float scale_log2e) {
+                         int H, int ld_ctx, float scale_log2e, const int* __restrict__ kv_map) {
     using C = AttCfg<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             tma_prefetch_desc(&tm_q);
             tma_prefetch_desc(&tm_k);
             tma_prefetch_desc(&tm_v);
+            const int bkv = kv_map != nullptr ? __ldg(kv_map + b) : b;
             mbar_arrive_expect_tx(bar_q, C::SQ_BYTES);
 #pragma unroll
             for (int kb = 0; kb < C::NKB; ++kb)
@@ -174,14 +175,14 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
 #pragma unroll
                 for (int kb = 0; kb < C::NKB; ++kb)
                     tma_load_3d(sK + st * C::SK_BYTES + kb * C::BLK_BYTES, &tm_k, &bar_kfull[st], col0 + kb * 64,
-                                j * C::BN, b);
+                                j * C::BN, bkv);
                 mbar_wait(&bar_vempty[st], ph);
                 TL(0, j, 1);
                 mbar_arrive_expect_tx(&bar_vfull[st], C::SV_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < C::NKB; ++kb)
                     tma_load_3d(sV + st * C::SV_BYTES + kb * C::BLK_BYTES, &tm_v, &bar_vfull[st], col0 + kb * 64,
-                                j * C::BN, b);
+                                j * C::BN, bkv);
             }
         } else if (warp == 1 && lane == 0) {
             // ===================== MMA issuer =====================
@@ -356,10 +357,10 @@ int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
     if (int rc = make_tmap_3d_bf16(&tq, a.q, (uint64_t)a.batch, (uint64_t)a.tokens_q, cols, (uint64_t)a.ld_q,
                                    (uint64_t)a.tokens_q * a.ld_q, C::BM, 64))
         return rc;
-    if (int rc = make_tmap_3d_bf16(&tk, a.k, (uint64_t)a.batch, (uint64_t)a.tokens_kv, cols, (uint64_t)a.ld_kv,
+    if (int rc = make_tmap_3d_bf16(&tk, a.k, (uint64_t)(a.kv_batch > 0 ? a.kv_batch : a.batch), (uint64_t)a.tokens_kv, cols, (uint64_t)a.ld_kv,
                                    (uint64_t)a.tokens_kv * a.ld_kv, C::BN, 64))
         return rc;
-    if (int rc = make_tmap_3d_bf16(&tv, a.v, (uint64_t)a.batch, (uint64_t)a.tokens_kv, cols, (uint64_t)a.ld_kv,
+    if (int rc = make_tmap_3d_bf16(&tv, a.v, (uint64_t)(a.kv_batch > 0 ? a.kv_batch : a.batch), (uint64_t)a.tokens_kv, cols, (uint64_t)a.ld_kv,
                                    (uint64_t)a.tokens_kv * a.ld_kv, C::BN, 64))
         return rc;
     auto kern = attention_fwd_kernel<D>;
@@ -372,7 +373,8 @@ int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
     {
         ProfScope ps(KC_ATTENTION, stream, 4.0 * a.batch * a.heads * (double)a.tokens_q * a.tokens_kv * a.head_dim_real);
         kern<<<grid, C::THREADS, C::SMEM, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(a.ctx), a.tokens_q,
-                                                     a.tokens_kv, a.heads, a.ld_ctx, a.scale * 1.4426950408889634f);
+                                                     a.tokens_kv, a.heads, a.ld_ctx, a.scale * 1.4426950408889634f,
+                                                     a.kv_batch_map);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -17,6 +17,8 @@ struct AttentionArgs {
     int head_dim = 64, head_dim_real = 64;
     int ld_q = 0, ld_kv = 0, ld_ctx = 0;
     float scale = 0.125f;
+    int kv_batch = 0;                   // number of K/V batches when kv_batch_map is used (0: same as batch)
+    const int* kv_batch_map = nullptr;  // optional [batch]: K/V batch index of each q batch (cross-attention sharing)
 };
 int launch_attention(const AttentionArgs& args, cudaStream_t stream);
 

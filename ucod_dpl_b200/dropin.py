@@ -23,8 +23,14 @@ ALIASES = {
     "models": "ucod_dpl_b200.models",
     "models.uscod": "ucod_dpl_b200.models.uscod",
     "models.discriminator": "ucod_dpl_b200.models.discriminator",
+    "models.UDLR": "ucod_dpl_b200.models.UDLR",
     "models.modules": "ucod_dpl_b200.models.modules",
     "models.modules.DBA": "ucod_dpl_b200.models.modules.DBA",
+    "models.modules.ASR": "ucod_dpl_b200.models.modules.refiner",
+    "models.modules.HRE": "ucod_dpl_b200.models.modules.refiner",
+    "models.modules.CSF": "ucod_dpl_b200.models.modules.refiner",
+    "models.modules.GE_pix_level": "ucod_dpl_b200.models.modules.refiner",
+    "models.modules.mlp": "ucod_dpl_b200.models.modules.refiner",
     "data": "ucod_dpl_b200.data",
     "data.utils": "ucod_dpl_b200.data.utils",
     "data.utils.feature_extractor": "ucod_dpl_b200.data.utils.feature_extractor",

@@ -258,3 +258,148 @@ def apm_merge(pl: torch.Tensor, t_mask: torch.Tensor, p_s: torch.Tensor, p_p: to
                   ptr(p_p.float().contiguous()), c_float(epoch_term), ptr(merged), ptr(weight), ptr(loss), B, npix,
                   stream_ptr(pl.device))
     return merged, weight, loss
+
+
+# ------------------------------------------------------------------------------------------------
+# dense building blocks (host-assembled blocks: CORAL CSF)
+def gemm_bf16(a: torch.Tensor, w: torch.Tensor, mode: int, bias: torch.Tensor | None = None,
+              out: torch.Tensor | None = None) -> torch.Tensor:
+    """out = epilogue(a @ w.T): a [M,K] bf16, w [N,K] bf16 (row pitches may exceed K).  mode 0: bf16 (+bias),
+    1: bf16 gelu(+bias), 2: fp32 `out += acc + bias` (out required), 5: fp32 (+bias)."""
+    _lib.require_cuda(a, w)
+    M, K = a.shape
+    N = w.shape[0]
+    if out is None:
+        if mode == 2:
+            raise UcodError("gemm_bf16 mode 2 accumulates into `out`")
+        out = torch.empty(M, N, device=a.device, dtype=torch.float32 if mode == 5 else torch.bfloat16)
+    with torch.cuda.device(a.device):
+        _lib.call("ucod_gemm_bf16", ptr(a), a.stride(0), ptr(w), w.stride(0), M, N, K, int(mode), ptr(bias), ptr(out),
+                  out.stride(0), stream_ptr(a.device))
+    return out
+
+
+def layernorm_bf16(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float) -> torch.Tensor:
+    """x fp32 [rows, dim] contiguous -> bf16 [rows, dim]."""
+    _lib.require_cuda(x)
+    rows, dim = x.shape
+    y = torch.empty(rows, dim, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.call("ucod_layernorm_bf16", ptr(x), ptr(weight), ptr(bias), ptr(y), rows, dim, c_float(eps),
+                  stream_ptr(x.device))
+    return y
+
+
+def cast_bf16(x: torch.Tensor) -> torch.Tensor:
+    _lib.require_cuda(x)
+    x = x.contiguous()
+    y = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.call("ucod_cast_f32_bf16", ptr(x), ptr(y), _u64(x.numel()), stream_ptr(x.device))
+    return y
+
+
+def features_to_tokens_f32(features: torch.Tensor) -> torch.Tensor:
+    """[B,C,H,W] fp32 -> token-major fp32 [B,H*W,C]."""
+    _lib.require_cuda(features)
+    features = features.float()
+    B, C, H, W = features.shape
+    if features.stride(2) != W * features.stride(3):
+        features = features.contiguous()
+    out = torch.empty(B, H * W, C, device=features.device, dtype=torch.float32)
+    with torch.cuda.device(features.device):
+        _lib.call("ucod_features_to_tokens_f32", ptr(features), ptr(out), B, C, H * W, _i64(features.stride(0)),
+                  _i64(features.stride(1)), _i64(features.stride(3)), stream_ptr(features.device))
+    return out
+
+
+def resize_tokens_bilinear(tokens: torch.Tensor, grid_in, grid_out, want_f32: bool = True, want_bf16: bool = False):
+    """tokens fp32 [n, gh*gw, C] -> (fp32 | None, bf16 | None) on the `grid_out` grid (bilinear, align_corners=False)."""
+    _lib.require_cuda(tokens)
+    tokens = tokens.float().contiguous()
+    n, P, C = tokens.shape
+    (gh, gw), (oh, ow) = grid_in, grid_out
+    if gh * gw != P:
+        raise UcodError("resize_tokens_bilinear: token count does not match the input grid")
+    o32 = torch.empty(n, oh * ow, C, device=tokens.device, dtype=torch.float32) if want_f32 else None
+    o16 = torch.empty(n, oh * ow, C, device=tokens.device, dtype=torch.bfloat16) if want_bf16 else None
+    with torch.cuda.device(tokens.device):
+        _lib.call("ucod_resize_tokens_bilinear", ptr(tokens), ptr(o32), ptr(o16), n, gh, gw, oh, ow, C,
+                  stream_ptr(tokens.device))
+    return o32, o16
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, head_dim: int, scale: float,
+              kv_batch_map: torch.Tensor | None = None, head_dim_real: int | None = None) -> torch.Tensor:
+    """q [B,Tq,>=heads*head_dim] bf16, k / v [Bkv,Tk,...] bf16 views with the same row pitch -> ctx bf16
+    [B,Tq,heads*head_dim].  `kv_batch_map` int32 [B]: K/V batch of each q batch."""
+    _lib.require_cuda(q, k, v)
+    B, Tq = q.shape[0], q.shape[1]
+    Bkv, Tk = k.shape[0], k.shape[1]
+    if k.stride(1) != v.stride(1) or q.stride(2) != 1 or k.stride(2) != 1 or v.stride(2) != 1:
+        raise UcodError("attention: k and v must share a row pitch and be unit-stride in the last dim")
+    if q.stride(0) != Tq * q.stride(1) or k.stride(0) != Tk * k.stride(1):
+        raise UcodError("attention: batch stride must equal tokens * row pitch")
+    ctx = torch.empty(B, Tq, heads * head_dim, device=q.device, dtype=torch.bfloat16)
+    with torch.cuda.device(q.device):
+        _lib.call("ucod_attention_shared_kv", ptr(q), q.stride(1), ptr(k), ptr(v), k.stride(1), ptr(ctx),
+                  heads * head_dim, B, heads, head_dim, int(head_dim_real or head_dim), Tq, Tk, c_float(scale),
+                  ptr(kv_batch_map), Bkv if kv_batch_map is not None else 0, stream_ptr(q.device))
+    return ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# CORAL second stage
+def coral_entropy_select(preds: torch.Tensor, threshold: float, window_size: int):
+    """preds [B,1,P,P] -> (entropy [B,1,P,P], scores [B,1,w,w], mask bool [B,1,w,w])."""
+    _lib.require_cuda(preds)
+    p = preds.float().contiguous()
+    B, _, P, _ = p.shape
+    dev = p.device
+    entropy = torch.empty_like(p)
+    scores = torch.empty(B, 1, window_size, window_size, device=dev, dtype=torch.float32)
+    mask = torch.empty(B, 1, window_size, window_size, device=dev, dtype=torch.uint8)
+    scratch = torch.empty(1, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_coral_entropy_select", ptr(p), B, P, window_size, c_float(threshold), ptr(entropy),
+                  ptr(scores), ptr(mask), ptr(scratch), stream_ptr(dev))
+    return entropy, scores, mask.bool()
+
+
+def coral_window_head(taps: torch.Tensor, n_windows: int, grid: int, bias_const: float) -> torch.Tensor:
+    _lib.require_cuda(taps)
+    out = torch.empty(n_windows, 1, grid, grid, device=taps.device, dtype=torch.float32)
+    with torch.cuda.device(taps.device):
+        _lib.call("ucod_coral_window_head", ptr(taps), taps.stride(0), n_windows, grid, c_float(bias_const), ptr(out),
+                  stream_ptr(taps.device))
+    return out
+
+
+def coral_scatter_windows(window_preds: torch.Tensor | None, slot_of_cell: torch.Tensor, batch: int, window_size: int,
+                          grid: int) -> torch.Tensor:
+    _lib.require_cuda(slot_of_cell)
+    dev = slot_of_cell.device
+    S = window_size * grid
+    out = torch.empty(batch, 1, S, S, device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_coral_scatter_windows", ptr(window_preds), ptr(slot_of_cell), batch, window_size, grid,
+                  ptr(out), stream_ptr(dev))
+    return out
+
+
+def coral_gated_ensemble(preds: torch.Tensor, h_preds: torch.Tensor, w0, b0, w2, b2):
+    """preds [B,1,P,P], h_preds [B,1,S,S] -> (out [B,1,S,S], weight [B,1,S,S])."""
+    _lib.require_cuda(preds, h_preds)
+    p, h = preds.float().contiguous(), h_preds.float().contiguous()
+    B, _, P, _ = p.shape
+    S = h.shape[-1]
+    dev = p.device
+    out, weight = torch.empty_like(h), torch.empty_like(h)
+    lib = _lib.load()
+    lib.ucod_coral_gated_ensemble_workspace_bytes.restype = _u64
+    ws = _ws(lib.ucod_coral_gated_ensemble_workspace_bytes(B, S), dev)
+    wp, wn = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_coral_gated_ensemble", ptr(p), P, ptr(h), B, S, ptr(w0), ptr(b0), ptr(w2), ptr(b2), ptr(out),
+                  ptr(weight), wp, wn, stream_ptr(dev))
+    return out, weight
