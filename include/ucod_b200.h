@@ -122,7 +122,9 @@ int ucod_features_to_tokens_bf16(const float* in, void* out, int batch, int chan
                                  int64_t sc, int64_t sp, void* stream);
 
 /* F.interpolate(mode='bilinear', align_corners=False) of [batch,in_h,in_w] fp32.  binarize = 0: fp32 output;
- * binarize = 1: uint8 {0,1} mask of `sigmoid(x) > 0.5` (engine/runner/loop_UCOD_DPL.py:356-361). */
+ * binarize = 1: uint8 {0,1} mask of `sigmoid(up(x)) > 0.5` (engine/runner/loop_UCOD_DPL.py:356-361);
+ * binarize = 2: mask of `up(sigmoid(x)) > 0.5`, binarize = 3: mask of `up(x) > 0.5` for inputs that already are
+ * probabilities (the two branches of engine/runner/loop_CORAL.py:331-340). */
 int ucod_upsample_bilinear(const float* in, void* out, int batch, int in_h, int in_w, int out_h, int out_w,
                            int binarize, void* stream);
 

@@ -24,3 +24,43 @@ def first_stage_eval(vit_sd, spec, dec_sd, images_u8: torch.Tensor, image_size, 
     up = odec.upsample_bilinear(fg, image_size)
     mask = (torch.sigmoid(up) > 0.5).squeeze(1).to(torch.uint8)
     return {"keys": keys, "logits": fg, "mask": mask}
+
+
+@torch.no_grad()
+def coral_eval(vit_sd, spec, dec_sd, ref_sd, image_u8_hwc, image_size: int, label_size, window_size: int = 3,
+               window_length: int = 56, threshold: float = 0.0015):
+    """Second-stage eval of ONE image (require_m_patches=False): data/datasets/lr_dataset.py:82-152 feature
+    production + engine/runner/loop_CORAL.py:130-166.  image_u8_hwc: numpy [H0,W0,3] uint8."""
+    import numpy as np
+
+    from . import coral as oc
+    from . import pil_resample as pr
+
+    S, ws, g = image_size, window_size, window_length
+
+    def features(img):
+        low = pr.resize_u8(img, S, S, "bilinear")                      # transforms.Resize((S,S)) on the PIL image
+        big = pr.resize_u8(img, S * ws, S * ws, "bilinear")            # self.resize_img, lr_dataset.py:57-63
+        wins = [big[i * S:(i + 1) * S, j * S:(j + 1) * S] for i in range(ws) for j in range(ws)]
+        batch = torch.from_numpy(np.stack([low] + wins)).permute(0, 3, 1, 2)
+        keys = ovit.keys_to_map(ovit.vit_forward(vit_sd, spec, ovit.normalize_u8(batch))["key_tokens"])
+        return keys[:1], keys[1:].unsqueeze(0)
+
+    def prepare(l, h):
+        lf = odec.upsample_bilinear(l, (g, g))
+        hf = odec.upsample_bilinear(h.flatten(0, 1), (g, g)).reshape(1, ws * ws, -1, g, g)
+        preds, _, _ = odec.baseline_forward(dec_sd, lf, want_ortho=False)
+        return lf, hf, preds
+
+    lf, hf, preds = prepare(*features(image_u8_hwc))
+    coarse = preds
+    crop = oc.should_crop_center(preds)
+    if crop:
+        H0, W0 = image_u8_hwc.shape[:2]
+        nh, nw = H0 // 2, W0 // 2
+        top, left = (H0 - nh) // 2, (W0 - nw) // 2
+        lf, hf, preds = prepare(*features(image_u8_hwc[top:top + nh, left:left + nw]))
+    out, opt = oc.sparse_refiner_forward(ref_sd, lf, hf, preds, threshold, ws)
+    if crop:
+        out = oc.center_pad(out)
+    return {"coarse": coarse, "crop": crop, "refined": out, "mask": oc.process_preds(out, label_size), "opt": opt}

@@ -96,3 +96,52 @@ def test_resize_tokens_matches_interpolate():
     got = o32.reshape(2, 56, 56, 768).permute(0, 3, 1, 2).cpu()
     np.testing.assert_allclose(got.numpy(), ref.numpy(), atol=1e-5)
     assert (o16.float().cpu() - o32.cpu()).abs().max() < 0.04
+
+
+def test_coral_evaluator_end_to_end():
+    """Whole second-stage eval of one image vs the CPU oracle pipeline (random-init ViT-B/14 + shipped decoder +
+    seeded refiner).  bf16 backbone vs fp32 oracle: coarse logits within tolerance, final masks >= 98 % equal."""
+    from safetensors.torch import load_file
+    from oracle import pipeline as opipe
+    from oracle import vit as ovit
+    from ucod_dpl_b200.engine.runner.loop_CORAL import CoralEvaluator
+    from ucod_dpl_b200.models.uscod import baseline
+    from ucod_dpl_b200.synth import random_vit_state_dict, synth_image_u8
+    from ucod_dpl_b200.vit import VitKeyExtractor, spec_for
+    root = Path(__file__).resolve().parents[1]
+    S = 224                                     # small network size keeps the CPU oracle (10 ViT passes) fast
+    img = synth_image_u8(3, 300, 340)           # [3,H0,W0] uint8
+    vit_sd = random_vit_state_dict(spec_for("dinov2"), seed=0)
+    dec_sd = load_file(str(root / "weights" / "UCOD_DPL_dinov2.safetensors"))
+    ref_sd = random_refiner_state_dict(0)
+    model = baseline(SimpleNamespace(dim=768))
+    model.load_state_dict(dec_sd, strict=True)
+    refiner = SparseRefiner.from_config(SimpleNamespace(window_size=3, threshold=0.0015))
+    refiner.load_state_dict(ref_sd, strict=True)
+    ev = CoralEvaluator(VitKeyExtractor(vit_sd, spec_for("dinov2")), model.cuda().eval(), refiner.cuda().eval(),
+                        (S, S), window_size=3, window_length=56)
+    results, crop = ev.refine(img.unsqueeze(0).cuda())
+    masks = ev(img.unsqueeze(0).cuda(), label_sizes=[(300, 340)])
+    ref = opipe.coral_eval(vit_sd, ovit.spec_for("dinov2"), dec_sd, ref_sd, img.permute(1, 2, 0).numpy(), S, (300, 340))
+    assert bool(crop[0]) == ref["crop"]
+    got = results[0].cpu()
+    assert got.shape == ref["refined"].shape
+    scale = ref["refined"].abs().max().item()
+    assert (got - ref["refined"]).abs().max().item() < 0.1 * max(scale, 1.0)
+    agree = (masks[0].cpu().float() == ref["mask"][0]).float().mean().item()
+    assert agree >= 0.98, agree
+
+
+def test_coral_glue_matches_oracle():
+    from ucod_dpl_b200.engine.runner.loop_CORAL import CoralEvaluator as CE
+    gold = np.load(GOLD / "coral.npz")
+    g = torch.Generator().manual_seed(9)
+    p4 = torch.randn(2, 4, 1, 68, 68, generator=g)
+    np.testing.assert_allclose(CE.concate_preds(p4.cuda()).cpu().numpy(), gold["concate_preds_out"], atol=1e-6)
+    x = torch.randn(1, 1, 168, 168, generator=g)
+    assert np.array_equal(CE._center_pad(x.cuda()).cpu().numpy(), gold["center_pad_out"])
+    m = CE.process_preds(x.cuda(), (300, 417)).cpu().numpy().astype(np.float32)
+    want = gold["process_preds_out"]
+    assert (m != want).mean() < 2e-4        # fp32 sigmoid/interp rounding exactly at the 0.5 boundary only
+    mp = CE.process_preds(x.sigmoid().cuda(), (300, 417)).cpu().numpy().astype(np.float32)
+    assert (mp != want).mean() < 2e-4

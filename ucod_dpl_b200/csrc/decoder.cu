@@ -329,8 +329,13 @@ __global__ void upsample_bilinear_kernel(const float* __restrict__ in, void* __r
         float lx;
         bilinear_tap(ox < out_w ? ox : out_w - 1, in_w, out_w, x0, x1, lx);
         const float hx = 1.f - lx, hy = 1.f - ly;
-        v[i] = hy * (hx * __ldg(src + y0 * in_w + x0) + lx * __ldg(src + y0 * in_w + x1)) +
-               ly * (hx * __ldg(src + y1 * in_w + x0) + lx * __ldg(src + y1 * in_w + x1));
+        float t00 = __ldg(src + y0 * in_w + x0), t01 = __ldg(src + y0 * in_w + x1);
+        float t10 = __ldg(src + y1 * in_w + x0), t11 = __ldg(src + y1 * in_w + x1);
+        if constexpr (MODE == 2) {  // probabilities first, then interpolate (loop_CORAL.py:331-338)
+            t00 = 1.f / (1.f + expf(-t00)), t01 = 1.f / (1.f + expf(-t01));
+            t10 = 1.f / (1.f + expf(-t10)), t11 = 1.f / (1.f + expf(-t11));
+        }
+        v[i] = hy * (hx * t00 + lx * t01) + ly * (hx * t10 + lx * t11);
     }
     const size_t o = ((size_t)b * out_h + oy) * out_w + ox0;
     if constexpr (MODE == 0) {
@@ -338,7 +343,8 @@ __global__ void upsample_bilinear_kernel(const float* __restrict__ in, void* __r
         for (int i = 0; i < 4 && ox0 + i < out_w; ++i) dst[i] = v[i];
     } else {
         uint8_t* dst = static_cast<uint8_t*>(out) + o;
-        for (int i = 0; i < 4 && ox0 + i < out_w; ++i) dst[i] = v[i] > UCOD_SIGMOID_HALF_THRESHOLD ? 1 : 0;
+        for (int i = 0; i < 4 && ox0 + i < out_w; ++i)
+            dst[i] = (MODE == 1 ? v[i] > UCOD_SIGMOID_HALF_THRESHOLD : v[i] > 0.5f) ? 1 : 0;
     }
 }
 
@@ -347,8 +353,13 @@ int upsample_bilinear(const float* in, void* out, int B, int in_h, int in_w, int
     UCOD_REQUIRE(in && out && B > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0, "upsample: bad argument");
     dim3 block(128), grid(ceil_div(ceil_div(out_w, 4), 128), out_h, B);
     ProfScope ps(KC_RESAMPLE, stream, (double)B * in_h * in_w * 4 + (double)B * out_h * out_w * (binarize ? 1 : 4));
-    if (binarize)
+    UCOD_REQUIRE(binarize >= 0 && binarize <= 3, "upsample: binarize mode %d unknown", binarize);
+    if (binarize == 1)
         upsample_bilinear_kernel<1><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
+    else if (binarize == 2)
+        upsample_bilinear_kernel<2><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
+    else if (binarize == 3)
+        upsample_bilinear_kernel<3><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
     else
         upsample_bilinear_kernel<0><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
     UCOD_CHECK_CUDA(cudaGetLastError());

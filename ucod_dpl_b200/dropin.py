@@ -20,6 +20,7 @@ ALIASES = {
     "engine.registry.root": "ucod_dpl_b200.engine.registry.root",
     "engine.runner": "ucod_dpl_b200.engine.runner",
     "engine.runner.loop_UCOD_DPL": "ucod_dpl_b200.engine.runner.loop_UCOD_DPL",
+    "engine.runner.loop_CORAL": "ucod_dpl_b200.engine.runner.loop_CORAL",
     "models": "ucod_dpl_b200.models",
     "models.uscod": "ucod_dpl_b200.models.uscod",
     "models.discriminator": "ucod_dpl_b200.models.discriminator",

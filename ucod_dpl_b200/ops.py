@@ -67,9 +67,9 @@ def decoder_forward(keys_bf16: torch.Tensor, grid_in, grid_out, w_dec_bf16, b_de
     return fg, bg, ortho
 
 
-def upsample_bilinear(x: torch.Tensor, size, binarize: bool = False) -> torch.Tensor:
+def upsample_bilinear(x: torch.Tensor, size, binarize=False) -> torch.Tensor:
     """F.interpolate(x, size, mode='bilinear', align_corners=False) for [B,1,h,w] / [B,h,w] fp32 maps;
-    `binarize=True` returns the uint8 mask sigmoid(x) > 0.5 instead."""
+    `binarize=True|1` returns the uint8 mask sigmoid(up(x)) > 0.5, 2: up(sigmoid(x)) > 0.5, 3: up(x) > 0.5."""
     _lib.require_cuda(x)
     shp = x.shape
     x3 = x.reshape(-1, shp[-2], shp[-1]).float().contiguous()
@@ -77,7 +77,7 @@ def upsample_bilinear(x: torch.Tensor, size, binarize: bool = False) -> torch.Te
     out = torch.empty(x3.shape[0], oh, ow, device=x.device, dtype=torch.uint8 if binarize else torch.float32)
     with torch.cuda.device(x.device):
         _lib.call("ucod_upsample_bilinear", ptr(x3), ptr(out), x3.shape[0], shp[-2], shp[-1], oh, ow,
-                  1 if binarize else 0, stream_ptr(x.device))
+                  int(binarize), stream_ptr(x.device))
     return out.reshape(*shp[:-2], oh, ow)
 
 
