@@ -298,6 +298,13 @@ def main():
         fn()
         print("wrote", name, flush=True)
     try:
+        from tools.make_golden_train import gold_train
+        if not only or "train" in only:
+            gold_train()
+            print("wrote train", flush=True)
+    except ImportError:
+        pass
+    try:
         from tools.make_golden_coral import gold_coral
         if not only or "coral" in only:
             gold_coral()
