@@ -204,6 +204,30 @@ int ucod_apm_binarize(const float* student, const float* teacher, const float* p
 int ucod_apm_merge(const float* pl, const float* t_mask, const float* p_s, const float* p_p, float epoch_term,
                    float* merged, float* weight, float* dis_loss, int batch, int pixels, void* stream);
 
+/* ---- first-stage training step ----------------------------------------------------------------------------
+ * Backward of the student `RevDecoder` for `TrainLoop._process_batch` (engine/runner/loop_UCOD_DPL.py:148-184):
+ * loss = BCEWithLogits(fg, target) + BCEWithLogits(bg, 1 - target) + ortho, target = APM-merged pseudo labels
+ * [batch, out_h*out_w] (constant).  Call after ucod_decoder_fwd(... ortho != NULL ...) on the same keys, passing
+ * that call's workspace; fg / bg are its outputs.  Gradients (fp32, zeroed here): g_w_dec [128,dim], g_b_dec [128],
+ * g_w_fg [64], g_b_fg [1], g_w_bg [64], g_b_bg [1]; the gradient of learnable_embedding is identically zero
+ * (F.normalize).  loss2: device float[2] = the two BCE means (add the forward's ortho for the total).
+ * Autograd entry: pass target = NULL and the upstream gradients dfg, dbg [batch, out_h*out_w] and dortho (device
+ * scalar) instead; then no loss is computed. */
+uint64_t ucod_decoder_bwd_workspace_bytes(int batch, int gin_h, int gin_w);
+int ucod_decoder_bwd(const void* keys_bf16, int batch, int dim, int gin_h, int gin_w, int out_h, int out_w,
+                     const void* w_dec, const float* b_dec, const float* emb, const float* w_fg, const float* b_fg,
+                     const float* w_bg, const float* b_bg, const float* fg, const float* bg, const float* target,
+                     const float* dfg, const float* dbg, const float* dortho, void* fwd_workspace,
+                     uint64_t fwd_workspace_bytes, float* g_w_dec, float* g_b_dec, float* g_w_fg,
+                     float* g_b_fg, float* g_w_bg, float* g_b_bg, float* loss2, void* workspace,
+                     uint64_t workspace_bytes, void* stream);
+/* torch.optim.AdamW step (decoupled weight decay, bias correction with step >= 1) on flat fp32 buffers, fused with
+ * `update_ema_decoder` (loop_UCOD_DPL.py:186-191): ema = ema_alpha*ema + (1-ema_alpha)*param (ema may be NULL).
+ * grads are multiplied by grad_scale first (1/world_size after the gradient all-reduce). */
+int ucod_adamw_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema, uint64_t n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                        float ema_alpha, void* stream);
+
 /* ---- CORAL second stage (SparseRefiner, eval) ----------------------------------------------------------
  * The dense part of the CSF block (models/modules/CSF.py:38-43, mlp.py:134-148) is assembled by the host from
  * ucod_layernorm_bf16 + ucod_gemm_bf16 + ucod_attention_shared_kv; the functions below are the remaining stages.

@@ -40,7 +40,7 @@ def student_forward(p: dict, x: torch.Tensor):
 def train_step(sd: dict, dis_sd: dict, state: dict, features: torch.Tensor, pseudo_labels: torch.Tensor, *,
                cur_epoch: int, global_step: int, lr: float, feature_size: int = 68, finetune: bool = False,
                ema_weight: float = 0.99, max_epoch: int = 25, start_finetune: int = -5, betas=(0.9, 0.999),
-               eps: float = 1e-8, weight_decay: float = 0.01):
+               eps: float = 1e-8, weight_decay: float = 0.01, merged_override=None, dis_loss_override=None):
     """One `_process_batch`.  sd: full baseline state_dict (student + EMA), updated in place; state: dict with
     'm', 'v' (dicts of tensors) and 't' (AdamW step count), updated in place.
     Returns dict(loss, grads, merged, dis_loss, ortho)."""
@@ -52,6 +52,8 @@ def train_step(sd: dict, dis_sd: dict, state: dict, features: torch.Tensor, pseu
     p = {k: sd["decoder." + k].clone().float().requires_grad_(True) for k in PARAM_ORDER}
     fg, bg, ortho = student_forward(p, x)
     merged, dis_loss, w, _, _ = odec.apm_merge(dis_sd, pl, teacher, fg.detach(), cur_epoch, max_epoch, start_finetune)
+    if merged_override is not None:  # stage isolation for the GPU parity test: APM outputs injected
+        merged, dis_loss = merged_override.float(), dis_loss_override.float()
     flat_t = merged.permute(0, 2, 3, 1).reshape(-1, 1)
     loss = F.binary_cross_entropy_with_logits(fg.permute(0, 2, 3, 1).reshape(-1, 1), flat_t)
     if not finetune:

@@ -1,0 +1,117 @@
+"""First-stage training step (CUDA) vs. the CPU oracle / the reference-generated golden vectors."""
+from pathlib import Path
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+from safetensors.torch import load_file
+
+from oracle import decoder as odec
+from oracle import train as otr
+from ucod_dpl_b200 import ops
+from ucod_dpl_b200.models.discriminator import Discriminator
+from ucod_dpl_b200.models.uscod import baseline
+from ucod_dpl_b200.train import FirstStageTrainer
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def train_inputs(seed: int, B: int = 2):
+    g = torch.Generator().manual_seed(seed)
+    feats = torch.randn(B, 768, 37, 37, generator=g)
+    pl = (torch.rand(B, 1, 16, 16, generator=g) < 0.35).float()
+    return feats, pl
+
+
+def _models():
+    sd = load_file(str(ROOT / "weights" / "UCOD_DPL_dinov2.safetensors"))
+    model = baseline(SimpleNamespace(dim=768))
+    model.load_state_dict(sd, strict=True)
+    D = Discriminator(SimpleNamespace(dis_use_features=False, dim=768, feature_size=68))
+    D.load_state_dict(odec.random_discriminator_state_dict(68, seed=31), strict=True)
+    return sd, model.cuda().train(), D.cuda().train()
+
+
+def test_autograd_gradients_match_oracle():
+    """model(features) + loss.backward() through the custom autograd Function == torch autograd on the fp32 oracle
+    (the 1x1 conv input is bf16 on the GPU: tolerance 2 % of the largest gradient entry)."""
+    sd, model, _ = _models()
+    feats, _ = train_inputs(100)
+    x = torch.nn.functional.interpolate(feats, size=(68, 68), mode="bilinear")
+    g = torch.Generator().manual_seed(5)
+    tgt = torch.rand(2, 1, 68, 68, generator=g)
+    p = {k: sd["decoder." + k].clone().float().requires_grad_(True) for k in otr.PARAM_ORDER}
+    fg, bg, ortho = otr.student_forward(p, x)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits
+    (bce(fg, tgt) + bce(bg, 1 - tgt) + ortho).backward()
+    fg2, bg2, ortho2 = model(x.cuda())
+    loss = bce(fg2, tgt.cuda()) + bce(bg2, 1 - tgt.cuda()) + ortho2
+    loss.backward()
+    assert abs(float(ortho2) - float(ortho)) < 2e-2 * abs(float(ortho))
+    for k in otr.PARAM_ORDER:
+        ref = p[k].grad
+        got = dict(model.decoder.named_parameters())[k].grad.cpu()
+        tol = 2e-2 * ref.abs().max().item() + 1e-7
+        assert (got - ref).abs().max().item() < tol, (k, (got - ref).abs().max().item(), tol)
+
+
+def test_three_fused_steps_match_oracle():
+    """Three fused steps (teacher fwd, student fwd, APM, BCE + ortho, backward, AdamW, StepLR, EMA) vs the oracle,
+    which is itself pinned to the reference's TrainLoop._process_batch (tests/test_oracle_train.py).
+    Stage isolation: with random features the binarised student / teacher masks sit on the sigmoid = 0.5 boundary,
+    and a BatchNorm-in-train-mode discriminator at batch 2 amplifies single-pixel flips, so the APM outputs of the
+    GPU run (parity-tested on their own in test_discriminator_apm_gpu.py) are injected into the oracle step."""
+    gold = np.load(ROOT / "tests" / "golden" / "train.npz")
+    sd0, model, D = _models()
+    dis_sd = odec.random_discriminator_state_dict(68, seed=31)
+    tr = FirstStageTrainer(model, D, lr0=2e-4)
+    tr.cur_epoch = 3
+    sd = {k: v.clone() for k, v in sd0.items()}
+    state = otr.new_state(sd)
+    for step in range(3):
+        feats, pl = train_inputs(100 + step)
+        tok = ops.features_to_tokens_bf16(feats.cuda())
+        loss = tr.process_batch(tok, (37, 37), pl.cuda())
+        out = otr.train_step(sd, dis_sd, state, feats, pl, cur_epoch=3, global_step=2 * step,
+                             lr=otr.step_lr(2e-4, step), merged_override=tr.last["merged"].cpu(),
+                             dis_loss_override=tr.last["dis_loss"].cpu())
+        assert abs(float(loss) - float(out["loss"])) < 2e-3 * abs(float(out["loss"])) + 2e-4
+        assert abs(float(loss) - float(gold[f"loss_{step}"])) < 0.15      # same ballpark as the un-isolated reference
+        for name in otr.PARAM_ORDER:
+            ref = out["grads"][name].reshape(-1).numpy()
+            got = tr.views[name].cpu().numpy()
+            tol = 2e-2 * np.abs(ref).max() + 1e-7
+            assert np.abs(got - ref).max() < tol, (step, name, np.abs(got - ref).max(), tol)
+    # AdamW moves every element by ~lr per step; compare the movement of the parameters after the three steps
+    for k, v in model.state_dict().items():
+        ref, init = sd[k].numpy(), sd0[k].numpy()
+        moved_ref, moved = ref - init, v.cpu().numpy() - init
+        assert np.abs(moved - moved_ref).mean() < 0.25 * np.abs(moved_ref).mean() + 1e-7, k
+        np.testing.assert_allclose(v.cpu().numpy(), ref, atol=1.3e-3)
+    assert tr.global_step == 6 and tr.opt_steps == 3
+
+
+def test_adamw_ema_kernel_matches_torch():
+    from ucod_dpl_b200 import _lib
+    import ctypes
+    g = torch.Generator().manual_seed(0)
+    n = 98690
+    p = torch.randn(n, generator=g)
+    ema = torch.randn(n, generator=g)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=2e-4)
+    dp, dm, dv, de = p.cuda(), torch.zeros(n).cuda(), torch.zeros(n).cuda(), ema.cuda()
+    ema_ref = ema.clone()
+    for t in range(1, 4):
+        grad = torch.randn(n, generator=g) * 0.01
+        ref.grad = grad.clone()
+        opt.step()
+        alpha = min(1 - 1 / (2 * (t - 1) + 1), 0.99)
+        ema_ref.mul_(alpha).add_(ref.data, alpha=1 - alpha)
+        _lib.call("ucod_adamw_ema_step", _lib.ptr(dp), _lib.ptr((grad * 2).cuda()), _lib.ptr(dm), _lib.ptr(dv),
+                  _lib.ptr(de), ctypes.c_uint64(n), _lib.c_float(2e-4), _lib.c_float(0.9), _lib.c_float(0.999),
+                  _lib.c_float(1e-8), _lib.c_float(0.01), t, _lib.c_float(0.5), _lib.c_float(alpha), _lib.stream_ptr())
+    np.testing.assert_allclose(dp.cpu().numpy(), ref.data.numpy(), atol=2e-6)
+    np.testing.assert_allclose(de.cpu().numpy(), ema_ref.numpy(), atol=2e-6)

@@ -163,6 +163,31 @@ int ucod_apm_merge(const float* pl, const float* t_mask, const float* p_s, const
                      reinterpret_cast<cudaStream_t>(stream));
 }
 
+// ---- first-stage training ----
+uint64_t ucod_decoder_bwd_workspace_bytes(int batch, int gin_h, int gin_w) {
+    return (uint64_t)decoder_backward_workspace_bytes(batch, gin_h, gin_w);
+}
+int ucod_decoder_bwd(const void* keys_bf16, int batch, int dim, int gin_h, int gin_w, int out_h, int out_w,
+                     const void* w_dec, const float* b_dec, const float* emb, const float* w_fg, const float* b_fg,
+                     const float* w_bg, const float* b_bg, const float* fg, const float* bg, const float* target,
+                     const float* dfg, const float* dbg, const float* dortho, void* fwd_workspace,
+                     uint64_t fwd_workspace_bytes, float* g_w_dec, float* g_b_dec, float* g_w_fg,
+                     float* g_b_fg, float* g_w_bg, float* g_b_bg, float* loss2, void* workspace,
+                     uint64_t workspace_bytes, void* stream) {
+    UCOD_REQUIRE(w_dec && b_dec && emb && w_fg && b_fg && w_bg && b_bg, "ucod_decoder_bwd: null weight pointer");
+    DecoderWeights w{dim, w_dec, b_dec, emb, w_fg, b_fg, w_bg, b_bg};
+    DecoderGrads g{g_w_dec, g_b_dec, g_w_fg, g_b_fg, g_w_bg, g_b_bg};
+    return decoder_backward(keys_bf16, batch, gin_h, gin_w, out_h, out_w, w, fg, bg, target, dfg, dbg, dortho,
+                            fwd_workspace, (size_t)fwd_workspace_bytes, g, loss2, workspace, (size_t)workspace_bytes,
+                            reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_adamw_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema, uint64_t n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                        float ema_alpha, void* stream) {
+    return adamw_ema_step(params, grads, exp_avg, exp_avg_sq, ema, (size_t)n, lr, beta1, beta2, eps, weight_decay, step,
+                          grad_scale, ema_alpha, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // ---- CORAL second stage ----
 int ucod_coral_entropy_select(const float* preds, int batch, int size, int window_size, float threshold,
                               float* entropy, float* scores, uint8_t* mask, void* scratch, void* stream) {

@@ -268,6 +268,327 @@ int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_
 // -> token-major bf16 [B, H*W, C].  32x32 smem-tiled transpose; coalesced on both sides for the
 // contiguous-NCHW case, and for the channels-last case reads are coalesced along c directly.
 // ------------------------------------------------------------------------------------------------
+// Backward of the student decoder for the first-stage training step (engine/runner/loop_UCOD_DPL.py:148-184):
+//   loss = BCEwL(fg, t) + BCEwL(bg, 1 - t) + ortho,  t = APM-merged pseudo label (no gradient flows into t).
+// With d = U(D_in) (bilinear upsample of the 1x1-conv output), r_c = sign(e_c) / sqrt(sum_p d_pc^2), fh = d r,
+// u = fh d, a = sigmoid(u) + d:
+//   dlogit = (sigmoid(logit) - target) / (B npix)          da = dlogit * w_head
+//   dfh    = da s(1-s) d + (2 / (B npix^2)) [ (Fh_k G_other)_pc - (fh1_p . fh2_p) fh_other_pc ]      (Gram identity)
+//   dd     = da (1 + s(1-s) fh) + r (dfh - fh t_c),  t_c = sum_p dfh_pc fh_pc                         (normalisation)
+//          = P1 - d r^2 t_c
+//   dD_in  = U^T P1 - (r^2 t_c) U^T d        -> two scatter-add buffers (A = U^T P1, E = U^T d), one elementwise pass
+//   dW_dec = dD_in^T X, db_dec = sum dD_in ; the gradient of learnable_embedding is identically zero
+//   (F.normalize removes |e|; the reference's autograd value is rounding noise, see tests/test_oracle_train.py).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void atomic_add4(float* dst, float4 v) {
+    atomicAdd(reinterpret_cast<float4*>(dst), v);
+}
+
+__global__ void __launch_bounds__(256)
+    decoder_bwd_pixels_kernel(const float* __restrict__ d_in, const float* __restrict__ sumsq,
+                              const float* __restrict__ emb, const float* __restrict__ w_fg,
+                              const float* __restrict__ w_bg, const float* __restrict__ fhat,
+                              const float* __restrict__ gram, const float* __restrict__ fg,
+                              const float* __restrict__ bg, const float* __restrict__ target,
+                              const float* __restrict__ dfg, const float* __restrict__ dbg,
+                              const float* __restrict__ dortho, float* __restrict__ a_buf, float* __restrict__ e_buf, float* __restrict__ tsum,
+                              float* __restrict__ g_wfg, float* __restrict__ g_bfg, float* __restrict__ g_wbg,
+                              float* __restrict__ g_bbg, float* __restrict__ loss2, int B, int gin_h, int gin_w,
+                              int out_h, int out_w) {
+    __shared__ __align__(16) float sG[2][64 * 64];
+    __shared__ __align__(16) float sf[8][128];
+    __shared__ float4 red4[8][32];
+    __shared__ float red1[8][32];
+    const int b = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int branch = lane >> 4, ch0 = lane * 4, col = ch0 & 63;
+    const int npix = out_h * out_w;
+    for (int i = threadIdx.x; i < 2 * 4096; i += 256) (&sG[0][0])[i] = gram[(size_t)b * 8192 + i];
+    __syncthreads();
+    const float* d_img = d_in + (size_t)b * gin_h * gin_w * 128;
+    const float4 ss = reinterpret_cast<const float4*>(sumsq + (size_t)b * 128)[lane];
+    const float4 e = __ldg(reinterpret_cast<const float4*>(emb) + lane);
+    const float4 wh = lane < 16 ? __ldg(reinterpret_cast<const float4*>(w_fg) + lane)
+                                : __ldg(reinterpret_cast<const float4*>(w_bg) + (lane - 16));
+    float4 r;
+    r.x = e.x / fmaxf(fabsf(e.x) * sqrtf(ss.x), 1e-12f);
+    r.y = e.y / fmaxf(fabsf(e.y) * sqrtf(ss.y), 1e-12f);
+    r.z = e.z / fmaxf(fabsf(e.z) * sqrtf(ss.z), 1e-12f);
+    r.w = e.w / fmaxf(fabsf(e.w) * sqrtf(ss.w), 1e-12f);
+    const float inv_n = 1.0f / ((float)B * (float)npix);
+    const float oc = 2.0f / ((float)B * (float)npix * (float)npix) * (dortho != nullptr ? __ldg(dortho) : 1.f);
+    const float* Gother = sG[branch ^ 1];
+    float4 gw = make_float4(0.f, 0.f, 0.f, 0.f), tacc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float gb = 0.f, lacc = 0.f;
+
+    for (int i = 0; i < DEC_PIX_PER_BLOCK / 8; ++i) {
+        const int pix = blockIdx.x * DEC_PIX_PER_BLOCK + i * 8 + warp;
+        if (pix >= npix) break;  // warp-uniform
+        const int oy = pix / out_w, ox = pix - oy * out_w;
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_tap(oy, gin_h, out_h, y0, y1, ly);
+        bilinear_tap(ox, gin_w, out_w, x0, x1, lx);
+        const float4 d = sample_d(d_img, gin_w, y0, y1, ly, x0, x1, lx, lane);
+        const float4 f = reinterpret_cast<const float4*>(fhat + ((size_t)b * npix + pix) * 128)[lane];
+        __syncwarp();
+        reinterpret_cast<float4*>(sf[warp])[lane] = f;
+        __syncwarp();
+        const float4 fo = reinterpret_cast<const float4*>(sf[warp])[lane ^ 16];  // other branch, same column
+        const float sp = 0.5f * warp_sum(f.x * fo.x + f.y * fo.y + f.z * fo.z + f.w * fo.w);
+        float4 O = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* own = sf[warp] + branch * 64;
+#pragma unroll 8
+        for (int c = 0; c < 64; ++c) {
+            const float fc = own[c];
+            const float4 gr = *reinterpret_cast<const float4*>(Gother + c * 64 + col);
+            O.x += fc * gr.x, O.y += fc * gr.y, O.z += fc * gr.z, O.w += fc * gr.w;
+        }
+        O.x -= sp * fo.x, O.y -= sp * fo.y, O.z -= sp * fo.z, O.w -= sp * fo.w;
+        const float logit = branch == 0 ? fg[(size_t)b * npix + pix] : bg[(size_t)b * npix + pix];
+        float dlog;
+        if (dfg != nullptr) {  // upstream gradients given (autograd entry)
+            dlog = branch == 0 ? dfg[(size_t)b * npix + pix] : dbg[(size_t)b * npix + pix];
+        } else {               // fused BCE-with-logits against the merged pseudo label
+            const float t0 = target[(size_t)b * npix + pix];
+            const float tt = branch == 0 ? t0 : 1.f - t0;
+            dlog = (1.f / (1.f + expf(-logit)) - tt) * inv_n;
+            if ((lane & 15) == 0) lacc += fmaxf(logit, 0.f) - logit * tt + log1pf(expf(-fabsf(logit)));
+        }
+        float4 sg, a, da, dfh, p1;
+        sg.x = 1.f / (1.f + expf(-f.x * d.x)), sg.y = 1.f / (1.f + expf(-f.y * d.y));
+        sg.z = 1.f / (1.f + expf(-f.z * d.z)), sg.w = 1.f / (1.f + expf(-f.w * d.w));
+        a.x = sg.x + d.x, a.y = sg.y + d.y, a.z = sg.z + d.z, a.w = sg.w + d.w;
+        da.x = dlog * wh.x, da.y = dlog * wh.y, da.z = dlog * wh.z, da.w = dlog * wh.w;
+        gw.x += dlog * a.x, gw.y += dlog * a.y, gw.z += dlog * a.z, gw.w += dlog * a.w;
+        if ((lane & 15) == 0) gb += dlog;
+        const float4 ds = make_float4(sg.x * (1.f - sg.x), sg.y * (1.f - sg.y), sg.z * (1.f - sg.z), sg.w * (1.f - sg.w));
+        dfh.x = da.x * ds.x * d.x + oc * O.x, dfh.y = da.y * ds.y * d.y + oc * O.y;
+        dfh.z = da.z * ds.z * d.z + oc * O.z, dfh.w = da.w * ds.w * d.w + oc * O.w;
+        tacc.x += dfh.x * f.x, tacc.y += dfh.y * f.y, tacc.z += dfh.z * f.z, tacc.w += dfh.w * f.w;
+        p1.x = da.x * (1.f + ds.x * f.x) + r.x * dfh.x, p1.y = da.y * (1.f + ds.y * f.y) + r.y * dfh.y;
+        p1.z = da.z * (1.f + ds.z * f.z) + r.z * dfh.z, p1.w = da.w * (1.f + ds.w * f.w) + r.w * dfh.w;
+        // adjoint of the bilinear upsample: scatter to the four source pixels
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+        const size_t base = (size_t)b * gin_h * gin_w;
+        const size_t q00 = (base + (size_t)y0 * gin_w + x0) * 128 + ch0, q01 = (base + (size_t)y0 * gin_w + x1) * 128 + ch0;
+        const size_t q10 = (base + (size_t)y1 * gin_w + x0) * 128 + ch0, q11 = (base + (size_t)y1 * gin_w + x1) * 128 + ch0;
+        atomic_add4(a_buf + q00, make_float4(p1.x * w00, p1.y * w00, p1.z * w00, p1.w * w00));
+        atomic_add4(a_buf + q01, make_float4(p1.x * w01, p1.y * w01, p1.z * w01, p1.w * w01));
+        atomic_add4(a_buf + q10, make_float4(p1.x * w10, p1.y * w10, p1.z * w10, p1.w * w10));
+        atomic_add4(a_buf + q11, make_float4(p1.x * w11, p1.y * w11, p1.z * w11, p1.w * w11));
+        atomic_add4(e_buf + q00, make_float4(d.x * w00, d.y * w00, d.z * w00, d.w * w00));
+        atomic_add4(e_buf + q01, make_float4(d.x * w01, d.y * w01, d.z * w01, d.w * w01));
+        atomic_add4(e_buf + q10, make_float4(d.x * w10, d.y * w10, d.z * w10, d.w * w10));
+        atomic_add4(e_buf + q11, make_float4(d.x * w11, d.y * w11, d.z * w11, d.w * w11));
+    }
+    // block reduction of the per-lane accumulators, then one atomic per channel / scalar
+    red4[warp][lane] = gw;
+    __syncthreads();
+    if (warp == 0) {
+        float4 t = red4[0][lane];
+        for (int w = 1; w < 8; ++w) t.x += red4[w][lane].x, t.y += red4[w][lane].y, t.z += red4[w][lane].z, t.w += red4[w][lane].w;
+        float* dst = lane < 16 ? g_wfg + ch0 : g_wbg + (ch0 - 64);
+        atomicAdd(dst + 0, t.x), atomicAdd(dst + 1, t.y), atomicAdd(dst + 2, t.z), atomicAdd(dst + 3, t.w);
+    }
+    __syncthreads();
+    red4[warp][lane] = tacc;
+    red1[warp][lane] = (lane & 15) == 0 ? gb : 0.f;
+    __syncthreads();
+    if (warp == 0) {
+        float4 t = red4[0][lane];
+        float g1 = red1[0][lane];
+        for (int w = 1; w < 8; ++w) {
+            t.x += red4[w][lane].x, t.y += red4[w][lane].y, t.z += red4[w][lane].z, t.w += red4[w][lane].w;
+            g1 += red1[w][lane];
+        }
+        float* dst = tsum + (size_t)b * 128 + ch0;
+        atomicAdd(dst + 0, t.x), atomicAdd(dst + 1, t.y), atomicAdd(dst + 2, t.z), atomicAdd(dst + 3, t.w);
+        if (lane == 0) atomicAdd(g_bfg, g1);
+        if (lane == 16) atomicAdd(g_bbg, g1);
+    }
+    __syncthreads();
+    red1[warp][lane] = lacc;
+    __syncthreads();
+    if (warp == 0 && (lane & 15) == 0) {
+        float l = 0.f;
+        for (int w = 0; w < 8; ++w) l += red1[w][lane];
+        atomicAdd(loss2 + (lane >> 4), l * inv_n);
+    }
+}
+
+// dD = A - (r_c^2 t_c) E ; db_dec[c] += sum over rows
+__global__ void __launch_bounds__(256)
+    decoder_bwd_finish_kernel(const float* __restrict__ a_buf, const float* __restrict__ e_buf,
+                              const float* __restrict__ tsum, const float* __restrict__ sumsq,
+                              const float* __restrict__ emb, float* __restrict__ dD, float* __restrict__ g_bdec,
+                              int rows_per_img, int total_rows) {
+    const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
+    const int r0 = blockIdx.x * 64;
+    const float e = __ldg(emb + c);
+    float acc = 0.f;
+    for (int i = half; i < 64; i += 2) {
+        const int row = r0 + i;
+        if (row >= total_rows) break;
+        const int b = row / rows_per_img;
+        const float g = e / fmaxf(fabsf(e) * sqrtf(sumsq[b * 128 + c]), 1e-12f);
+        const float v = a_buf[(size_t)row * 128 + c] - g * g * tsum[b * 128 + c] * e_buf[(size_t)row * 128 + c];
+        dD[(size_t)row * 128 + c] = v;
+        acc += v;
+    }
+    atomicAdd(g_bdec + c, acc);
+}
+
+// dW[c][k] += sum_t dD[t][c] * X[t][k]   (c < 128, k < dim; X bf16 token-major; split over token ranges)
+__global__ void __launch_bounds__(256)
+    decoder_wgrad_kernel(const float* __restrict__ dD, const __nv_bfloat16* __restrict__ X, float* __restrict__ dW,
+                         int T, int dim, int tokens_per_split) {
+    __shared__ __align__(16) float sD[16][128];
+    __shared__ __align__(16) float sX[16][64];
+    const int k0 = blockIdx.x * 64;
+    const int t_begin = blockIdx.y * tokens_per_split;
+    const int t_end = min(T, t_begin + tokens_per_split);
+    const int cg = threadIdx.x >> 4, kg = threadIdx.x & 15;  // 16 x 16 thread grid: 8 channels x 4 features each
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int t0 = t_begin; t0 < t_end; t0 += 16) {
+        const int n = min(16, t_end - t0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < 16 * 32; i += 256) {  // dD: 16 rows x 128 floats as float4
+            const int rr = i >> 5, cc = (i & 31) * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rr < n) v = *reinterpret_cast<const float4*>(dD + (size_t)(t0 + rr) * 128 + cc);
+            *reinterpret_cast<float4*>(&sD[rr][cc]) = v;
+        }
+        for (int i = threadIdx.x; i < 16 * 32; i += 256) {  // X: 16 rows x 64 bf16 as bf16x2
+            const int rr = i >> 5, cc = (i & 31) * 2;
+            float2 v = make_float2(0.f, 0.f);
+            if (rr < n) v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(X + (size_t)(t0 + rr) * dim + k0 + cc));
+            sX[rr][cc] = v.x, sX[rr][cc + 1] = v.y;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int tt = 0; tt < 16; ++tt) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&sD[tt][cg * 8]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&sD[tt][cg * 8 + 4]);
+            const float4 bx = *reinterpret_cast<const float4*>(&sX[tt][kg * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[4] = {bx.x, bx.y, bx.z, bx.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) atomicAdd(dW + (size_t)(cg * 8 + i) * dim + k0 + kg * 4 + j, acc[i][j]);
+}
+
+size_t decoder_backward_workspace_bytes(int B, int gin_h, int gin_w) {
+    const size_t rows = (size_t)B * gin_h * gin_w;
+    return rows * 128 * 4 * 3 + (size_t)B * 128 * 4 + 4096;  // A, E, dD, tsum
+}
+
+int decoder_backward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_h, int out_w, const DecoderWeights& w,
+                     const float* fg, const float* bg, const float* target, const float* dfg, const float* dbg,
+                     const float* dortho, void* fwd_workspace, size_t fwd_ws_bytes, const DecoderGrads& g, float* loss2,
+                     void* workspace, size_t ws_bytes, cudaStream_t stream) {
+    UCOD_REQUIRE(keys_bf16 && fg && bg && fwd_workspace && workspace && loss2, "decoder_backward: null argument");
+    UCOD_REQUIRE(target != nullptr || (dfg != nullptr && dbg != nullptr),
+                 "decoder_backward: give either the BCE target or the upstream gradients dfg/dbg");
+    UCOD_REQUIRE(g.w_dec && g.b_dec && g.w_fg && g.b_fg && g.w_bg && g.b_bg, "decoder_backward: null gradient pointer");
+    UCOD_REQUIRE(w.dim % 64 == 0, "decoder_backward: dim must be a multiple of 64");
+    UCOD_REQUIRE(fwd_ws_bytes >= decoder_workspace_bytes(B, gin_h, gin_w, out_h, out_w, 1),
+                 "decoder_backward: the forward workspace must come from a forward with the ortho loss enabled");
+    UCOD_REQUIRE(ws_bytes >= decoder_backward_workspace_bytes(B, gin_h, gin_w), "decoder_backward: workspace too small");
+    const int npix = out_h * out_w;
+    const size_t rows = (size_t)B * gin_h * gin_w;
+    // forward workspace layout (see decoder_forward)
+    uint8_t* fb = static_cast<uint8_t*>(fwd_workspace);
+    const float* d_in = reinterpret_cast<const float*>(fb);
+    size_t off = rows * 128 * 4;
+    const float* sumsq = reinterpret_cast<const float*>(fb + off);
+    off += (size_t)B * 128 * 4;
+    const float* fhat = reinterpret_cast<const float*>(fb + off);
+    off += (size_t)B * npix * 128 * 4;
+    const float* gram = reinterpret_cast<const float*>(fb + off);
+    float* a_buf = static_cast<float*>(workspace);
+    float* e_buf = a_buf + rows * 128;
+    float* dD = e_buf + rows * 128;
+    float* tsum = dD + rows * 128;
+    UCOD_CHECK_CUDA(cudaMemsetAsync(a_buf, 0, rows * 128 * 4 * 2, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(tsum, 0, (size_t)B * 128 * 4, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(g.w_dec, 0, (size_t)128 * w.dim * 4, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(g.b_dec, 0, 128 * 4, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(g.w_fg, 0, 64 * 4, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(g.w_bg, 0, 64 * 4, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(g.b_fg, 0, 4, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(g.b_bg, 0, 4, stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(loss2, 0, 8, stream));
+    {
+        dim3 grid(ceil_div(npix, DEC_PIX_PER_BLOCK), B);
+        ProfScope ps(KC_DECODER, stream, (double)B * npix * 128 * 4 * 2 + (double)rows * 128 * 4 * 3);
+        decoder_bwd_pixels_kernel<<<grid, 256, 0, stream>>>(d_in, sumsq, w.emb, w.w_fg, w.w_bg, fhat, gram, fg, bg,
+                                                            target, dfg, dbg, dortho, a_buf, e_buf, tsum, g.w_fg,
+                                                            g.b_fg, g.w_bg, g.b_bg, loss2, B, gin_h, gin_w, out_h, out_w);
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    {
+        ProfScope ps(KC_DECODER, stream, (double)rows * 128 * 4 * 3);
+        decoder_bwd_finish_kernel<<<ceil_div((int)rows, 64), 256, 0, stream>>>(a_buf, e_buf, tsum, sumsq, w.emb, dD,
+                                                                               g.b_dec, gin_h * gin_w, (int)rows);
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    {
+        int splits = ceil_div(2 * device_sm_count(), w.dim / 64);
+        int tps = ceil_div((int)rows, splits);
+        tps = ceil_div(tps, 16) * 16;
+        splits = ceil_div((int)rows, tps);
+        dim3 grid(w.dim / 64, splits);
+        ProfScope ps(KC_DECODER, stream, (double)rows * (128 * 4 + w.dim * 2));
+        decoder_wgrad_kernel<<<grid, 256, 0, stream>>>(dD, static_cast<const __nv_bfloat16*>(keys_bf16), g.w_dec,
+                                                       (int)rows, w.dim, tps);
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Fused AdamW (torch semantics, decoupled weight decay) + EMA of the updated parameters
+// (engine/runner/runner.py:282-285, loop_UCOD_DPL.py:186-191) over flat fp32 buffers.
+__global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, float* __restrict__ ema, size_t n, float lr, float b1, float b2,
+                                 float eps, float wd, float bc1, float bc2_sqrt, float grad_scale, float ema_alpha) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float gi = g[i] * grad_scale;
+        float pi = p[i] * (1.f - lr * wd);
+        const float mi = b1 * m[i] + (1.f - b1) * gi;
+        const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+        pi -= (lr / bc1) * mi / (sqrtf(vi) / bc2_sqrt + eps);
+        p[i] = pi, m[i] = mi, v[i] = vi;
+        if (ema != nullptr) ema[i] = ema_alpha * ema[i] + (1.f - ema_alpha) * pi;
+    }
+}
+
+int adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int step_t, float grad_scale, float ema_alpha,
+                   cudaStream_t stream) {
+    UCOD_REQUIRE(p && g && m && v && n > 0 && step_t >= 1, "adamw_ema_step: bad argument");
+    const float bc1 = 1.f - powf(beta1, (float)step_t);
+    const float bc2s = sqrtf(1.f - powf(beta2, (float)step_t));
+    const unsigned grid = (unsigned)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+    ProfScope ps(KC_OTHER, stream, (double)n * 4 * 9);
+    adamw_ema_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, ema, n, lr, beta1, beta2, eps, weight_decay, bc1, bc2s,
+                                               grad_scale, ema_alpha);
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 __global__ void features_to_tokens_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int C, int P,
                                           long long sb, long long sc, long long sp) {
     __shared__ float tile[32][33];

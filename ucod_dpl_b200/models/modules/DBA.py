@@ -56,6 +56,7 @@ class RevDecoder(nn.Module):
         tokens = ops.features_to_tokens_bf16(x)
         if not self.ema and self.training and torch.is_grad_enabled():
             from ...train import decoder_forward_autograd  # training path (fwd + hand-written bwd kernels)
+            self._packed = None  # the optimiser may have stepped since the last call
             return decoder_forward_autograd(self, tokens, (H, W))
         fg, bg, ortho = self.forward_tokens(tokens, (H, W), (H, W), want_bg=(not self.ema) or get_bg_mask,
                                             want_ortho=not self.ema)

@@ -1,0 +1,190 @@
+"""First-stage training step on the GPU (reference: engine/runner/loop_UCOD_DPL.py:36-272 `TrainLoop`).
+
+* `decoder_forward_autograd` — `RevDecoder.forward` in training mode as a `torch.autograd.Function` whose backward
+  is the hand-written CUDA backward (`ucod_decoder_bwd`), so `loss.backward()` on (fg, bg, ortho) works with any
+  optimiser exactly like the reference module.
+* `FirstStageTrainer`       — the fused step: teacher (EMA) forward, student forward, APM merge, BCE + ortho loss
+  and backward in one kernel sequence, decoder-gradient all-reduce over NCCL (flat 98 690-float buffer), fused
+  AdamW + EMA update, StepLR stepped per iteration.  Mirrors `_process_batch` / `update_ema_decoder`.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib, ops
+from ._lib import c_float, ptr, stream_ptr
+from .models.discriminator import merge_pseudo_label
+
+_u64 = ctypes.c_uint64
+
+
+def _decoder_pointers(dec):
+    return (ptr(dec._w_dec_bf16()), ptr(dec.decoupling.bias.detach()), ptr(dec.learnable_embedding.detach()),
+            ptr(dec.conv_out_fg.weight.detach()), ptr(dec.conv_out_fg.bias.detach()),
+            ptr(dec.conv_out_bg.weight.detach()), ptr(dec.conv_out_bg.bias.detach()))
+
+
+def _forward_with_workspace(dec, tokens, grid_in, grid_out):
+    """Student forward that keeps its workspace (d_in, sumsq, fhat, Grams) for the backward."""
+    B, P, dim = tokens.shape
+    (gh, gw), (oh, ow) = grid_in, grid_out
+    dev = tokens.device
+    lib = _lib.load()
+    lib.ucod_decoder_workspace_bytes.restype = _u64
+    need = lib.ucod_decoder_workspace_bytes(B, gh, gw, oh, ow, 1)
+    ws = torch.empty(int(need) + 1024, dtype=torch.uint8, device=dev)
+    off = (-ws.data_ptr()) % 1024
+    fg = torch.empty(B, 1, oh, ow, device=dev)
+    bg = torch.empty(B, 1, oh, ow, device=dev)
+    ortho = torch.empty((), device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_decoder_fwd", ptr(tokens), B, dim, gh, gw, oh, ow, *_decoder_pointers(dec), ptr(fg), ptr(bg),
+                  ptr(ortho), ctypes.c_void_p(ws.data_ptr() + off), _u64(ws.numel() - off), stream_ptr(dev))
+    return fg, bg, ortho, (ws, off)
+
+
+def _backward(dec, tokens, grid_in, grid_out, fg, bg, fwd_ws, grads, *, target=None, dfg=None, dbg=None, dortho=None):
+    """grads: dict name -> fp32 tensor views (w_dec [128,dim], b_dec, w_fg, b_fg, w_bg, b_bg). Returns loss2 | None."""
+    B, P, dim = tokens.shape
+    (gh, gw), (oh, ow) = grid_in, grid_out
+    dev = tokens.device
+    lib = _lib.load()
+    lib.ucod_decoder_bwd_workspace_bytes.restype = _u64
+    bws = torch.empty(int(lib.ucod_decoder_bwd_workspace_bytes(B, gh, gw)) + 1024, dtype=torch.uint8, device=dev)
+    boff = (-bws.data_ptr()) % 1024
+    ws, off = fwd_ws
+    loss2 = torch.empty(2, device=dev)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_decoder_bwd", ptr(tokens), B, dim, gh, gw, oh, ow, *_decoder_pointers(dec), ptr(fg), ptr(bg),
+                  ptr(target), ptr(dfg), ptr(dbg), ptr(dortho), ctypes.c_void_p(ws.data_ptr() + off),
+                  _u64(ws.numel() - off), ptr(grads["w_dec"]), ptr(grads["b_dec"]), ptr(grads["w_fg"]),
+                  ptr(grads["b_fg"]), ptr(grads["w_bg"]), ptr(grads["b_bg"]), ptr(loss2),
+                  ctypes.c_void_p(bws.data_ptr() + boff), _u64(bws.numel() - boff), stream_ptr(dev))
+    return loss2
+
+
+class _DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec, tokens, grid, w, b, emb, wfg, bfg, wbg, bbg):
+        fg, bg, ortho, ws = _forward_with_workspace(dec, tokens, grid, grid)
+        ctx.dec, ctx.tokens, ctx.grid, ctx.ws = dec, tokens, grid, ws
+        ctx.save_for_backward(fg, bg)
+        return fg, bg, ortho
+
+    @staticmethod
+    def backward(ctx, dfg, dbg, dortho):
+        dec, tokens = ctx.dec, ctx.tokens
+        fg, bg = ctx.saved_tensors
+        dev = tokens.device
+        dim = tokens.shape[-1]
+        g = {"w_dec": torch.empty(128, dim, device=dev), "b_dec": torch.empty(128, device=dev),
+             "w_fg": torch.empty(64, device=dev), "b_fg": torch.empty(1, device=dev),
+             "w_bg": torch.empty(64, device=dev), "b_bg": torch.empty(1, device=dev)}
+        zeros = lambda t: torch.zeros_like(t) if t is None else t.contiguous().float()  # noqa: E731
+        dfg = torch.zeros_like(fg) if dfg is None else dfg.contiguous().float()
+        dbg = torch.zeros_like(bg) if dbg is None else dbg.contiguous().float()
+        dortho = torch.zeros((), device=dev) if dortho is None else dortho.contiguous().float()
+        _backward(dec, tokens, ctx.grid, ctx.grid, fg, bg, ctx.ws, g, dfg=dfg, dbg=dbg, dortho=dortho)
+        return (None, None, None, g["w_dec"].reshape(128, dim, 1, 1), g["b_dec"],
+                torch.zeros_like(dec.learnable_embedding), g["w_fg"].reshape(1, 64, 1, 1), g["b_fg"],
+                g["w_bg"].reshape(1, 64, 1, 1), g["b_bg"])
+
+
+def decoder_forward_autograd(dec, tokens_bf16: torch.Tensor, grid):
+    """(fg, bg, ortho) with autograd support for the student decoder parameters (features need no gradient)."""
+    return _DecoderFn.apply(dec, tokens_bf16, tuple(grid), dec.decoupling.weight, dec.decoupling.bias,
+                            dec.learnable_embedding, dec.conv_out_fg.weight, dec.conv_out_fg.bias,
+                            dec.conv_out_bg.weight, dec.conv_out_bg.bias)
+
+
+class FirstStageTrainer:
+    """Fused first-stage training (config 5).  `model` is a `baseline`; `discriminator` a `Discriminator` (frozen
+    during decoder epochs, BatchNorm in train mode like the reference)."""
+
+    def __init__(self, model, discriminator, *, lr0: float = 2e-4, step_lr_size: int = 25, step_lr_gamma: float = 0.95,
+                 feature_size: int = 68, ema_weight: float = 0.99, max_epoch: int = 25, start_finetune: int = -5,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, process_group=None):
+        self.model, self.discriminator = model, discriminator
+        self.fs = int(feature_size)
+        self.lr0, self.step_size, self.gamma = lr0, step_lr_size, step_lr_gamma
+        self.ema_weight, self.max_epoch, self.start_finetune = ema_weight, max_epoch, start_finetune
+        self.betas, self.eps, self.wd = betas, eps, weight_decay
+        self.pg = process_group
+        self.global_step = 0      # the reference's counter (bumped twice per batch: loop_UCOD_DPL.py:143,182)
+        self.opt_steps = 0        # optimiser / scheduler steps
+        self.cur_epoch = 0
+        self.finetune = False
+        dec, ema = model.decoder, model.decoder_ema
+        dev = dec.decoupling.weight.device
+        if dev.type != "cuda":
+            raise _lib.UcodError("FirstStageTrainer needs the model on a CUDA device; there is no CPU fallback")
+        # flat parameter / EMA / gradient / moment buffers in nn.Module.parameters() order; the modules' parameters
+        # become views of the flat buffers, so state_dict() / checkpoints are unaffected.
+        # Every slot is padded to a multiple of 4 floats so that the kernels' 128-bit loads stay aligned.
+        self.names = [n for n, _ in dec.named_parameters()]
+        sizes = [p.numel() for p in dec.parameters()]
+        slots = [(sz + 3) // 4 * 4 for sz in sizes]
+        self.n = sum(slots)
+        self.flat_p = torch.zeros(self.n, device=dev)
+        self.flat_ema = torch.zeros(self.n, device=dev)
+        self.flat_g = torch.zeros(self.n, device=dev)
+        self.flat_m = torch.zeros(self.n, device=dev)
+        self.flat_v = torch.zeros(self.n, device=dev)
+        self.views = {}
+        o = 0
+        for (name, p), (_, pe), sz, slot in zip(dec.named_parameters(), ema.named_parameters(), sizes, slots):
+            self.flat_p[o:o + sz].copy_(p.detach().flatten())
+            self.flat_ema[o:o + sz].copy_(pe.detach().flatten())
+            p.data = self.flat_p[o:o + sz].view_as(p)
+            pe.data = self.flat_ema[o:o + sz].view_as(pe)
+            self.views[name] = self.flat_g[o:o + sz]
+            o += slot
+        dim = dec.decoupling.weight.shape[1]
+        self.grads = {"w_dec": self.views["decoupling.weight"].view(128, dim), "b_dec": self.views["decoupling.bias"],
+                      "w_fg": self.views["conv_out_fg.weight"], "b_fg": self.views["conv_out_fg.bias"],
+                      "w_bg": self.views["conv_out_bg.weight"], "b_bg": self.views["conv_out_bg.bias"]}
+
+    @property
+    def lr(self) -> float:
+        return self.lr0 * self.gamma ** (self.opt_steps // self.step_size)
+
+    def start_finetune_phase(self):
+        self.finetune = True
+        self.global_step = 0
+
+    @torch.no_grad()
+    def process_batch(self, key_tokens_bf16: torch.Tensor, grid_in, pseudo_labels: torch.Tensor):
+        """key_tokens_bf16 [B, gh*gw, dim] (cached backbone keys), pseudo_labels [B,1,16,16] {0,1}.
+        Returns the loss tensor (device scalar), like `_process_batch`."""
+        dec, ema = self.model.decoder, self.model.decoder_ema
+        fs = (self.fs, self.fs)
+        pl = ops.upsample_bilinear(pseudo_labels.float(), fs)                    # F.interpolate(pl, 68x68)
+        teacher, _, _ = ema.forward_tokens(key_tokens_bf16, grid_in, fs, want_bg=False)
+        dec._packed = None                                                       # weights changed last step
+        fg, bg, ortho, ws = _forward_with_workspace(dec, key_tokens_bf16, grid_in, fs)
+        merged, dis_loss = merge_pseudo_label(self.discriminator, pl, teacher, fg, None, cur_epoch=self.cur_epoch,
+                                              max_epoch=self.max_epoch, start_finetune=self.start_finetune)
+        loss2 = _backward(dec, key_tokens_bf16, grid_in, fs, fg, bg, ws, self.grads, target=merged)
+        self.views["learnable_embedding"].zero_()
+        loss = loss2.sum() + ortho
+        if not self.finetune:
+            loss = loss - dis_loss
+        world = 1
+        if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            world = torch.distributed.get_world_size(self.pg)
+            if world > 1:
+                torch.distributed.all_reduce(self.flat_g, group=self.pg)         # one 395 KB NCCL all-reduce
+        self.opt_steps += 1
+        lr = self.lr0 * self.gamma ** ((self.opt_steps - 1) // self.step_size)
+        alpha = min(1 - 1 / (self.global_step + 1), self.ema_weight)
+        dev = self.flat_p.device
+        with torch.cuda.device(dev):
+            _lib.call("ucod_adamw_ema_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), ptr(self.flat_v),
+                      ptr(self.flat_ema), _u64(self.n), c_float(lr), c_float(self.betas[0]), c_float(self.betas[1]),
+                      c_float(self.eps), c_float(self.wd), int(self.opt_steps), c_float(1.0 / world), c_float(alpha),
+                      stream_ptr(dev))
+        self.global_step += 2
+        self.last = {"merged": merged, "dis_loss": dis_loss, "ortho": ortho, "bce": loss2}
+        return loss
