@@ -33,6 +33,12 @@ WORKLOAD = "UCOD-DPL_dinov2 first-stage eval, synthetic batch 64 @518x518 per GP
 VIT_GFLOP_PER_IMAGE = 279.6
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class from the round's
+# `ncu --set full` capture of this very command at batch 64 (profiles/r01_gemm2_ncu_summary.txt: mean over the 47
+# GEMM launches of a step; per shape 488 / 630 / 616 / 1058 MB, each <= the algorithmic bytes).  None = no capture.
+NCU_TRAFFIC_BYTES = {"gemm": 6.73e8, "attention": None}
+
+
 def _peaks():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -164,7 +170,6 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     B, NB = args.batch, args.rotate
     host = [synth_batch_u8((rank * NB + i) * B, B, IMAGE, IMAGE).pin_memory() for i in range(NB)]
     dev_in = [h.to(dev) for h in host]
-    out_host = torch.empty(B, IMAGE, IMAGE, dtype=torch.uint8).pin_memory()
 
     def barrier():
         if dist is not None:
@@ -196,17 +201,51 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     ms_c, work_c, n_c = (ctypes.c_double * KC)(), (ctypes.c_double * KC)(), (ctypes.c_longlong * KC)()
     lib.ucod_prof_collect(ms_c, work_c, n_c)
 
-    # ---- timed region 2: end to end through the public call, pinned host in, masks read back ----
-    for i in range(2):
-        pipe(host[i % NB].to(dev, non_blocking=True))
+    # ---- timed region 2: end to end through the public call, pinned host in, masks read back to the host ----
+    # Every step uploads its own input batch from pinned host memory and downloads its own masks; uploads of step
+    # i+1 and downloads of step i-1 run on a copy stream while step i computes (double-buffered device inputs and
+    # mask buffers), as a serving loop would.  All copies are inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    dev_buf = [torch.empty_like(dev_in[0]) for _ in range(2)]
+    out_dev = [torch.empty(B, IMAGE, IMAGE, dtype=torch.uint8, device=dev) for _ in range(2)]
+    out_hosts = [torch.empty(B, IMAGE, IMAGE, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    up_done = [torch.cuda.Event() for _ in range(2)]
+    comp_done = [torch.cuda.Event() for _ in range(2)]
+    down_done = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(n):
+        with torch.cuda.stream(copy_stream):
+            dev_buf[0].copy_(host[0], non_blocking=True)
+            up_done[0].record(copy_stream)
+        for i in range(n):
+            cur, nxt = i & 1, (i + 1) & 1
+            if i + 1 < n:
+                with torch.cuda.stream(copy_stream):
+                    if i >= 1:
+                        copy_stream.wait_event(comp_done[nxt])   # step i-1 no longer reads dev_buf[nxt]
+                    dev_buf[nxt].copy_(host[(i + 1) % NB], non_blocking=True)
+                    up_done[nxt].record(copy_stream)
+            main.wait_event(up_done[cur])
+            if i >= 2:
+                main.wait_event(down_done[cur])                  # out_dev[cur] has been downloaded
+            masks = pipe(dev_buf[cur])
+            out_dev[cur].copy_(masks)
+            comp_done[cur].record(main)
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(comp_done[cur])
+                out_hosts[cur].copy_(out_dev[cur], non_blocking=True)
+                down_done[cur].record(copy_stream)
+            if i >= 1:
+                down_done[cur ^ 1].synchronize()                 # the host consumes step i-1's masks
+        down_done[(n - 1) & 1].synchronize()
+
+    e2e_loop(2)
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
-    for i in range(args.steps):
-        x = host[i % NB].to(dev, non_blocking=True)
-        masks = pipe(x)
-        out_host.copy_(masks, non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the step's result is read on the host
+    e2e_loop(args.steps)
+    copy_stream.synchronize()
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -233,7 +272,8 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     if dom in (0, 1):
         achieved = work_c[dom] / (ms_c[dom] * 1e-3) / 1e12
         roof = {"kernel": names[dom], "bound": "tensor", "achieved": achieved, "peak": peaks["tensor"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["tensor"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peaks["tensor"],
+                "traffic": NCU_TRAFFIC_BYTES.get(names[dom]) if B == 64 else None,
                 "peak_source": peaks["source"] + ", sustained bf16"}
     else:
         achieved = work_c[dom] / (ms_c[dom] * 1e-3) / 1e9
