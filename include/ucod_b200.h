@@ -228,6 +228,20 @@ int ucod_adamw_ema_step(float* params, const float* grads, float* exp_avg, float
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                         float ema_alpha, void* stream);
 
+/* Backward of one `ucod_discriminator_fwd(bn_train = 1)` call for `TrainLoop.Discriminator_epoch`
+ * (engine/runner/loop_UCOD_DPL.py:230-255): loss = BCE(prob, label) averaged over n_total samples (the epoch's two
+ * calls — pseudo labels with label 1, student masks with label 0 — use n_total = 2*batch).  fwd_workspace: the
+ * workspace of that forward call.  Gradients (fp32, shapes of the weights) and `loss` (device scalar) are ACCUMULATED;
+ * zero them before the first call of a step.  Apply them with ucod_adamw_ema_step(ema = NULL). */
+typedef struct ucod_disc_grads {
+    float* conv1; float* bn1_w; float* bn1_b; float* conv2; float* bn2_w; float* bn2_b;
+    float* conv3; float* bn3_w; float* bn3_b; float* lin_w; float* lin_b;
+} ucod_disc_grads;
+uint64_t ucod_discriminator_bwd_workspace_bytes(int batch, int fs);
+int ucod_discriminator_bwd(const float* mask, int batch, int fs, const ucod_disc_weights* w, const float* prob,
+                           float label, int n_total, const ucod_disc_grads* g, float* loss, void* fwd_workspace,
+                           void* workspace, uint64_t workspace_bytes, void* stream);
+
 /* ---- CORAL second stage (SparseRefiner, eval) ----------------------------------------------------------
  * The dense part of the CSF block (models/modules/CSF.py:38-43, mlp.py:134-148) is assembled by the host from
  * ucod_layernorm_bf16 + ucod_gemm_bf16 + ucod_attention_shared_kv; the functions below are the remaining stages.

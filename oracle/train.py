@@ -92,3 +92,54 @@ def step_lr(lr0: float, optimizer_steps: int, step_size: int = 25, gamma: float 
     """StepLR stepped once per iteration (loop_UCOD_DPL.py:178): lr used for optimiser step number `optimizer_steps`
     (0-based)."""
     return lr0 * gamma ** (optimizer_steps // step_size)
+
+
+# ---- discriminator epoch step (engine/runner/loop_UCOD_DPL.py:230-255) --------------------------------------
+DIS_PARAM_ORDER = ["maskConv.layers.0.weight", "maskConv.layers.1.weight", "maskConv.layers.1.bias",
+                   "convs.0.layers.0.weight", "convs.0.layers.1.weight", "convs.0.layers.1.bias",
+                   "convs.1.layers.0.weight", "convs.1.layers.1.weight", "convs.1.layers.1.bias",
+                   "linear.weight", "linear.bias"]
+
+
+def _disc_forward_train(p: dict, sd: dict, mask: torch.Tensor, momentum: float = 0.1):
+    """Differentiable Discriminator.forward in train mode; updates the running statistics in `sd` in place."""
+    y = mask
+    for prefix, stride in (("maskConv.", 1), ("convs.0.", 2), ("convs.1.", 2)):
+        y = F.conv2d(y, p[prefix + "layers.0.weight"], None, stride=stride, padding=1)
+        y = F.batch_norm(y, sd[prefix + "layers.1.running_mean"], sd[prefix + "layers.1.running_var"],
+                         p[prefix + "layers.1.weight"], p[prefix + "layers.1.bias"], training=True, momentum=momentum,
+                         eps=1e-5)
+        y = F.leaky_relu(y, 0.1)
+    return torch.sigmoid(F.linear(torch.flatten(y, 1), p["linear.weight"], p["linear.bias"]))
+
+
+def discriminator_step(dis_sd: dict, state: dict, pseudo_mask: torch.Tensor, student_mask: torch.Tensor, lr: float,
+                       betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01):
+    """One iteration of Discriminator_epoch given the two binarised inputs: loss = BCE(cat(D(student), D(pseudo)),
+    cat(0, 1)); AdamW(dis_lr0) step.  dis_sd (incl. BatchNorm running stats) and state are updated in place."""
+    p = {k: dis_sd[k].clone().float().requires_grad_(True) for k in DIS_PARAM_ORDER}
+    probs_pseudo = _disc_forward_train(p, dis_sd, pseudo_mask.float())
+    probs_student = _disc_forward_train(p, dis_sd, student_mask.float())
+    B = pseudo_mask.shape[0]
+    label = torch.cat((torch.zeros(B), torch.ones(B))).unsqueeze(-1)
+    loss = F.binary_cross_entropy(torch.cat((probs_student, probs_pseudo), dim=0), label)
+    loss.backward()
+    grads = {k: p[k].grad.detach().clone() for k in DIS_PARAM_ORDER}
+    state["t"] += 1
+    t = state["t"]
+    b1, b2 = betas
+    with torch.no_grad():
+        for k in DIS_PARAM_ORDER:
+            w_, g = dis_sd[k], grads[k]
+            w_.mul_(1 - lr * weight_decay)
+            state["m"][k].mul_(b1).add_(g, alpha=1 - b1)
+            state["v"][k].mul_(b2).addcmul_(g, g, value=1 - b2)
+            denom = (state["v"][k].sqrt() / math.sqrt(1 - b2 ** t)).add_(eps)
+            w_.addcdiv_(state["m"][k], denom, value=-lr / (1 - b1 ** t))
+    return {"loss": loss.detach(), "grads": grads, "probs_pseudo": probs_pseudo.detach(),
+            "probs_student": probs_student.detach()}
+
+
+def new_dis_state(dis_sd: dict) -> dict:
+    return {"t": 0, "m": {k: torch.zeros_like(dis_sd[k], dtype=torch.float32) for k in DIS_PARAM_ORDER},
+            "v": {k: torch.zeros_like(dis_sd[k], dtype=torch.float32) for k in DIS_PARAM_ORDER}}

@@ -115,3 +115,36 @@ def test_adamw_ema_kernel_matches_torch():
                   _lib.c_float(1e-8), _lib.c_float(0.01), t, _lib.c_float(0.5), _lib.c_float(alpha), _lib.stream_ptr())
     np.testing.assert_allclose(dp.cpu().numpy(), ref.data.numpy(), atol=2e-6)
     np.testing.assert_allclose(de.cpu().numpy(), ema_ref.numpy(), atol=2e-6)
+
+
+def dis_inputs(seed: int, B: int = 4):
+    g = torch.Generator().manual_seed(seed)
+    pseudo = (torch.rand(B, 1, 68, 68, generator=g) < 0.4).float()
+    student = (torch.rand(B, 1, 68, 68, generator=g) < torch.rand(B, 1, 1, 1, generator=g)).float()
+    return pseudo, student
+
+
+def test_discriminator_epoch_steps_match_reference_golden():
+    """Three Discriminator_epoch iterations (fwd + hand-written conv/BN/LeakyReLU/linear backward, AdamW, StepLR,
+    running statistics) vs the reference module + torch autograd (tests/golden/train.npz).  All fp32."""
+    from ucod_dpl_b200.train import DiscriminatorTrainer
+    gold = np.load(ROOT / "tests" / "golden" / "train.npz")
+    D = Discriminator(SimpleNamespace(dis_use_features=False, dim=768, feature_size=68))
+    D.load_state_dict(odec.random_discriminator_state_dict(68, seed=31), strict=True)
+    D = D.cuda().train()
+    tr = DiscriminatorTrainer(D, lr0=1e-3)
+    names = [n for n, _ in D.named_parameters()]
+    for step in range(3):
+        pseudo, student = dis_inputs(200 + step)
+        loss = tr.step(pseudo.cuda(), student.cuda())
+        assert abs(float(loss) - float(gold[f"dis_loss_{step}"])) < 2e-4 * abs(float(gold[f"dis_loss_{step}"])) + 1e-5
+        if step == 0:
+            for n, view in zip(names, tr.grad_views):
+                ref = gold["dis_grad0_" + n].reshape(-1)
+                tol = 2e-3 * np.abs(ref).max() + 1e-7
+                assert np.abs(view.cpu().numpy() - ref).max() < tol, (n, np.abs(view.cpu().numpy() - ref).max(), tol)
+    for k, v in D.state_dict().items():
+        if "num_batches_tracked" in k:
+            assert int(v) == int(gold["dis_final_" + k])
+            continue
+        np.testing.assert_allclose(v.cpu().numpy(), gold["dis_final_" + k], atol=3e-5, rtol=2e-3, err_msg=k)

@@ -298,9 +298,10 @@ def main():
         fn()
         print("wrote", name, flush=True)
     try:
-        from tools.make_golden_train import gold_train
+        from tools.make_golden_train import gold_discriminator_train, gold_train
         if not only or "train" in only:
             gold_train()
+            gold_discriminator_train()
             print("wrote train", flush=True)
     except ImportError:
         pass

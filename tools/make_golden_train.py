@@ -66,3 +66,46 @@ def gold_train():
     for n, p in model.state_dict().items():
         res["final_" + n] = p.detach().numpy().copy()
     np.savez_compressed(GOLD / "train.npz", **res)
+
+
+def dis_inputs(seed: int, B: int = 4):
+    g = torch.Generator().manual_seed(seed)
+    pseudo = (torch.rand(B, 1, 68, 68, generator=g) < 0.4).float()
+    student = (torch.rand(B, 1, 68, 68, generator=g) < torch.rand(B, 1, 1, 1, generator=g)).float()
+    return pseudo, student
+
+
+def gold_discriminator_train():
+    """The reference's `Discriminator` module + BCELoss + torch AdamW/StepLR driven exactly like
+    `TrainLoop.Discriminator_epoch` (loop_UCOD_DPL.py:230-255) for three iterations."""
+    from engine.config.config import CfgNode as RefCfg
+    from models.discriminator import Discriminator
+
+    from oracle import decoder as odec
+    res = dict(np.load(GOLD / "train.npz"))
+    D = Discriminator(RefCfg({"dis_use_features": False, "dim": 768, "feature_size": 68}))
+    D.load_state_dict(odec.random_discriminator_state_dict(68, seed=31), strict=True)
+    D.train()
+    for p in D.parameters():
+        p.requires_grad = True
+    opt = torch.optim.AdamW(D.parameters(), lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=25, gamma=0.95)
+    bce = nn.BCELoss()
+    for step in range(3):
+        pseudo, student = dis_inputs(200 + step)
+        opt.zero_grad()
+        B = pseudo.shape[0]
+        label = torch.cat((torch.zeros(B), torch.ones(B)), dim=-1).unsqueeze(-1)
+        probs_pseudo = D(pseudo, None)
+        probs_student = D(student, None)
+        loss = bce(torch.cat((probs_student, probs_pseudo), dim=0), label)
+        loss.backward()
+        if step == 0:
+            for n, p in D.named_parameters():
+                res["dis_grad0_" + n] = p.grad.detach().numpy().copy()
+        opt.step()
+        sched.step()
+        res[f"dis_loss_{step}"] = np.float32(loss.item())
+    for n, p in D.state_dict().items():
+        res["dis_final_" + n] = p.detach().numpy().copy()
+    np.savez_compressed(GOLD / "train.npz", **res)

@@ -188,6 +188,21 @@ int ucod_adamw_ema_step(float* params, const float* grads, float* exp_avg, float
                           grad_scale, ema_alpha, reinterpret_cast<cudaStream_t>(stream));
 }
 
+uint64_t ucod_discriminator_bwd_workspace_bytes(int batch, int fs) {
+    return (uint64_t)discriminator_backward_workspace_bytes(batch, fs);
+}
+int ucod_discriminator_bwd(const float* mask, int batch, int fs, const ucod_disc_weights* w, const float* prob,
+                           float label, int n_total, const ucod_disc_grads* g, float* loss, void* fwd_workspace,
+                           void* workspace, uint64_t workspace_bytes, void* stream) {
+    UCOD_REQUIRE(w != nullptr && g != nullptr, "ucod_discriminator_bwd: null weights / grads");
+    DiscWeights d{w->conv1, w->bn1_w, w->bn1_b, w->bn1_mean, w->bn1_var, w->conv2, w->bn2_w, w->bn2_b, w->bn2_mean,
+                  w->bn2_var, w->conv3, w->bn3_w, w->bn3_b, w->bn3_mean, w->bn3_var, w->lin_w, w->lin_b};
+    DiscGrads gg{g->conv1, g->bn1_w, g->bn1_b, g->conv2, g->bn2_w, g->bn2_b, g->conv3, g->bn3_w, g->bn3_b, g->lin_w,
+                 g->lin_b};
+    return discriminator_backward(mask, batch, fs, d, prob, label, n_total, gg, loss, fwd_workspace, workspace,
+                                  (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+
 // ---- CORAL second stage ----
 int ucod_coral_entropy_select(const float* preds, int batch, int size, int window_size, float threshold,
                               float* entropy, float* scores, uint8_t* mask, void* scratch, void* stream) {

@@ -197,6 +197,180 @@ __global__ void apm_merge_kernel(const float* __restrict__ pl, const float* __re
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward of the discriminator for its own training epochs (`TrainLoop.Discriminator_epoch`,
+// engine/runner/loop_UCOD_DPL.py:230-255): BatchNorm in train mode (batch statistics), LeakyReLU(0.1), BCE.
+// With z = raw conv output, xh = (z - mu) / sigma, y = gamma xh + beta, h = lrelu(y):
+//   dy = dh * lrelu'(y);  dgamma = sum dy xh;  dbeta = sum dy;
+//   dz = gamma / sigma * (dy - mean(dy) - xh * mean(dy xh))
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bn_stats(int c, const double* sums, double count, float eps, float& mean, float& inv) {
+    const double m = sums[2 * c] / count;
+    double v = sums[2 * c + 1] / count - m * m;
+    if (v < 0) v = 0;
+    mean = (float)m;
+    inv = rsqrtf((float)v + eps);
+}
+
+// head: dt[b] = dprob-side gradient wrt the pre-sigmoid logit; dh3 = dt * lin_w; dlin_w += dt * h3; dlin_b += dt
+template <int C>
+__global__ void __launch_bounds__(256)
+    disc_head_bwd_kernel(const float* __restrict__ z3, const double* __restrict__ sums3, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, float eps, const float* __restrict__ lin_w,
+                         const float* __restrict__ dt, float* __restrict__ dh3, float* __restrict__ g_lin_w,
+                         float* __restrict__ g_lin_b, int B, int hw) {
+    __shared__ float s_scale[C], s_shift[C];
+    const double count = (double)B * hw;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float mean, inv;
+        bn_stats(c, sums3, count, eps, mean, inv);
+        s_scale[c] = gamma[c] * inv;
+        s_shift[c] = beta[c] - mean * gamma[c] * inv;
+    }
+    __syncthreads();
+    const int b = blockIdx.x, n = C * hw;
+    const float d = dt[b];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = i / hw;
+        float t = z3[(size_t)b * n + i] * s_scale[c] + s_shift[c];
+        t = t > 0.f ? t : LRELU * t;
+        dh3[(size_t)b * n + i] = d * lin_w[i];
+        atomicAdd(g_lin_w + i, d * t);
+    }
+    if (threadIdx.x == 0) atomicAdd(g_lin_b, d);
+}
+
+// pass 1 over a layer: dy = dh * lrelu'(y) (written in place over dh), per-channel sums of dy and dy*xh
+template <int C>
+__global__ void __launch_bounds__(256)
+    disc_bn_bwd_reduce_kernel(const float* __restrict__ z, float* __restrict__ dh, const double* __restrict__ sums,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                              double* __restrict__ dsums /*[C][2]*/, int B, int hw) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    float mean, inv;
+    bn_stats(c, sums, (double)B * hw, eps, mean, inv);
+    const float g = gamma[c], be = beta[c];
+    const size_t base = ((size_t)b * C + c) * hw;
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+        const float xh = (z[base + i] - mean) * inv;
+        const float y = g * xh + be;
+        const float dy = dh[base + i] * (y > 0.f ? 1.f : LRELU);
+        dh[base + i] = dy;
+        s0 += dy, s1 += dy * xh;
+    }
+    s0 = warp_sum(s0), s1 = warp_sum(s1);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&dsums[2 * c], (double)s0);
+        atomicAdd(&dsums[2 * c + 1], (double)s1);
+    }
+}
+// pass 2: dz = gamma*inv * (dy - mean(dy) - xh*mean(dy*xh)) in place; dgamma / dbeta written by block (0,c,0)
+template <int C>
+__global__ void __launch_bounds__(256)
+    disc_bn_bwd_apply_kernel(const float* __restrict__ z, float* __restrict__ dy, const double* __restrict__ sums,
+                             const float* __restrict__ gamma, float eps, const double* __restrict__ dsums,
+                             float* __restrict__ g_gamma, float* __restrict__ g_beta, int B, int hw) {
+    const int c = blockIdx.y, b = blockIdx.z;
+    const double count = (double)B * hw;
+    float mean, inv;
+    bn_stats(c, sums, count, eps, mean, inv);
+    const float m0 = (float)(dsums[2 * c] / count), m1 = (float)(dsums[2 * c + 1] / count);
+    const float k = gamma[c] * inv;
+    const size_t base = ((size_t)b * C + c) * hw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < hw; i += gridDim.x * blockDim.x) {
+        const float xh = (z[base + i] - mean) * inv;
+        dy[base + i] = k * (dy[base + i] - m0 - xh * m1);
+    }
+    if (blockIdx.x == 0 && b == 0 && threadIdx.x == 0) {
+        g_gamma[c] += (float)dsums[2 * c + 1];
+        g_beta[c] += (float)dsums[2 * c];
+    }
+}
+// weight gradient: one thread per weight element and image; dW[co,ci,k] += sum_pix dz[b,co,pix] * hin[b,ci,pix*s+k-1]
+template <int CIN, int COUT, int STRIDE, bool IN_BN>
+__global__ void __launch_bounds__(128)
+    disc_conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dz, const double* __restrict__ in_sums,
+                           const float* __restrict__ in_gamma, const float* __restrict__ in_beta, float eps,
+                           float* __restrict__ g_w, int B, int Hin, int Win, int Hout, int Wout) {
+    const int widx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (widx >= COUT * CIN * 9) return;
+    const int b = blockIdx.y;
+    const int co = widx / (CIN * 9), ci = (widx / 9) % CIN, k = widx % 9, ky = k / 3, kx = k % 3;
+    float scale = 1.f, shift = 0.f;
+    if (IN_BN) {
+        float mean, inv;
+        bn_stats(ci, in_sums, (double)B * Hin * Win, eps, mean, inv);
+        scale = in_gamma[ci] * inv;
+        shift = in_beta[ci] - mean * scale;
+    }
+    const float* img = in + ((size_t)b * CIN + ci) * Hin * Win;
+    const float* d = dz + ((size_t)b * COUT + co) * Hout * Wout;
+    float acc = 0.f;
+    for (int oy = 0; oy < Hout; ++oy) {
+        const int iy = oy * STRIDE + ky - 1;
+        if (iy < 0 || iy >= Hin) continue;
+        for (int ox = 0; ox < Wout; ++ox) {
+            const int ix = ox * STRIDE + kx - 1;
+            if (ix < 0 || ix >= Win) continue;
+            float t = img[iy * Win + ix];
+            if (IN_BN) {
+                t = t * scale + shift;
+                t = t > 0.f ? t : LRELU * t;
+            }
+            acc += d[oy * Wout + ox] * t;
+        }
+    }
+    atomicAdd(g_w + widx, acc);
+}
+// data gradient: dh_in[b,ci,iy,ix] = sum_{co,ky,kx} dz[b,co,oy,ox] * W[co,ci,ky,kx], iy = oy*s + ky - 1
+template <int CIN, int COUT, int STRIDE>
+__global__ void __launch_bounds__(128)
+    disc_conv_dgrad_kernel(const float* __restrict__ dz, const float* __restrict__ weight, float* __restrict__ dh_in,
+                           int Hin, int Win, int Hout, int Wout) {
+    __shared__ float s_w[COUT * CIN * 9];
+    for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) s_w[i] = weight[i];
+    __syncthreads();
+    const int b = blockIdx.y;
+    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= Hin * Win) return;
+    const int iy = pix / Win, ix = pix - iy * Win;
+    float acc[CIN];
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) acc[c] = 0.f;
+    for (int ky = 0; ky < 3; ++ky) {
+        const int ty = iy + 1 - ky;
+        if (ty < 0 || ty % STRIDE) continue;
+        const int oy = ty / STRIDE;
+        if (oy >= Hout) continue;
+        for (int kx = 0; kx < 3; ++kx) {
+            const int tx = ix + 1 - kx;
+            if (tx < 0 || tx % STRIDE) continue;
+            const int ox = tx / STRIDE;
+            if (ox >= Wout) continue;
+            for (int co = 0; co < COUT; ++co) {
+                const float d = dz[((size_t)b * COUT + co) * Hout * Wout + oy * Wout + ox];
+                const float* w = s_w + (size_t)co * CIN * 9 + ky * 3 + kx;
+#pragma unroll
+                for (int c = 0; c < CIN; ++c) acc[c] += d * w[c * 9];
+            }
+        }
+    }
+    float* dst = dh_in + (size_t)b * CIN * Hin * Win + pix;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) dst[(size_t)c * Hin * Win] = acc[c];
+}
+// dt[b] = (prob[b] - label) / n_total  (BCE mean over n_total samples, through the sigmoid); loss += BCE terms
+__global__ void disc_bce_grad_kernel(const float* __restrict__ prob, float label, float inv_n, float* __restrict__ dt,
+                                     float* __restrict__ loss, int B) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const float p = prob[b];
+    dt[b] = (p - label) * inv_n;
+    const float l = -(label * fmaxf(logf(p), -100.f) + (1.f - label) * fmaxf(logf(1.f - p), -100.f));
+    atomicAdd(loss, l * inv_n);
+}
+
 }  // namespace
 
 size_t discriminator_workspace_bytes(int B, int fs) {
@@ -233,6 +407,68 @@ int discriminator_forward(const float* mask, int B, int fs, const DiscWeights& w
         a2, w.conv3, a3, s3, s2, bn2, bn_train, update_running, eps, mom, B, h2, h2, h3, h3);
     disc_head_kernel<8><<<B, 256, 0, stream>>>(a3, s3, bn3, bn_train, update_running, eps, mom, w.lin_w, w.lin_b, prob,
                                                B, h3, h3);
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
+size_t discriminator_backward_workspace_bytes(int B, int fs) {
+    const int h2 = (fs + 1) / 2, h3 = (h2 + 1) / 2;
+    return ((size_t)B * 32 * fs * fs + (size_t)B * 16 * h2 * h2 + (size_t)B * 8 * h3 * h3 + B) * 4 + 56 * 2 * 8 + 1024;
+}
+
+// grads are ACCUMULATED (the epoch adds the pseudo-label call and the student call); the caller zeroes them.
+int discriminator_backward(const float* mask, int B, int fs, const DiscWeights& w, const float* prob, float label,
+                           int n_total, const DiscGrads& g, float* loss, void* fwd_workspace, void* workspace,
+                           size_t ws_bytes, cudaStream_t stream) {
+    UCOD_REQUIRE(mask && prob && loss && fwd_workspace && workspace, "discriminator_backward: null argument");
+    UCOD_REQUIRE(ws_bytes >= discriminator_backward_workspace_bytes(B, fs), "discriminator_backward: workspace too small");
+    const int h1 = fs, h2 = (fs + 2 - 3) / 2 + 1, h3 = (h2 + 2 - 3) / 2 + 1;
+    uint8_t* p = static_cast<uint8_t*>(fwd_workspace);
+    const double* sums = reinterpret_cast<const double*>(p);
+    p += 56 * 2 * 8;
+    const float* z1 = reinterpret_cast<const float*>(p);
+    p += (size_t)B * 32 * h1 * h1 * 4;
+    const float* z2 = reinterpret_cast<const float*>(p);
+    p += (size_t)B * 16 * h2 * h2 * 4;
+    const float* z3 = reinterpret_cast<const float*>(p);
+    const double *s1 = sums, *s2 = sums + 64, *s3 = sums + 96;
+    uint8_t* q = static_cast<uint8_t*>(workspace);
+    double* dsums = reinterpret_cast<double*>(q);
+    q += 56 * 2 * 8;
+    float* d1 = reinterpret_cast<float*>(q);
+    q += (size_t)B * 32 * h1 * h1 * 4;
+    float* d2 = reinterpret_cast<float*>(q);
+    q += (size_t)B * 16 * h2 * h2 * 4;
+    float* d3 = reinterpret_cast<float*>(q);
+    q += (size_t)B * 8 * h3 * h3 * 4;
+    float* dt = reinterpret_cast<float*>(q);
+    double *ds1 = dsums, *ds2 = dsums + 64, *ds3 = dsums + 96;
+    const float eps = 1e-5f;
+    UCOD_CHECK_CUDA(cudaMemsetAsync(dsums, 0, 56 * 2 * 8, stream));
+    ProfScope ps(KC_OTHER, stream, (double)B * (32 * h1 * h1 + 16 * h2 * h2 + 8 * h3 * h3) * 24);
+    disc_bce_grad_kernel<<<ceil_div(B, 128), 128, 0, stream>>>(prob, label, 1.0f / (float)n_total, dt, loss, B);
+    disc_head_bwd_kernel<8><<<B, 256, 0, stream>>>(z3, s3, w.bn3_w, w.bn3_b, eps, w.lin_w, dt, d3, g.lin_w, g.lin_b, B,
+                                                   h3 * h3);
+    // layer 3
+    disc_bn_bwd_reduce_kernel<8><<<dim3(2, 8, B), 256, 0, stream>>>(z3, d3, s3, w.bn3_w, w.bn3_b, eps, ds3, B, h3 * h3);
+    disc_bn_bwd_apply_kernel<8><<<dim3(2, 8, B), 256, 0, stream>>>(z3, d3, s3, w.bn3_w, eps, ds3, g.bn3_w, g.bn3_b, B,
+                                                                   h3 * h3);
+    disc_conv_wgrad_kernel<16, 8, 2, true><<<dim3(ceil_div(8 * 16 * 9, 128), B), 128, 0, stream>>>(
+        z2, d3, s2, w.bn2_w, w.bn2_b, eps, g.conv3, B, h2, h2, h3, h3);
+    disc_conv_dgrad_kernel<16, 8, 2><<<dim3(ceil_div(h2 * h2, 128), B), 128, 0, stream>>>(d3, w.conv3, d2, h2, h2, h3, h3);
+    // layer 2
+    disc_bn_bwd_reduce_kernel<16><<<dim3(4, 16, B), 256, 0, stream>>>(z2, d2, s2, w.bn2_w, w.bn2_b, eps, ds2, B, h2 * h2);
+    disc_bn_bwd_apply_kernel<16><<<dim3(4, 16, B), 256, 0, stream>>>(z2, d2, s2, w.bn2_w, eps, ds2, g.bn2_w, g.bn2_b, B,
+                                                                     h2 * h2);
+    disc_conv_wgrad_kernel<32, 16, 2, true><<<dim3(ceil_div(16 * 32 * 9, 128), B), 128, 0, stream>>>(
+        z1, d2, s1, w.bn1_w, w.bn1_b, eps, g.conv2, B, h1, h1, h2, h2);
+    disc_conv_dgrad_kernel<32, 16, 2><<<dim3(ceil_div(h1 * h1, 128), B), 128, 0, stream>>>(d2, w.conv2, d1, h1, h1, h2, h2);
+    // layer 1
+    disc_bn_bwd_reduce_kernel<32><<<dim3(8, 32, B), 256, 0, stream>>>(z1, d1, s1, w.bn1_w, w.bn1_b, eps, ds1, B, h1 * h1);
+    disc_bn_bwd_apply_kernel<32><<<dim3(8, 32, B), 256, 0, stream>>>(z1, d1, s1, w.bn1_w, eps, ds1, g.bn1_w, g.bn1_b, B,
+                                                                     h1 * h1);
+    disc_conv_wgrad_kernel<1, 32, 1, false><<<dim3(ceil_div(32 * 9, 128), B), 128, 0, stream>>>(
+        mask, d1, nullptr, nullptr, nullptr, eps, g.conv1, B, h1, h1, h1, h1);
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -21,6 +21,16 @@ struct DiscWeights {
 size_t discriminator_workspace_bytes(int B, int fs);
 int discriminator_forward(const float* mask, int B, int fs, const DiscWeights& w, int bn_train, int update_running,
                           float* prob, void* workspace, size_t ws_bytes, cudaStream_t stream);
+struct DiscGrads {  // fp32, same shapes as the weights; accumulated into
+    float *conv1, *bn1_w, *bn1_b, *conv2, *bn2_w, *bn2_b, *conv3, *bn3_w, *bn3_b, *lin_w, *lin_b;
+};
+size_t discriminator_backward_workspace_bytes(int B, int fs);
+// Backward of one discriminator_forward(bn_train = 1) call whose workspace is `fwd_workspace`; the loss is
+// BCE(prob, label) averaged over n_total samples (the epoch's two calls share n_total = 2B).  Gradients and
+// `loss` are accumulated.
+int discriminator_backward(const float* mask, int B, int fs, const DiscWeights& w, const float* prob, float label,
+                           int n_total, const DiscGrads& g, float* loss, void* fwd_workspace, void* workspace,
+                           size_t ws_bytes, cudaStream_t stream);
 int apm_binarize(const float* student, const float* teacher, const float* pl, float* s_mask, float* t_mask,
                  float* p_mask, size_t n, cudaStream_t stream);
 int apm_merge(const float* pl, const float* t_mask, const float* p_s, const float* p_p, float epoch_term,

@@ -188,3 +188,119 @@ class FirstStageTrainer:
         self.global_step += 2
         self.last = {"merged": merged, "dis_loss": dis_loss, "ortho": ortho, "bce": loss2}
         return loss
+
+
+class _DiscPtrs(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in (
+        "conv1", "bn1_w", "bn1_b", "bn1_mean", "bn1_var", "conv2", "bn2_w", "bn2_b", "bn2_mean", "bn2_var",
+        "conv3", "bn3_w", "bn3_b", "bn3_mean", "bn3_var", "lin_w", "lin_b")]
+
+
+class _DiscGradPtrs(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("conv1", "bn1_w", "bn1_b", "conv2", "bn2_w", "bn2_b", "conv3", "bn3_w",
+                                               "bn3_b", "lin_w", "lin_b")]
+
+
+class DiscriminatorTrainer:
+    """`TrainLoop.Discriminator_epoch` iterations (engine/runner/loop_UCOD_DPL.py:230-255): BCE on
+    [student masks -> 0, pseudo labels -> 1], AdamW(dis_lr0) + StepLR per iteration.  Forward and backward run in
+    csrc/discriminator.cu; parameters live in one flat buffer (the module's parameters are views of it)."""
+
+    _GRAD_FIELDS = ["conv1", "bn1_w", "bn1_b", "conv2", "bn2_w", "bn2_b", "conv3", "bn3_w", "bn3_b", "lin_w", "lin_b"]
+
+    def __init__(self, discriminator, *, lr0: float = 1e-3, step_lr_size: int = 25, step_lr_gamma: float = 0.95,
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, process_group=None):
+        self.D = discriminator
+        self.lr0, self.step_size, self.gamma = lr0, step_lr_size, step_lr_gamma
+        self.betas, self.eps, self.wd = betas, eps, weight_decay
+        self.pg = process_group
+        self.opt_steps = 0
+        params = list(discriminator.parameters())     # maskConv.{conv,bn.w,bn.b}, convs.0.*, convs.1.*, linear.{w,b}
+        dev = params[0].device
+        if dev.type != "cuda":
+            raise _lib.UcodError("DiscriminatorTrainer needs the discriminator on a CUDA device")
+        sizes = [p.numel() for p in params]
+        slots = [(s + 3) // 4 * 4 for s in sizes]
+        self.n = sum(slots)
+        self.flat_p = torch.zeros(self.n, device=dev)
+        self.flat_g = torch.zeros(self.n, device=dev)
+        self.flat_m = torch.zeros(self.n, device=dev)
+        self.flat_v = torch.zeros(self.n, device=dev)
+        self.grad_views = []
+        o = 0
+        for p, sz, slot in zip(params, sizes, slots):
+            self.flat_p[o:o + sz].copy_(p.detach().flatten())
+            p.data = self.flat_p[o:o + sz].view_as(p)
+            self.grad_views.append(self.flat_g[o:o + sz])
+            o += slot
+        self.loss = torch.zeros((), device=dev)
+
+    def _forward(self, mask):
+        D = self.D
+        B, _, fs, _ = mask.shape
+        dev = mask.device
+        lib = _lib.load()
+        lib.ucod_discriminator_workspace_bytes.restype = _u64
+        ws = torch.empty(int(lib.ucod_discriminator_workspace_bytes(B, fs)) + 1024, dtype=torch.uint8, device=dev)
+        off = (-ws.data_ptr()) % 1024
+        t = D._tensors()
+        w = _DiscPtrs(*[t[n].data_ptr() for n, _ in _DiscPtrs._fields_])
+        prob = torch.empty(B, 1, device=dev)
+        with torch.cuda.device(dev):
+            _lib.call("ucod_discriminator_fwd", ptr(mask), B, fs, ctypes.byref(w), 1, 1, ptr(prob),
+                      ctypes.c_void_p(ws.data_ptr() + off), _u64(ws.numel() - off), stream_ptr(dev))
+        for blk in (D.maskConv.layers, D.convs[0].layers, D.convs[1].layers):
+            blk[1].num_batches_tracked += 1
+        return prob, w, (ws, off)
+
+    def _backward(self, mask, prob, w, fwd_ws, label: float, n_total: int):
+        B, _, fs, _ = mask.shape
+        dev = mask.device
+        lib = _lib.load()
+        lib.ucod_discriminator_bwd_workspace_bytes.restype = _u64
+        bws = torch.empty(int(lib.ucod_discriminator_bwd_workspace_bytes(B, fs)) + 1024, dtype=torch.uint8, device=dev)
+        boff = (-bws.data_ptr()) % 1024
+        g = _DiscGradPtrs(*[v.data_ptr() for v in self.grad_views])
+        ws, off = fwd_ws
+        with torch.cuda.device(dev):
+            _lib.call("ucod_discriminator_bwd", ptr(mask), B, fs, ctypes.byref(w), ptr(prob), c_float(label),
+                      int(n_total), ctypes.byref(g), ptr(self.loss), ctypes.c_void_p(ws.data_ptr() + off),
+                      ctypes.c_void_p(bws.data_ptr() + boff), _u64(bws.numel() - boff), stream_ptr(dev))
+
+    @torch.no_grad()
+    def step(self, pseudo_masks: torch.Tensor, student_masks: torch.Tensor):
+        """pseudo_masks, student_masks: fp32 {0,1} [B,1,fs,fs] (already binarised like loop_UCOD_DPL.py:239-240).
+        Returns the BCE loss (device scalar)."""
+        pm, sm = pseudo_masks.float().contiguous(), student_masks.float().contiguous()
+        B = pm.shape[0]
+        self.flat_g.zero_()
+        self.loss.zero_()
+        prob_p, w, ws_p = self._forward(pm)           # the reference evaluates the pseudo labels first (:244-245)
+        self._backward(pm, prob_p, w, ws_p, 1.0, 2 * B)
+        prob_s, w, ws_s = self._forward(sm)
+        self._backward(sm, prob_s, w, ws_s, 0.0, 2 * B)
+        world = 1
+        if torch.distributed.is_available() and torch.distributed.is_initialized():
+            world = torch.distributed.get_world_size(self.pg)
+            if world > 1:
+                torch.distributed.all_reduce(self.flat_g, group=self.pg)
+        self.opt_steps += 1
+        lr = self.lr0 * self.gamma ** ((self.opt_steps - 1) // self.step_size)
+        dev = self.flat_p.device
+        with torch.cuda.device(dev):
+            _lib.call("ucod_adamw_ema_step", ptr(self.flat_p), ptr(self.flat_g), ptr(self.flat_m), ptr(self.flat_v),
+                      ptr(None), _u64(self.n), c_float(lr), c_float(self.betas[0]), c_float(self.betas[1]),
+                      c_float(self.eps), c_float(self.wd), int(self.opt_steps), c_float(1.0 / world), c_float(0.0),
+                      stream_ptr(dev))
+        self.last = {"probs_pseudo": prob_p, "probs_student": prob_s}
+        return self.loss.clone()
+
+    @torch.no_grad()
+    def epoch_step(self, model, key_tokens_bf16: torch.Tensor, grid_in, pseudo_labels: torch.Tensor, feature_size=68):
+        """One `Discriminator_epoch` iteration from cached keys: student forward (no grad) -> sigmoid > 0.5,
+        pseudo labels bilinear 16 -> fs then > 0.5, then `step`."""
+        fs = (feature_size, feature_size)
+        fg, _, _ = model.decoder.forward_tokens(key_tokens_bf16, grid_in, fs, want_bg=False)
+        pl = ops.upsample_bilinear(pseudo_labels.float(), fs)
+        s_mask, _, p_mask = ops.apm_binarize(fg, fg, pl)
+        return self.step(p_mask, s_mask)
