@@ -15,7 +15,9 @@
 //        the whole 128-wide S row lives in registers (S is read from TMEM exactly once).
 // Measured on B200 (tools/att_timeline.py, tools/ubench/mma_rate.cu): the softmax warps are busy ~85 % of a tile
 // period (exp phase bound by the 16/clk/SM MUFU rate shared by the two resident CTAs); dependent N=64 P.V MMAs
-// retire every ~74 clk (latency-bound chain), S MMAs every 67 clk.
+// retire every ~74 clk (latency-bound chain), S MMAs every 67 clk.  Tried and rejected (measured slower): a
+// TMA L2 prefetch of K/V, the MMA issuer in the high warp ids, 25 % of the exponentials as an FMA-pipe polynomial
+// (UCOD_ATT_POLY_EVERY), and two softmax threads per row (8 softmax warps, shared-memory max/sum exchange).
 // TMEM: S fp32 [0,128) | P bf16-packed [128,192) | O fp32 [192,192+D).
 //   S_j  = Q K_j^T                (SS MMA, both operands K-major SW128 tiles)
 //   P_j  = exp2(S_j*c - m_ref)    (written back to TMEM as packed bf16; never touches shared memory)
@@ -86,6 +88,21 @@ __device__ __forceinline__ float ex2_approx(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax of 2^f on [-0.5, 0.5], relative error 7.5e-5 — far
+// below the bf16 resolution of P).  Used for a fixed fraction of the probabilities so that the 16-lane MUFU unit,
+// which bounds the softmax phase at head_dim 64, is not the only exponential engine.  x <= 8 on this path.
+__device__ __forceinline__ float ex2_poly(float x) {
+    x = fmaxf(x, -126.f);
+    const float t = x + 12582912.f;                 // 1.5 * 2^23: round-to-nearest integer lands in the mantissa
+    const float f = x - (t - 12582912.f);           // in [-0.5, 0.5]
+    float p = fmaf(0.05517121031880379f, f, 0.24261027574539185f);
+    p = fmaf(p, f, 0.6932609677314758f);
+    p = fmaf(p, f, 0.9999281167984009f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+#ifndef UCOD_ATT_POLY_EVERY
+#define UCOD_ATT_POLY_EVERY 0  // every n-th exponential goes to the FMA pipe (0 = all on MUFU; measured: 4 is 6 % slower)
+#endif
 template <int N>
 __device__ __forceinline__ void reg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
@@ -272,14 +289,30 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             bool grow = false;
             if (j == 0) {
                 m_ref = ms;
-            } else {
-                if (ms > m_ref + 8.f) {
-                    alpha = ex2_approx(m_ref - ms);
-                    m_ref = ms;
-                    grow = true;
-                }
-                // previous P V must have retired before P is overwritten / O is rescaled
-                TL(2, j, 3);
+            } else if (ms > m_ref + 8.f) {
+                alpha = ex2_approx(m_ref - ms);
+                m_ref = ms;
+                grow = true;
+            }
+            TL(2, j, 3);
+            // ---- probabilities -> packed bf16 (registers) ----
+            const float neg_m = -m_ref;
+            float ls[4] = {0.f, 0.f, 0.f, 0.f};
+            uint32_t pk[64];
+#pragma unroll
+            for (int i = 0; i < 64; ++i) {
+                const float x0 = fmaf(__uint_as_float(u[2 * i]), scale_log2e, neg_m);
+                const float x1 = fmaf(__uint_as_float(u[2 * i + 1]), scale_log2e, neg_m);
+                const float p0 = ex2_approx(x0);
+                // every UCOD_ATT_POLY_EVERY-th exponential (the odd element of every (EVERY/2)-th pair) on the FMA pipe
+                const float p1 = (UCOD_ATT_POLY_EVERY >= 2 && (i % (UCOD_ATT_POLY_EVERY / 2)) == 0) ? ex2_poly(x1)
+                                                                                                   : ex2_approx(x1);
+                ls[i & 3] += p0 + p1;
+                pk[i] = pack_bf16x2(p0, p1);
+            }
+            l_run = l_run * alpha + (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            // ---- the previous P V must have retired before P is overwritten / O is rescaled ----
+            if (j > 0) {
                 mbar_wait(bar_pv, (j - 1) & 1);
                 TL(2, j, 4);
                 tc_fence_after();
@@ -293,25 +326,10 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
                         tmem_st32(tmem_o + lane_off + c * 32, o);
                     }
-                    l_run *= alpha;
                 }
             }
-            // ---- probabilities -> packed bf16 -> TMEM ----
-            const float neg_m = -m_ref;
-            float ls[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t pk[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(u[64 * half + 2 * i]), scale_log2e, neg_m));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(u[64 * half + 2 * i + 1]), scale_log2e, neg_m));
-                    ls[i & 3] += p0 + p1;
-                    pk[i] = pack_bf16x2(p0, p1);
-                }
-                tmem_st32(tmem_p + lane_off + half * 32, pk);
-            }
-            l_run += (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            tmem_st32(tmem_p + lane_off, reinterpret_cast<uint32_t(&)[32]>(pk[0]));
+            tmem_st32(tmem_p + lane_off + 32, reinterpret_cast<uint32_t(&)[32]>(pk[32]));
             TL(2, j, 5);
             tmem_wait_st();
             tc_fence_before();
