@@ -122,15 +122,36 @@ __global__ void __launch_bounds__(PL_THREADS)
         __syncthreads();
     }
 
-    // ---- one warp per patch: cos(ref, p) ----
+    // ---- one warp per patch: cos(ref, p); 128-bit key loads (8 bf16 / 4 fp32 per lane and step) ----
+    constexpr int EPV = 16 / sizeof(TK);  // elements per 16-byte vector (a vector never straddles a 64-wide head)
+    const int nvec = C / EPV;
     float wmax = -INFINITY;
     for (int p = warp; p < P; p += nw) {
-        const TK* kr = keys_b + (size_t)p * C;
+        const uint4* kr = reinterpret_cast<const uint4*>(keys_b + (size_t)p * C);
         float dot = 0.f, q = 0.f;
-        for (int i = lane; i < C; i += 32) {
-            const float v = key_at<TK>(kr, i) * s_beta[i >> 6];
-            dot += v * s_ref[i];
-            q += v * v;
+#pragma unroll 3
+        for (int v = lane; v < nvec; v += 32) {
+            const uint4 raw = __ldg(kr + v);
+            const float beta = s_beta[(v * EPV) >> 6];
+            const float* rf = s_ref + v * EPV;
+            float x[EPV];
+            if constexpr (sizeof(TK) == 2) {
+                const uint32_t wds[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    x[2 * e] = __uint_as_float(wds[e] << 16);
+                    x[2 * e + 1] = __uint_as_float(wds[e] & 0xffff0000u);
+                }
+            } else {
+                x[0] = __uint_as_float(raw.x), x[1] = __uint_as_float(raw.y);
+                x[2] = __uint_as_float(raw.z), x[3] = __uint_as_float(raw.w);
+            }
+#pragma unroll
+            for (int e = 0; e < EPV; ++e) {
+                const float val = x[e] * beta;
+                dot += val * rf[e];
+                q += val * val;
+            }
         }
         dot = warp_sum(dot);
         q = warp_sum(q);
