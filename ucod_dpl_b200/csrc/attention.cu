@@ -17,7 +17,8 @@
 // period (exp phase bound by the 16/clk/SM MUFU rate shared by the two resident CTAs); dependent N=64 P.V MMAs
 // retire every ~74 clk (latency-bound chain), S MMAs every 67 clk.  Tried and rejected (measured slower): a
 // TMA L2 prefetch of K/V, the MMA issuer in the high warp ids, 25 % of the exponentials as an FMA-pipe polynomial
-// (UCOD_ATT_POLY_EVERY), and two softmax threads per row (8 softmax warps, shared-memory max/sum exchange).
+// (UCOD_ATT_POLY_EVERY), two softmax threads per row (8 softmax warps, shared-memory max/sum exchange), and
+// staggering the two co-resident CTAs by half a tile period (no effect: the exp phases are not MUFU-contended).
 // TMEM: S fp32 [0,128) | P bf16-packed [128,192) | O fp32 [192,192+D).
 //   S_j  = Q K_j^T                (SS MMA, both operands K-major SW128 tiles)
 //   P_j  = exp2(S_j*c - m_ref)    (written back to TMEM as packed bf16; never touches shared memory)
@@ -31,6 +32,8 @@
 // reached from data/utils/feature_extractor.py:49-59, and nn.MultiheadAttention in models/modules/mlp.py:134-148.
 #include "attention.cuh"
 #include "prof.cuh"
+
+#include <stdlib.h>
 
 namespace ucod {
 
@@ -186,14 +189,14 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j & 1;
                 const uint32_t ph = ((uint32_t)(j >> 1) & 1) ^ 1;
-                mbar_wait(&bar_kempty[st], ph);
+                mbar_wait_parked(&bar_kempty[st], ph);
                 TL(0, j, 0);
                 mbar_arrive_expect_tx(&bar_kfull[st], C::SK_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < C::NKB; ++kb)
                     tma_load_3d(sK + st * C::SK_BYTES + kb * C::BLK_BYTES, &tm_k, &bar_kfull[st], col0 + kb * 64,
                                 j * C::BN, bkv);
-                mbar_wait(&bar_vempty[st], ph);
+                mbar_wait_parked(&bar_vempty[st], ph);
                 TL(0, j, 1);
                 mbar_arrive_expect_tx(&bar_vfull[st], C::SV_BYTES);
 #pragma unroll
@@ -218,24 +221,24 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                 umma_commit(&bar_kempty[j & 1]);
                 umma_commit(bar_s);
             };
-            mbar_wait(bar_q, 0);
-            mbar_wait(&bar_kfull[0], 0);
+            mbar_wait_parked(bar_q, 0);
+            mbar_wait_parked(&bar_kfull[0], 0);
             tc_fence_after();
             issue_s(0);
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j & 1;
                 if (j + 1 < n_tiles) {
-                    mbar_wait(&bar_kfull[(j + 1) & 1], ((j + 1) >> 1) & 1);
+                    mbar_wait_parked(&bar_kfull[(j + 1) & 1], ((j + 1) >> 1) & 1);
                     TL(1, j, 0);
-                    mbar_wait(bar_sfree, j & 1);  // S_j is in the softmax warps' registers
+                    mbar_wait_parked(bar_sfree, j & 1);  // S_j is in the softmax warps' registers
                     TL(1, j, 1);
                     tc_fence_after();
                     issue_s(j + 1);
                     TL(1, j, 2);
                 }
-                mbar_wait(&bar_vfull[st], (j >> 1) & 1);
+                mbar_wait_parked(&bar_vfull[st], (j >> 1) & 1);
                 TL(1, j, 3);
-                mbar_wait(bar_p, j & 1);  // P_j published
+                mbar_wait_parked(bar_p, j & 1);  // P_j published
                 TL(1, j, 4);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sV + st * C::SV_BYTES);

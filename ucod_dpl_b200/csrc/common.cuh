@@ -100,6 +100,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// Same wait for the single-thread producer / MMA-issuer roles: the try_wait carries a suspend-time hint so the
+// hardware parks the warp until the phase completes (or ~`hint_ns` elapse) instead of re-polling every few dozen
+// cycles — the polls compete for issue slots with the compute warps of the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t* bar, uint32_t parity, uint32_t hint_ns = 20000) {
+    uint32_t ok = 0;
+    long long t0 = 0;
+    uint32_t spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+            : "memory");
+        if (ok) return;
+        if (spins++ == 0) t0 = clock64();
+        if ((spins & 0xff) == 0 && (clock64() - t0) > UCOD_MBAR_TIMEOUT_CYCLES) {
+            printf("ucod: mbarrier timeout (parked) block (%d,%d) thread %d\n", blockIdx.x, blockIdx.y, threadIdx.x);
+            __trap();
+        }
+    }
+}
+
 // ---- TMA ----
 __device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
