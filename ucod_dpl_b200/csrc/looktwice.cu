@@ -268,7 +268,8 @@ __device__ __forceinline__ double filt_bicubic(double x) {
 }
 
 // job geometry for one axis: in_size source samples -> out_size samples (box = whole source)
-// bounds[(job*2+axis)*out_cap + xx] = {xmin, count} ; coef[((job*2+axis)*out_cap + xx)*RS_KMAX + k]
+// bounds[(job*2+axis)*out_cap + xx] = {xmin, count} ; coef[((job*2+axis)*RS_KMAX + k)*out_cap + xx]
+// (tap-major, so that neighbouring output samples read neighbouring coefficients: coalesced in the horizontal passes)
 __global__ void resample_coeffs_kernel(const int* __restrict__ in_sizes /*[njobs,2] (w,h)*/,
                                        const int* __restrict__ out_sizes /*[njobs,2] (w,h)*/, int njobs, int out_cap,
                                        int bicubic, int2* __restrict__ bounds, int* __restrict__ coef,
@@ -303,14 +304,13 @@ __global__ void resample_coeffs_kernel(const int* __restrict__ in_sizes /*[njobs
     }
     const size_t o = ((size_t)job * 2 + axis) * out_cap + xx;
     bounds[o] = make_int2(xmin, n);
-    int* kk = coef + o * RS_KMAX;
+    int* kk = coef + ((size_t)job * 2 + axis) * RS_KMAX * out_cap + xx;  // stride out_cap between taps
     for (int x = 0; x < n; ++x) {
         double k = w[x];
         if (ww != 0.0) k = __ddiv_rn(k, ww);
         const double f = __dmul_rn(k, (double)(1 << RS_PRECISION_BITS));
-        kk[x] = k < 0 ? (int)__dadd_rn(-0.5, f) : (int)__dadd_rn(0.5, f);
+        kk[(size_t)x * out_cap] = k < 0 ? (int)__dadd_rn(-0.5, f) : (int)__dadd_rn(0.5, f);
     }
-    for (int x = n; x < RS_KMAX; ++x) kk[x] = 0;
 }
 
 __device__ __forceinline__ uint8_t clip8(int v) {
@@ -337,14 +337,14 @@ __global__ void crop_hpass_kernel(const uint8_t* __restrict__ images, int H0, in
     const int sy = jb[2] + y_first + r;  // source row in the original image
     const size_t hb = ((size_t)job * 2 + 0) * out_cap + xx;
     const int2 bd = bounds[hb];
-    const int* kk = coef + hb * RS_KMAX;
+    const int* kk = coef + ((size_t)job * 2 + 0) * RS_KMAX * out_cap + xx;
     int acc = 1 << (RS_PRECISION_BITS - 1);
     if (sy >= 0 && sy < H0) {
         const uint8_t* row = images + (size_t)jb[0] * img_stride + (size_t)c * ch_stride + (size_t)sy * row_stride;
         for (int k = 0; k < bd.y; ++k) {
             const int sx = jb[1] + bd.x + k;
             const int px = (sx >= 0 && sx < W0) ? row[(size_t)sx * px_stride] : 0;
-            acc += px * kk[k];
+            acc += px * __ldg(kk + (size_t)k * out_cap);
         }
     }
     tmp[(((size_t)job * 3 + c) * tmp_rows + r) * out_w + xx] = clip8(acc);
@@ -367,10 +367,11 @@ __global__ void crop_vpass_kernel(const uint8_t* __restrict__ tmp, const int* __
     const size_t vb = ((size_t)job * 2 + 1) * out_cap;
     const int y_first = bounds[vb].x;
     const int2 bd = bounds[vb + yy];
-    const int* kk = coef + (vb + yy) * RS_KMAX;
+    const int* kk = coef + ((size_t)job * 2 + 1) * RS_KMAX * out_cap + yy;  // same address for the whole block
     const uint8_t* src = tmp + ((size_t)job * 3 + c) * tmp_rows * out_w + xx;
     int acc = 1 << (RS_PRECISION_BITS - 1);
-    for (int k = 0; k < bd.y; ++k) acc += (int)src[(size_t)(bd.x - y_first + k) * out_w] * kk[k];
+    for (int k = 0; k < bd.y; ++k)
+        acc += (int)src[(size_t)(bd.x - y_first + k) * out_w] * __ldg(kk + (size_t)k * out_cap);
     *dst = clip8(acc);
 }
 
@@ -386,10 +387,10 @@ __global__ void paste_hpass_kernel(const float* __restrict__ logits, int g_h, in
     if (w <= 0 || h <= 0 || xx >= w || xx >= out_cap) return;
     const size_t hb = ((size_t)job * 2 + 0) * out_cap + xx;
     const int2 bd = bounds[hb];
-    const int* kk = coef + hb * RS_KMAX;
+    const int* kk = coef + ((size_t)job * 2 + 0) * RS_KMAX * out_cap + xx;
     const float* row = logits + ((size_t)job * g_h + r) * g_w;
     int acc = 1 << (RS_PRECISION_BITS - 1);
-    for (int k = 0; k < bd.y; ++k) acc += (row[bd.x + k] > 0x1.8p-24f ? 255 : 0) * kk[k];
+    for (int k = 0; k < bd.y; ++k) acc += (row[bd.x + k] > 0x1.8p-24f ? 255 : 0) * __ldg(kk + (size_t)k * out_cap);
     tmp[((size_t)job * g_h + r) * out_cap + xx] = clip8(acc);
 }
 
@@ -407,11 +408,11 @@ __global__ void paste_vpass_kernel(const uint8_t* __restrict__ tmp, int g_h, con
     if (dx < 0 || dx >= S_w || dy < 0 || dy >= S_h) return;  // Image.paste clips
     const size_t vb = ((size_t)job * 2 + 1) * out_cap + yy;
     const int2 bd = bounds[vb];
-    const int* kk = coef + vb * RS_KMAX;
+    const int* kk = coef + ((size_t)job * 2 + 1) * RS_KMAX * out_cap + yy;
     // the horizontal pass covered source rows y_first.. ; for an un-cropped source y_first is bounds[0].xmin
     const uint8_t* src = tmp + (size_t)job * g_h * out_cap + xx;
     int acc = 1 << (RS_PRECISION_BITS - 1);
-    for (int k = 0; k < bd.y; ++k) acc += (int)src[(size_t)(bd.x + k) * out_cap] * kk[k];
+    for (int k = 0; k < bd.y; ++k) acc += (int)src[(size_t)(bd.x + k) * out_cap] * __ldg(kk + (size_t)k * out_cap);
     mask[((size_t)jb[0] * S_h + dy) * S_w + dx] = clip8(acc);
 }
 
