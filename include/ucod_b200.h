@@ -279,6 +279,17 @@ int ucod_features_to_tokens_f32(const float* in, float* out, int batch, int chan
 int ucod_resize_tokens_bilinear(const float* in, float* out_f32, void* out_bf16, int n, int gin_h, int gin_w,
                                 int gout_h, int gout_w, int channels, void* stream);
 
+/* ---- COD metric suite (next row after the model path) ------------------------------------------
+ * `statistics.step` per image (engine/utils/metrics/metric.py:19-74,128-531) in fp64 on the device:
+ * gt, pred fp32 [batch,h,w] (any value range: `_prepare_data` normalisation is applied);
+ * out fp64 [batch, UCOD_METRICS_OUT] = acc, iou, mae, s-measure, adaptive E, adaptive F, weighted F,
+ * E curve[256], F curve[256] (index t = threshold 255 - t, like the reference's flipped cumulative histograms).
+ * Dataset results are the means over images (and max / mean of the mean curves), `statistics.get_result`. */
+#define UCOD_METRICS_OUT 519
+uint64_t ucod_cod_metrics_workspace_bytes(int batch, int h, int w);
+int ucod_cod_metrics(const float* gt, const float* pred, int batch, int h, int w, double* out, void* workspace,
+                     uint64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -298,6 +298,13 @@ def main():
         fn()
         print("wrote", name, flush=True)
     try:
+        from tools.make_golden_metrics import gold_metrics
+        if not only or "metrics" in only:
+            gold_metrics()
+            print("wrote metrics", flush=True)
+    except ImportError:
+        pass
+    try:
         from tools.make_golden_train import gold_discriminator_train, gold_train
         if not only or "train" in only:
             gold_train()

@@ -9,6 +9,7 @@
 #include "pseudo_label.cuh"
 #include "looktwice.cuh"
 #include "discriminator.cuh"
+#include "metrics.cuh"
 
 using namespace ucod;
 
@@ -243,6 +244,16 @@ int ucod_resize_tokens_bilinear(const float* in, float* out_f32, void* out_bf16,
                                 int gout_h, int gout_w, int channels, void* stream) {
     return resize_tokens_bilinear(in, out_f32, out_bf16, n, gin_h, gin_w, gout_h, gout_w, channels,
                                   reinterpret_cast<cudaStream_t>(stream));
+}
+
+// ---- COD metric suite ----
+uint64_t ucod_cod_metrics_workspace_bytes(int batch, int h, int w) {
+    return (uint64_t)cod_metrics_workspace_bytes(batch, h, w);
+}
+int ucod_cod_metrics(const float* gt, const float* pred, int batch, int h, int w, double* out, void* workspace,
+                     uint64_t workspace_bytes, void* stream) {
+    return cod_metrics(gt, pred, batch, h, w, out, workspace, (size_t)workspace_bytes,
+                       reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

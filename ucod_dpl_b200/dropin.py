@@ -18,6 +18,9 @@ ALIASES = {
     "engine.registry": "ucod_dpl_b200.engine.registry",
     "engine.registry.registry": "ucod_dpl_b200.engine.registry.registry",
     "engine.registry.root": "ucod_dpl_b200.engine.registry.root",
+    "engine.utils": "ucod_dpl_b200.engine.utils",
+    "engine.utils.metrics": "ucod_dpl_b200.engine.utils.metrics",
+    "engine.utils.metrics.metric": "ucod_dpl_b200.engine.utils.metrics.metric",
     "engine.runner": "ucod_dpl_b200.engine.runner",
     "engine.runner.loop_UCOD_DPL": "ucod_dpl_b200.engine.runner.loop_UCOD_DPL",
     "engine.runner.loop_CORAL": "ucod_dpl_b200.engine.runner.loop_CORAL",
