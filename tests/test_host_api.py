@@ -176,3 +176,43 @@ def test_argument_errors_do_not_need_a_gpu():
     rc = lib.ucod_gemm_bf16(None, 8, None, 8, 0, 128, 64, 0, None, None, 128, None)
     assert rc != 0
     assert b"gemm" in lib.ucod_last_error()
+
+
+def test_cache_format_interop_with_reference(tmp_path):
+    """MetaListPickleIO writes what the reference reads and reads what the reference writes
+    (engine/utils/fileio/backend/ioctl/pickleio.py:54-142)."""
+    from ucod_dpl_b200.engine.utils.fileio import MetaListPickleIO
+    items = [torch.full((1, 16, 16), float(i)) for i in range(5)]
+    io = MetaListPickleIO(base_path=tmp_path / "ours")
+    assert io.mode == "w"
+    io.dump_list(items)
+    assert sorted(p.name for p in (tmp_path / "ours").iterdir()) == ["data_%d.pkl" % i for i in range(5)] + ["index.json"]
+    assert json.loads((tmp_path / "ours" / "index.json").read_text()) == {str(i): f"data_{i}.pkl" for i in range(5)}
+    rd = MetaListPickleIO(base_path=tmp_path / "ours")
+    assert rd.mode == "r" and rd.len() == 5 and torch.equal(rd.read_file(3), items[3])
+    with pytest.raises(AssertionError):
+        rd.write_file(9, items[0])
+    (tmp_path / "ours" / "data_2.pkl").unlink()                      # a missing item invalidates the cache
+    assert MetaListPickleIO(base_path=tmp_path / "ours").mode == "w"
+    if not Path("/root/reference/engine/utils/fileio/backend/ioctl/pickleio.py").exists():
+        return                                                       # GPU box: no reference tree
+    # build box: drive the REAL reference class in a subprocess (its package needs the shims of tools/make_golden.py)
+    import subprocess, sys
+    io2 = MetaListPickleIO(base_path=tmp_path / "ours2")
+    io2.dump_list(items)
+    code = f"""
+import sys, torch
+sys.path.insert(0, {str(ROOT)!r})
+import tools.make_golden as mg
+mg.install_shims()
+from engine.utils.fileio.backend.ioctl.pickleio import MetaListPickleIO as Ref
+rd = Ref(base_path={str(tmp_path / 'ours2')!r})
+assert rd.mode == 'r' and rd.len() == 5 and float(rd.read_file(4)[0, 0, 0]) == 4.0
+wr = Ref(base_path={str(tmp_path / 'theirs')!r})
+wr.dump_list([torch.full((1, 16, 16), float(i)) for i in range(5)])
+print('REF_OK')
+"""
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert "REF_OK" in out.stdout, out.stderr[-2000:]
+    ours_rd = MetaListPickleIO(base_path=tmp_path / "theirs")
+    assert ours_rd.mode == "r" and ours_rd.len() == 5 and torch.equal(ours_rd.read_file(1), items[1])

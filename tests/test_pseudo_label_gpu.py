@@ -111,3 +111,22 @@ def test_generator_end_to_end_small():
         want = opl.refine_post_process((1 - bkg[0]).numpy())
         agree += (want == masks[b]).mean()
     assert agree / 3 >= 0.99
+
+
+def test_pseudo_label_cache_written_in_reference_format(tmp_path):
+    """generate_pseudo_label.py:141-150 equivalent: masks land in data_{i}.pkl + index.json as CPU float [1,16,16]."""
+    from ucod_dpl_b200.engine.utils.fileio import MetaListPickleIO
+    from ucod_dpl_b200.generate_pseudo_label import PseudoLabelGenerator, generate_pseudo_label_cache
+    from ucod_dpl_b200.synth import random_vit_state_dict, synth_batch_u8
+    from ucod_dpl_b200.vit import spec_for
+    gen = PseudoLabelGenerator(random_vit_state_dict(spec_for("dinov2"), seed=0), "dinov2")
+    imgs = synth_batch_u8(0, 6, 224, 224)
+    n = generate_pseudo_label_cache(gen, imgs, tmp_path / "TR-SYNTH", batch=4)
+    assert n == 6
+    rd = MetaListPickleIO(base_path=tmp_path / "TR-SYNTH")
+    assert rd.mode == "r" and rd.len() == 6
+    direct = gen(imgs.cuda()).cpu()
+    for i in range(6):
+        item = rd.read_file(i)
+        assert item.shape == (1, 16, 16) and item.dtype == torch.float32 and not item.is_cuda
+        assert torch.equal(item[0].to(torch.uint8), direct[i])

@@ -19,6 +19,7 @@ ALIASES = {
     "engine.registry.registry": "ucod_dpl_b200.engine.registry.registry",
     "engine.registry.root": "ucod_dpl_b200.engine.registry.root",
     "engine.utils": "ucod_dpl_b200.engine.utils",
+    "engine.utils.fileio": "ucod_dpl_b200.engine.utils.fileio",
     "engine.utils.metrics": "ucod_dpl_b200.engine.utils.metrics",
     "engine.utils.metrics.metric": "ucod_dpl_b200.engine.utils.metrics.metric",
     "engine.runner": "ucod_dpl_b200.engine.runner",

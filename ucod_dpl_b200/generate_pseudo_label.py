@@ -56,3 +56,36 @@ def generate_mask(image_path, th_bkg: float = 0.6):
     x = tf(Image.open(image_path).convert("RGB")).unsqueeze(0).cuda()
     _generator.th_bkg = th_bkg
     return _generator(x)[0].cpu().unsqueeze(0).float()
+
+
+def write_pseudo_label_cache(masks_u8: torch.Tensor, cache_dir) -> int:
+    """Store masks uint8 [N,g,g] the way the reference's `main()` does (generate_pseudo_label.py:124,150): item i is a
+    CPU float tensor [1,g,g], `data_{i}.pkl` + `index.json` (MetaListPickleIO), readable by the reference trainer."""
+    from .engine.utils.fileio import MetaListPickleIO
+    io = MetaListPickleIO(base_path=cache_dir)
+    if io.mode != "w":
+        raise RuntimeError(f"{cache_dir} already holds a valid cache")
+    m = masks_u8.detach().cpu()
+    io.dump_list([m[i].unsqueeze(0).float() for i in range(m.shape[0])])
+    return m.shape[0]
+
+
+@torch.no_grad()
+def generate_pseudo_label_cache(generator: PseudoLabelGenerator, images_u8: torch.Tensor, cache_dir,
+                                batch: int = 256) -> int:
+    """Data-parallel version of the reference's serial loop (:141-150): this rank scores the images
+    `dist.shard_indices(N)`, the uint8 masks are gathered on rank 0, which writes the cache."""
+    from . import dist as ud
+    N = images_u8.shape[0]
+    idx = list(ud.shard_indices(N))
+    outs = []
+    for i in range(0, len(idx), batch):
+        sel = torch.as_tensor(idx[i:i + batch], dtype=torch.long)
+        outs.append(generator(images_u8[sel].to(generator.extractor.device)))
+    g = images_u8.shape[-1] // generator.extractor.spec.patch
+    local = torch.cat(outs, 0) if outs else torch.zeros(0, g, g, dtype=torch.uint8, device=generator.extractor.device)
+    full = ud.gather_sharded_masks(local, N)
+    rank, _ = ud.world()
+    if rank == 0:
+        return write_pseudo_label_cache(full, cache_dir)
+    return 0
