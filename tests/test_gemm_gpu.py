@@ -59,9 +59,11 @@ def test_gemm_epilogues():
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])
-@pytest.mark.parametrize("M,N,K", [(1370 * 2 + 3, 2304, 768), (77, 768, 3072), (128, 128, 64), (4000, 3072, 768)])
+@pytest.mark.parametrize("M,N,K", [(1370 * 2 + 3, 2304, 768), (77, 768, 3072), (128, 128, 64), (4000, 3072, 768),
+                                   (300, 768, 768), (641, 256, 128), (257, 512, 64)])
 def test_gemm_tma_epilogue_tails(mode, M, N, K):
-    """TMA-store / reduce-add epilogues: ragged M (clipped boxes), many tiles per CTA, strided output rows."""
+    """TMA-store / reduce-add epilogues: ragged M (clipped boxes), many tiles per CTA, strided output rows; M values
+    with an odd number of 128-row tiles leave the second CTA of the last pair entirely out of range."""
     g = torch.Generator(device="cuda").manual_seed(M + N + mode)
     a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
     w = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).to(torch.bfloat16)
