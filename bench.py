@@ -184,9 +184,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    lib.ucod_prof_collect(None, None, None)
     launches0 = lib.ucod_launch_count()
-    lib.ucod_prof_enable(1)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -194,9 +192,22 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
         pipe(dev_in[i % NB])
     e1.record()
     barrier()
-    lib.ucod_prof_enable(0)
     ms_total = e0.elapsed_time(e1)
     launches = lib.ucod_launch_count() - launches0
+
+    # ---- per-kernel-class breakdown: the same K steps again with the library's CUDA-event brackets enabled (two
+    # event records per launch cost ~1 % of a step, so they stay out of the headline region above) ----
+    lib.ucod_prof_collect(None, None, None)
+    lib.ucod_prof_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    p0.record()
+    for i in range(args.steps):
+        pipe(dev_in[i % NB])
+    p1.record()
+    barrier()
+    lib.ucod_prof_enable(0)
+    ms_prof_total = p0.elapsed_time(p1)
     KC = 9
     ms_c, work_c, n_c = (ctypes.c_double * KC)(), (ctypes.c_double * KC)(), (ctypes.c_longlong * KC)()
     lib.ucod_prof_collect(ms_c, work_c, n_c)
@@ -266,7 +277,7 @@ def run_ours(args, rank: int, world: int, local_rank: int) -> None:
     for i, n in enumerate(names):
         if n_c[i]:
             kern[n] = {"launches_per_step": n_c[i] / args.steps, "ms_per_step": ms_c[i] / args.steps,
-                       "share": ms_c[i] / ms_total if ms_total else None}
+                       "share": ms_c[i] / ms_prof_total if ms_prof_total else None}
     # dominant kernel class -> roofline entry (tensor classes: FLOPs; others: algorithmic bytes)
     dom = max(range(KC), key=lambda i: ms_c[i])
     if dom in (0, 1):
