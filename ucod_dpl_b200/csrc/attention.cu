@@ -380,256 +380,6 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Persistent variant for head_dim 64: 2 CTAs per SM stay resident and walk over (batch*head, q-tile) work items
-// (q-tile fastest, so concurrently running CTAs share K/V in L2).  Same roles, TMEM layout and softmax as above; the
-// difference is that barriers, TMEM and the K/V ring live across items and Q is double buffered, so the producer
-// prefetches the next item's Q / K_0 / V_0 while the current item drains and the ~3000-clk cold start of a CTA
-// (TMEM alloc, first DRAM round trip, first S MMA) is paid once per CTA instead of once per q-tile.
-// Global tile counter g: K/V stage g & 1, every per-tile barrier completes phase g.
-// ------------------------------------------------------------------------------------------------
-struct Att64P {
-    static constexpr int BM = 128, BN = 128, D = 64;
-    static constexpr int TILE_BYTES = 128 * 64 * 2;  // 16 KB
-    static constexpr int SMEM = 2 * TILE_BYTES + 2 * 2 * TILE_BYTES + 256 + 1024;  // Q x2, K x2, V x2
-    static constexpr int TM_S = 0, TM_P = 128, TM_O = 192, TMEM_COLS = 256;
-};
-
-__global__ void __launch_bounds__(256, 2)
-    attention64_persistent_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                                  const __grid_constant__ CUtensorMap tm_v, __nv_bfloat16* __restrict__ ctx, int Tq,
-                                  int Tk, int H, int BH, int ld_ctx, float scale_log2e,
-                                  const int* __restrict__ kv_map) {
-    using C = Att64P;
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sQ = smem;
-    uint8_t* sK = sQ + 2 * C::TILE_BYTES;
-    uint8_t* sV = sK + 2 * C::TILE_BYTES;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * C::TILE_BYTES);
-    uint64_t* bar_qfull = bars;        // [2]
-    uint64_t* bar_qempty = bars + 2;   // [2]
-    uint64_t* bar_kfull = bars + 4;    // [2]
-    uint64_t* bar_kempty = bars + 6;   // [2]
-    uint64_t* bar_vfull = bars + 8;    // [2]
-    uint64_t* bar_vempty = bars + 10;  // [2]
-    uint64_t* bar_s = bars + 12;
-    uint64_t* bar_sfree = bars + 13;
-    uint64_t* bar_p = bars + 14;
-    uint64_t* bar_pv = bars + 15;
-    uint64_t* bar_ofree = bars + 16;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_qt = (Tq + C::BM - 1) / C::BM;
-    const int n_tiles = (Tk + C::BN - 1) / C::BN;
-    const int n_items = n_qt * BH;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < 2; ++i) {
-            mbar_init(&bar_qfull[i], 1);
-            mbar_init(&bar_qempty[i], 1);
-            mbar_init(&bar_kfull[i], 1);
-            mbar_init(&bar_kempty[i], 1);
-            mbar_init(&bar_vfull[i], 1);
-            mbar_init(&bar_vempty[i], 1);
-        }
-        mbar_init(bar_s, 1);
-        mbar_init(bar_sfree, 128);
-        mbar_init(bar_p, 128);
-        mbar_init(bar_pv, 1);
-        mbar_init(bar_ofree, 128);
-        fence_mbar_init();
-    }
-    if (warp == 1) {
-        tmem_alloc(tmem_slot, C::TMEM_COLS);
-        tmem_relinquish();
-    }
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-    const uint32_t tmem_s = tmem_base + C::TM_S, tmem_p = tmem_base + C::TM_P, tmem_o = tmem_base + C::TM_O;
-
-    if (warp < 4) {
-        reg_dec<80>();
-        if (warp == 0 && lane == 0) {
-            // ===================== TMA producer =====================
-            tma_prefetch_desc(&tm_q);
-            tma_prefetch_desc(&tm_k);
-            tma_prefetch_desc(&tm_v);
-            uint32_t g = 0, n = 0;
-            for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-                const int bh = item / n_qt, qt = item - bh * n_qt;
-                const int b = bh / H, h = bh - b * H;
-                const int bkv = kv_map != nullptr ? __ldg(kv_map + b) : b;
-                const int qs = n & 1;
-                mbar_wait_parked(&bar_qempty[qs], ((n >> 1) & 1) ^ 1);
-                mbar_arrive_expect_tx(&bar_qfull[qs], C::TILE_BYTES);
-                tma_load_3d(sQ + qs * C::TILE_BYTES, &tm_q, &bar_qfull[qs], h * C::D, qt * C::BM, b);
-                for (int j = 0; j < n_tiles; ++j, ++g) {
-                    const int st = g & 1;
-                    const uint32_t ph = ((g >> 1) & 1) ^ 1;
-                    mbar_wait_parked(&bar_kempty[st], ph);
-                    mbar_arrive_expect_tx(&bar_kfull[st], C::TILE_BYTES);
-                    tma_load_3d(sK + st * C::TILE_BYTES, &tm_k, &bar_kfull[st], h * C::D, j * C::BN, bkv);
-                    mbar_wait_parked(&bar_vempty[st], ph);
-                    mbar_arrive_expect_tx(&bar_vfull[st], C::TILE_BYTES);
-                    tma_load_3d(sV + st * C::TILE_BYTES, &tm_v, &bar_vfull[st], h * C::D, j * C::BN, bkv);
-                }
-            }
-        } else if (warp == 1 && lane == 0) {
-            // ===================== MMA issuer =====================
-            constexpr uint32_t idesc_s = umma_idesc_bf16(C::BM, C::BN);
-            constexpr uint32_t idesc_o = umma_idesc_bf16(C::BM, C::D) | (1u << 16);
-            const int my_items = blockIdx.x < n_items ? (n_items - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-            const uint32_t total = (uint32_t)my_items * n_tiles;  // global tiles of this CTA
-            // S for global tile t (item t / n_tiles, tile t % n_tiles): needs its Q, its K and a free S region
-            auto issue_s = [&](uint32_t t) {
-                const uint32_t n = t / n_tiles, j = t - n * n_tiles;
-                const int qs = n & 1;
-                if (j == 0) mbar_wait_parked(&bar_qfull[qs], (n >> 1) & 1);
-                mbar_wait_parked(&bar_kfull[t & 1], (t >> 1) & 1);
-                if (t > 0) mbar_wait_parked(bar_sfree, (t - 1) & 1);  // softmax pulled S_{t-1} into registers
-                tc_fence_after();
-                const uint32_t q_addr = smem_u32(sQ + qs * C::TILE_BYTES);
-                const uint32_t k_addr = smem_u32(sK + (t & 1) * C::TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    umma_bf16_ss(tmem_s, umma_desc_kmajor_sw128(q_addr + k * 32), umma_desc_kmajor_sw128(k_addr + k * 32),
-                                 idesc_s, k != 0);
-                umma_commit(&bar_kempty[t & 1]);
-                if (j == (uint32_t)n_tiles - 1) umma_commit(&bar_qempty[qs]);  // last S of the item: Q slot reusable
-                umma_commit(bar_s);
-            };
-            if (total > 0) issue_s(0);
-            for (uint32_t t = 0; t < total; ++t) {
-                const uint32_t n = t / n_tiles, j = t - n * n_tiles;
-                if (t + 1 < total) issue_s(t + 1);
-                mbar_wait_parked(&bar_vfull[t & 1], (t >> 1) & 1);
-                mbar_wait_parked(bar_p, t & 1);  // P_t published
-                if (j == 0 && n > 0) mbar_wait_parked(bar_ofree, (n - 1) & 1);  // previous item's O has been read
-                tc_fence_after();
-                const uint32_t v_addr = smem_u32(sV + (t & 1) * C::TILE_BYTES);
-#pragma unroll
-                for (int k = 0; k < C::BN / 16; ++k)
-                    umma_bf16_ts(tmem_o, tmem_p + k * 8, umma_desc_mnmajor_sw128(v_addr + k * 2048, C::TILE_BYTES),
-                                 idesc_o, (j | k) != 0);
-                umma_commit(&bar_vempty[t & 1]);
-                umma_commit(bar_pv);
-            }
-        }
-    } else {
-        // ===================== softmax / correction / epilogue: one thread per query row ==============
-        reg_inc<176>();
-        const int quarter = warp & 3;
-        const int r = quarter * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
-        uint32_t g = 0, n = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n) {
-            const int bh = item / n_qt, qt = item - bh * n_qt;
-            const int b = bh / H, h = bh - b * H;
-            float m_ref = 0.f, l_run = 0.f;
-            for (int j = 0; j < n_tiles; ++j, ++g) {
-                mbar_wait(bar_s, g & 1);
-                tc_fence_after();
-                uint32_t u[128];
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    tmem_ld32(tmem_s + lane_off + c * 32, reinterpret_cast<uint32_t(&)[32]>(u[32 * c]));
-                tmem_wait_ld();
-                tc_fence_before();
-                mbar_arrive(bar_sfree);
-                const int valid = Tk - j * C::BN;
-                if (valid < C::BN) {
-#pragma unroll
-                    for (int i = 0; i < 128; ++i)
-                        if (i >= valid) u[i] = 0xff800000u;
-                }
-                float mx[4];
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    mx[c] = __uint_as_float(u[32 * c]);
-#pragma unroll
-                    for (int i = 1; i < 32; i += 2)
-                        mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(u[32 * c + i]),
-                                                   __uint_as_float(u[32 * c + (i + 1 < 32 ? i + 1 : i)])));
-                }
-                const float ms = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2e;
-                float alpha = 1.f;
-                bool grow = false;
-                if (j == 0) {
-                    m_ref = ms;
-                } else if (ms > m_ref + 8.f) {
-                    alpha = ex2_approx(m_ref - ms);
-                    m_ref = ms;
-                    grow = true;
-                }
-                const float neg_m = -m_ref;
-                float ls[4] = {0.f, 0.f, 0.f, 0.f};
-                uint32_t pk[64];
-#pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                    const float p0 = ex2_approx(fmaf(__uint_as_float(u[2 * i]), scale_log2e, neg_m));
-                    const float p1 = ex2_approx(fmaf(__uint_as_float(u[2 * i + 1]), scale_log2e, neg_m));
-                    ls[i & 3] += p0 + p1;
-                    pk[i] = pack_bf16x2(p0, p1);
-                }
-                l_run = l_run * alpha + (ls[0] + ls[1]) + (ls[2] + ls[3]);
-                if (g > 0) {  // P_{g-1} V_{g-1} (possibly the previous item's last tile) must have retired
-                    mbar_wait(bar_pv, (g - 1) & 1);
-                    tc_fence_after();
-                    if (j > 0 && __any_sync(0xffffffffu, grow)) {
-#pragma unroll 1
-                        for (int c = 0; c < C::D / 32; ++c) {
-                            uint32_t o[32];
-                            tmem_ld32(tmem_o + lane_off + c * 32, o);
-                            tmem_wait_ld();
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-                            tmem_st32(tmem_o + lane_off + c * 32, o);
-                        }
-                    }
-                }
-                tmem_st32(tmem_p + lane_off, reinterpret_cast<uint32_t(&)[32]>(pk[0]));
-                tmem_st32(tmem_p + lane_off + 32, reinterpret_cast<uint32_t(&)[32]>(pk[32]));
-                tmem_wait_st();
-                tc_fence_before();
-                mbar_arrive(bar_p);
-            }
-            // ---- epilogue of the item: O / l -> bf16 ctx, then hand the O columns back ----
-            mbar_wait(bar_pv, (g - 1) & 1);
-            tc_fence_after();
-            const float inv_l = 1.0f / l_run;
-            const int t = qt * C::BM + r;
-            __nv_bfloat16* out = ctx + ((size_t)b * Tq + t) * (size_t)ld_ctx + h * C::D;
-#pragma unroll 1
-            for (int c = 0; c < C::D / 32; ++c) {
-                uint32_t o[32];
-                tmem_ld32(tmem_o + lane_off + c * 32, o);
-                tmem_wait_ld();
-                if (t < Tq) {
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {
-                        uint4 v;
-                        v.x = pack_bf16x2(__uint_as_float(o[8 * q4 + 0]) * inv_l, __uint_as_float(o[8 * q4 + 1]) * inv_l);
-                        v.y = pack_bf16x2(__uint_as_float(o[8 * q4 + 2]) * inv_l, __uint_as_float(o[8 * q4 + 3]) * inv_l);
-                        v.z = pack_bf16x2(__uint_as_float(o[8 * q4 + 4]) * inv_l, __uint_as_float(o[8 * q4 + 5]) * inv_l);
-                        v.w = pack_bf16x2(__uint_as_float(o[8 * q4 + 6]) * inv_l, __uint_as_float(o[8 * q4 + 7]) * inv_l);
-                        reinterpret_cast<uint4*>(out + c * 32)[q4] = v;
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(bar_ofree);
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
-}
-
 template <int D>
 int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
     using C = AttCfg<D>;
@@ -651,27 +401,6 @@ int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
         configured = true;
     }
     dim3 grid((unsigned)ceil_div(a.tokens_q, C::BM), (unsigned)(a.batch * a.heads));
-    if (D == 64) {
-        static bool p_configured = false;
-        static bool use_persistent = false;
-        if (!p_configured) {
-            UCOD_CHECK_CUDA(cudaFuncSetAttribute(attention64_persistent_kernel,
-                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, Att64P::SMEM));
-            use_persistent = getenv("UCOD_ATT_NO_PERSIST") == nullptr;
-            p_configured = true;
-        }
-        if (use_persistent) {
-            const int items = (int)grid.x * (int)grid.y;
-            const int ctas = items < 2 * device_sm_count() ? items : 2 * device_sm_count();
-            ProfScope ps(KC_ATTENTION, stream,
-                         4.0 * a.batch * a.heads * (double)a.tokens_q * a.tokens_kv * a.head_dim_real);
-            attention64_persistent_kernel<<<ctas, 256, Att64P::SMEM, stream>>>(
-                tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(a.ctx), a.tokens_q, a.tokens_kv, a.heads,
-                a.batch * a.heads, a.ld_ctx, a.scale * 1.4426950408889634f, a.kv_batch_map);
-            UCOD_CHECK_CUDA(cudaGetLastError());
-            return 0;
-        }
-    }
     {
         ProfScope ps(KC_ATTENTION, stream, 4.0 * a.batch * a.heads * (double)a.tokens_q * a.tokens_kv * a.head_dim_real);
         kern<<<grid, C::THREADS, C::SMEM, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(a.ctx), a.tokens_q,
