@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UCOD_B200_ABI_VERSION 2
+#define UCOD_B200_ABI_VERSION 3
 
 /* Last error message of the calling thread ("" if none). */
 const char* ucod_last_error(void);
@@ -181,6 +181,13 @@ int ucod_paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const i
 /* out[i] = in[i] ? mul : 0  ({0,1} mask -> {0,255} canvas, loop_UCOD_DPL.py:330). */
 int ucod_mask_scale_u8(const uint8_t* in, uint8_t* out, uint64_t n, int mul, void* stream);
 
+/* torchvision `ToTensor` + `Normalize(mean, std)` of planar uint8 images (data/datasets/transforms.py:14-18,
+ * 31-35, 40-43): out = ((in / 255) - mean[c]) / std[c], every step one correctly rounded fp32 operation as in
+ * the torch ops it replaces (bit-exact).  in: uint8 [planes, hw] (4-byte aligned), plane p has channel p % channels;
+ * mean / stddev: HOST float[channels]; channels == 0: ToTensor only (label transform, transforms.py:23-26). */
+int ucod_to_tensor_normalize(const uint8_t* in, float* out, uint64_t planes, int hw, int channels,
+                             const float* mean, const float* stddev, void* stream);
+
 /* ---- APM: discriminator + pseudo-label fusion -----------------------------------------------------
  * `Discriminator.forward` (models/discriminator.py:86-95, dis_use_features = False): mask fp32 [batch,1,fs,fs]
  * -> prob fp32 [batch].  Weight pointers follow the reference state_dict: maskConv.layers.{0,1}, convs.{0,1}.layers.{0,1},
@@ -262,11 +269,14 @@ int ucod_coral_scatter_windows(const float* window_preds, const int32_t* slot_of
                                int grid, float* out, void* stream);
 /* `GatedEnsembler.forward` (models/modules/GE_pix_level.py:16-26): preds fp32 [batch,preds_size,preds_size] coarse
  * logits, h_preds fp32 [batch,size,size]; fuser weights w0[64], b0[64], w2[64], b2[1];
- * out / weight fp32 [batch,size,size] (the entropy maximum is taken over the whole call, as in the reference). */
+ * out / weight fp32 [batch,size,size].  `en_local.max()` (GE_pix_level.py:23) is a maximum over the whole tensor:
+ * max_per_image = 0 reproduces that for the call's batch; max_per_image = 1 takes it per image, which is what the
+ * reference's batch-1 eval loop (loop_CORAL.py:260-311) computes for every image and makes a batched eval
+ * independent of the batch composition. */
 uint64_t ucod_coral_gated_ensemble_workspace_bytes(int batch, int size);
 int ucod_coral_gated_ensemble(const float* preds, int preds_size, const float* h_preds, int batch, int size,
-                              const float* w0, const float* b0, const float* w2, const float* b2, float* out,
-                              float* weight, void* workspace, uint64_t workspace_bytes, void* stream);
+                              int max_per_image, const float* w0, const float* b0, const float* w2, const float* b2,
+                              float* out, float* weight, void* workspace, uint64_t workspace_bytes, void* stream);
 /* nn.LayerNorm over the last dim (dim % 128 == 0, <= 1024): x fp32 [rows,dim] -> y bf16 [rows,dim]. */
 int ucod_layernorm_bf16(const float* x, const float* weight, const float* bias, void* y, int rows, int dim, float eps,
                         void* stream);

@@ -145,3 +145,39 @@ def test_coral_glue_matches_oracle():
     assert (m != want).mean() < 2e-4        # fp32 sigmoid/interp rounding exactly at the 0.5 boundary only
     mp = CE.process_preds(x.sigmoid().cuda(), (300, 417)).cpu().numpy().astype(np.float32)
     assert (mp != want).mean() < 2e-4
+
+
+def test_evaluator_is_batch_independent():
+    """The reference's CORAL eval loop runs at batch 1 and `GatedEnsembler` normalises by `en_local.max()` over the
+    whole tensor, so a batched eval must take that maximum per image: image k inside a batch == image k alone."""
+    from safetensors.torch import load_file
+    from ucod_dpl_b200.engine.runner.loop_CORAL import CoralEvaluator
+    from ucod_dpl_b200.models.uscod import baseline
+    from ucod_dpl_b200.synth import random_vit_state_dict, synth_image_u8
+    from ucod_dpl_b200.vit import VitKeyExtractor, spec_for
+    root = Path(__file__).resolve().parents[1]
+    S = 224
+    vit_sd = random_vit_state_dict(spec_for("dinov2"), seed=0)
+    model = baseline(SimpleNamespace(dim=768)).cuda().eval()
+    model.load_state_dict(load_file(str(root / "weights" / "UCOD_DPL_dinov2.safetensors")), strict=True)
+    refiner = SparseRefiner.from_config(SimpleNamespace(window_size=3, threshold=0.0015)).cuda().eval()
+    refiner.load_state_dict(random_refiner_state_dict(0), strict=True)
+    ev = CoralEvaluator(VitKeyExtractor(vit_sd, spec_for("dinov2")), model, refiner, (S, S), 3, 56)
+    imgs = torch.stack([synth_image_u8(20 + i, 300, 340) for i in range(3)]).cuda()
+    batched, crop_b = ev.refine(imgs)
+    for k in range(3):
+        solo, crop_s = ev.refine(imgs[k:k + 1].contiguous())
+        assert bool(crop_b[k]) == bool(crop_s[0])
+        assert (batched[k] - solo[0]).abs().max().item() < 1e-4
+    # the module-level call keeps the reference's whole-batch maximum unless asked otherwise
+    l, h, preds = synth_coral_inputs(6, batch=2, uncertain=((1, 2),))
+    preds = preds.clone()
+    preds[1] = preds[1].clamp(max=-4.0)  # image 1 never reaches the entropy peak at f = 1/e, image 0 does
+    hp = torch.randn(2, 1, 168, 168, device="cuda")
+    whole, _ = refiner.GE(preds.cuda(), hp)
+    per, _ = refiner.GE(preds.cuda(), hp, max_per_image=True)
+    one0, _ = refiner.GE(preds[:1].cuda(), hp[:1])
+    one1, _ = refiner.GE(preds[1:].cuda(), hp[1:])
+    # (the mean of sigmoid(l1) is an atomic float sum: order-dependent in the last bits)
+    assert torch.allclose(per[0], one0[0], atol=1e-4) and torch.allclose(per[1], one1[0], atol=1e-4)
+    assert not torch.allclose(whole[1], one1[0], atol=1e-3)

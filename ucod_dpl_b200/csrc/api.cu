@@ -141,6 +141,11 @@ int ucod_paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const i
 int ucod_mask_scale_u8(const uint8_t* in, uint8_t* out, uint64_t n, int mul, void* stream) {
     return mask_scale_u8(in, out, (size_t)n, mul, reinterpret_cast<cudaStream_t>(stream));
 }
+int ucod_to_tensor_normalize(const uint8_t* in, float* out, uint64_t planes, int hw, int channels,
+                             const float* mean, const float* stddev, void* stream) {
+    return to_tensor_normalize(in, out, (size_t)planes, hw, channels, mean, stddev,
+                               reinterpret_cast<cudaStream_t>(stream));
+}
 
 uint64_t ucod_discriminator_workspace_bytes(int batch, int fs) {
     return (uint64_t)discriminator_workspace_bytes(batch, fs);
@@ -223,10 +228,10 @@ uint64_t ucod_coral_gated_ensemble_workspace_bytes(int batch, int size) {
     return (uint64_t)coral_gated_ensemble_workspace_bytes(batch, size);
 }
 int ucod_coral_gated_ensemble(const float* preds, int preds_size, const float* h_preds, int batch, int size,
-                              const float* w0, const float* b0, const float* w2, const float* b2, float* out,
-                              float* weight, void* workspace, uint64_t workspace_bytes, void* stream) {
-    return coral_gated_ensemble(preds, preds_size, h_preds, batch, size, w0, b0, w2, b2, out, weight, workspace,
-                                (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+                              int max_per_image, const float* w0, const float* b0, const float* w2, const float* b2,
+                              float* out, float* weight, void* workspace, uint64_t workspace_bytes, void* stream) {
+    return coral_gated_ensemble(preds, preds_size, h_preds, batch, size, max_per_image, w0, b0, w2, b2, out, weight,
+                                workspace, (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
 int ucod_layernorm_bf16(const float* x, const float* weight, const float* bias, void* y, int rows, int dim, float eps,
                         void* stream) {

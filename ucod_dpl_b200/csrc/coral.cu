@@ -147,7 +147,8 @@ int coral_scatter_windows(const float* window_preds, const int* slot_of_cell, in
 }
 
 // ------------------------------------------------------------------------------------------------
-// Gated ensemble.  ws layout: l1 [B,S,S] | prob [B,S,S] | en [B,S,S] | sums [B] | enmax (uint bits) [1]
+// Gated ensemble.  ws layout: l1 [B,S,S] | prob [B,S,S] | en [B,S,S] | sums [B] | enmax (uint bits) [B]
+// (enmax slot = image index when the maximum is per image, slot 0 when it is over the whole call)
 __device__ __forceinline__ void bilin_tap(int dst, int in, int out, int& i0, int& i1, float& l) {
     const float scale = (float)in / (float)out;
     float src = scale * ((float)dst + 0.5f) - 0.5f;
@@ -180,7 +181,7 @@ __global__ void ge_upsample_kernel(const float* __restrict__ preds, int P, int S
 }
 // 19x19 zero-padded box mean (divide by 361 always), local entropy, global max
 __global__ void ge_box_entropy_kernel(const float* __restrict__ prob, int S, float* __restrict__ en,
-                                      unsigned int* __restrict__ enmax) {
+                                      unsigned int* __restrict__ enmax, int max_per_image) {
     const int b = blockIdx.y;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     float e = 0.f;
@@ -200,13 +201,15 @@ __global__ void ge_box_entropy_kernel(const float* __restrict__ prob, int S, flo
         en[(size_t)b * S * S + idx] = e;
     }
     e = warp_max(e);
-    if ((threadIdx.x & 31) == 0 && e > 0.f) atomicMax(enmax, __float_as_uint(e));  // e >= 0: uint order == float order
+    // e >= 0: uint order == float order
+    if ((threadIdx.x & 31) == 0 && e > 0.f) atomicMax(enmax + (max_per_image ? b : 0), __float_as_uint(e));
 }
 __global__ void ge_fuse_kernel(const float* __restrict__ l1, const float* __restrict__ en,
                                const float* __restrict__ l2, const float* __restrict__ sums,
-                               const unsigned int* __restrict__ enmax, int S, const float* __restrict__ w0,
-                               const float* __restrict__ b0, const float* __restrict__ w2, const float* __restrict__ b2,
-                               float* __restrict__ out, float* __restrict__ weight) {
+                               const unsigned int* __restrict__ enmax, int max_per_image, int S,
+                               const float* __restrict__ w0, const float* __restrict__ b0,
+                               const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out,
+                               float* __restrict__ weight) {
     __shared__ float sw0[64], sb0[64], sw2[64];
     if (threadIdx.x < 64) sw0[threadIdx.x] = w0[threadIdx.x], sb0[threadIdx.x] = b0[threadIdx.x], sw2[threadIdx.x] = w2[threadIdx.x];
     __syncthreads();
@@ -214,7 +217,7 @@ __global__ void ge_fuse_kernel(const float* __restrict__ l1, const float* __rest
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= S * S) return;
     const size_t o = (size_t)b * S * S + idx;
-    const float emax = __uint_as_float(*enmax);
+    const float emax = __uint_as_float(enmax[max_per_image ? b : 0]);
     const float fg_g = sums[b] / (float)(S * S);
     const float wl = ((1.f - en[o] / emax) + fg_g) * 0.5f;
     const float y = l1[o] * wl + l2[o] * (1.f - wl);
@@ -226,11 +229,11 @@ __global__ void ge_fuse_kernel(const float* __restrict__ l1, const float* __rest
 }
 
 size_t coral_gated_ensemble_workspace_bytes(int B, int S) {
-    return ((size_t)3 * B * S * S + B + 4) * sizeof(float);
+    return ((size_t)3 * B * S * S + 2 * (size_t)B + 4) * sizeof(float);
 }
-int coral_gated_ensemble(const float* preds, int P, const float* h_preds, int B, int S, const float* w0, const float* b0,
-                         const float* w2, const float* b2, float* out, float* weight, void* workspace, size_t ws_bytes,
-                         cudaStream_t stream) {
+int coral_gated_ensemble(const float* preds, int P, const float* h_preds, int B, int S, int max_per_image,
+                         const float* w0, const float* b0, const float* w2, const float* b2, float* out, float* weight,
+                         void* workspace, size_t ws_bytes, cudaStream_t stream) {
     UCOD_REQUIRE(preds && h_preds && w0 && b0 && w2 && b2 && out && weight && workspace,
                  "coral_gated_ensemble: null pointer");
     UCOD_REQUIRE(ws_bytes >= coral_gated_ensemble_workspace_bytes(B, S), "coral_gated_ensemble: workspace too small");
@@ -239,12 +242,13 @@ int coral_gated_ensemble(const float* preds, int P, const float* h_preds, int B,
     float* en = prob + (size_t)B * S * S;
     float* sums = en + (size_t)B * S * S;
     unsigned int* enmax = reinterpret_cast<unsigned int*>(sums + B);
-    UCOD_CHECK_CUDA(cudaMemsetAsync(sums, 0, (B + 1) * sizeof(float), stream));
+    UCOD_CHECK_CUDA(cudaMemsetAsync(sums, 0, 2 * (size_t)B * sizeof(float), stream));
     dim3 grid(ceil_div(S * S, 256), B);
     ProfScope ps(KC_OTHER, stream, (double)B * S * S * 4 * 9);
     ge_upsample_kernel<<<grid, 256, 0, stream>>>(preds, P, S, l1, prob, sums);
-    ge_box_entropy_kernel<<<grid, 256, 0, stream>>>(prob, S, en, enmax);
-    ge_fuse_kernel<<<grid, 256, 0, stream>>>(l1, en, h_preds, sums, enmax, S, w0, b0, w2, b2, out, weight);
+    ge_box_entropy_kernel<<<grid, 256, 0, stream>>>(prob, S, en, enmax, max_per_image);
+    ge_fuse_kernel<<<grid, 256, 0, stream>>>(l1, en, h_preds, sums, enmax, max_per_image, S, w0, b0, w2, b2, out,
+                                             weight);
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -604,4 +604,53 @@ int mask_scale_u8(const uint8_t* in, uint8_t* out, size_t n, int mul, cudaStream
     return 0;
 }
 
+// torchvision ToTensor (u8 -> fp32 / 255) followed by Normalize ((x - mean) / std), each step one correctly
+// rounded fp32 operation like the torch elementwise ops it replaces (data/datasets/transforms.py:14-18).
+// Planar [planes, hw] with channel = plane % channels; channels == 0 skips the normalisation (label transform).
+__global__ void to_tensor_normalize_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, size_t n, int hw,
+                                           int channels, float m0, float m1, float m2, float s0, float s1, float s2) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    uint8_t v[4];
+    const bool full = i + 4 <= n;
+    if (full) {
+        *reinterpret_cast<uint32_t*>(v) = *reinterpret_cast<const uint32_t*>(in + i);
+    } else {
+        for (int k = 0; k < 4; ++k) v[k] = i + k < n ? in[i + k] : 0;
+    }
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float x = __fdiv_rn((float)v[k], 255.0f);
+        if (channels > 0) {
+            const int c = (int)(((i + k) / (size_t)hw) % (size_t)channels);
+            const float m = c == 0 ? m0 : (c == 1 ? m1 : m2), sd = c == 0 ? s0 : (c == 1 ? s1 : s2);
+            x = __fdiv_rn(__fsub_rn(x, m), sd);
+        }
+        r[k] = x;
+    }
+    if (full) {
+        *reinterpret_cast<float4*>(out + i) = make_float4(r[0], r[1], r[2], r[3]);
+    } else {
+        for (int k = 0; k < 4 && i + k < n; ++k) out[i + k] = r[k];
+    }
+}
+
+int to_tensor_normalize(const uint8_t* in, float* out, size_t planes, int hw, int channels, const float* mean,
+                        const float* stddev, cudaStream_t stream) {
+    UCOD_REQUIRE(in && out, "to_tensor_normalize: null argument");
+    UCOD_REQUIRE(channels == 0 || (channels <= 3 && mean && stddev), "to_tensor_normalize: 0..3 channels with mean/std");
+    UCOD_REQUIRE((reinterpret_cast<uintptr_t>(in) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                 "to_tensor_normalize: input must be 4-byte and output 16-byte aligned");
+    const size_t n = planes * (size_t)hw;
+    if (n == 0) return 0;
+    float m[3] = {0, 0, 0}, s[3] = {1, 1, 1};
+    for (int c = 0; c < channels; ++c) m[c] = mean[c], s[c] = stddev[c];
+    ProfScope ps(KC_RESAMPLE, stream, (double)n * 5);
+    to_tensor_normalize_kernel<<<(unsigned)((n / 4 + 255) / 256 + 1), 256, 0, stream>>>(in, out, n, hw, channels, m[0],
+                                                                                       m[1], m[2], s[0], s[1], s[2]);
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace ucod

@@ -20,5 +20,7 @@ int paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const int* j
                   int n_img, int S_h, int S_w, int out_cap, void* workspace, size_t ws_bytes, int* err_flag,
                   cudaStream_t stream);
 int mask_scale_u8(const uint8_t* in, uint8_t* out, size_t n, int mul, cudaStream_t stream);
+int to_tensor_normalize(const uint8_t* in, float* out, size_t planes, int hw, int channels, const float* mean,
+                        const float* stddev, cudaStream_t stream);
 
 }  // namespace ucod

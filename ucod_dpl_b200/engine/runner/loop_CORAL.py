@@ -113,7 +113,7 @@ class CoralEvaluator:
         l, h, m = self.get_features(originals, layout)
         l_t, h_t, preds = self._prepare(l, h, m)
         crop = self._should_crop_center(preds)
-        outputs, _, _ = self.refiner.forward_tokens(l_t, h_t, preds, self.g)
+        outputs, _, _ = self.refiner.forward_tokens(l_t, h_t, preds, self.g, per_image=True)
         results = [outputs[i:i + 1] for i in range(outputs.shape[0])]
         idx = torch.nonzero(crop).flatten().tolist()
         if idx:
@@ -125,7 +125,7 @@ class CoralEvaluator:
             sub = (sub[..., top:top + nh, left:left + nw] if layout == "CHW" else sub[:, top:top + nh, left:left + nw])
             l2, h2, m2 = self.get_features(sub.contiguous(), layout)
             l2t, h2t, p2 = self._prepare(l2, h2, m2)
-            out2, _, _ = self.refiner.forward_tokens(l2t, h2t, p2, self.g)
+            out2, _, _ = self.refiner.forward_tokens(l2t, h2t, p2, self.g, per_image=True)
             out2 = self._center_pad(out2)
             for k, i in enumerate(idx):
                 results[i] = out2[k:k + 1]

@@ -89,20 +89,25 @@ class LookTwiceEvaluator:
 
     @torch.no_grad()
     def look_twice_batch(self, originals: torch.Tensor, bboxes_per_image, masks_u8: torch.Tensor,
-                         layout: str = "CHW") -> torch.Tensor:
+                         layout: str = "CHW", orig_sizes=None) -> torch.Tensor:
         """originals: uint8 RGB originals of the batch ([N,3,H0,W0] or [N,H0,W0,3]); bboxes_per_image: list (len N)
         of box lists or None; masks_u8 [N,S,S] {0,1}.  Returns new masks float [N,S,S] in [0,1]
-        (loop_UCOD_DPL.py:326-352 for every image that has boxes; others keep their mask)."""
+        (loop_UCOD_DPL.py:326-352 for every image that has boxes; others keep their mask).
+        orig_sizes (optional, [N,2] (h, w)): `originals` is a zero-padded canvas of differently sized images
+        (`pack_padded`); boxes are mapped with each image's own size and crops past an image read 0 like PIL's."""
         ih, iw = self.img_size
         dev = masks_u8.device
         if layout == "CHW":
             H0, W0 = originals.shape[-2:]
         else:
             H0, W0 = originals.shape[1:3]
+        sizes = None if orig_sizes is None else torch.as_tensor(orig_sizes).tolist()
         crop_jobs, paste_jobs = [], []
         for n, bxs in enumerate(bboxes_per_image):
             if bxs is None:
                 continue
+            if sizes is not None:
+                H0, W0 = sizes[n]
             for rank, bb in enumerate(bxs):
                 x, y, w, h = resize_bbox(bb, iw, ih, W0, H0)
                 if w <= 0 or h <= 0 or bb[2] <= 0 or bb[3] <= 0:
@@ -121,10 +126,11 @@ class LookTwiceEvaluator:
         return canvas.float() / 255.0
 
     @torch.no_grad()
-    def __call__(self, images: torch.Tensor, originals: torch.Tensor | None = None, layout: str = "CHW"):
+    def __call__(self, images: torch.Tensor, originals: torch.Tensor | None = None, layout: str = "CHW",
+                 orig_sizes=None):
         """images: network-size inputs [N,3,S,S] (uint8 raw or fp32 normalised); originals: the original-resolution
-        uint8 images the crops are taken from (defaults to `images` when they are uint8).
-        Returns (final masks float [N,S,S] in [0,1], per-image bboxes)."""
+        uint8 images the crops are taken from (defaults to `images` when they are uint8; with `orig_sizes` a
+        zero-padded canvas of ragged images).  Returns (final masks float [N,S,S] in [0,1], per-image bboxes)."""
         fg = self.first_look(images)
         up, bboxes = self.process_preds(fg)
         if images.shape[0] == 1:
@@ -136,4 +142,4 @@ class LookTwiceEvaluator:
                 raise ValueError("originals (uint8) are required when `images` are already normalised")
             originals = images
         mask_u8 = up.to(torch.uint8)
-        return self.look_twice_batch(originals, bboxes, mask_u8, layout=layout), bboxes
+        return self.look_twice_batch(originals, bboxes, mask_u8, layout=layout, orig_sizes=orig_sizes), bboxes

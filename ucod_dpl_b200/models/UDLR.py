@@ -33,9 +33,10 @@ class SparseRefiner(nn.Module):
         return 0, opt
 
     @torch.no_grad()
-    def forward_tokens(self, l_tokens, h_tokens_all, preds, grid: int):
+    def forward_tokens(self, l_tokens, h_tokens_all, preds, grid: int, per_image: bool = False):
         """Device-pipeline entry: l_tokens fp32 [B,g*g,C]; h_tokens_all fp32 [B, w*w, g*g, C] (all windows,
-        token-major); preds [B,1,P,P].  Same outputs as `forward`."""
+        token-major); preds [B,1,P,P].  Same outputs as `forward`.  per_image: every image is treated as its own
+        batch-1 call (the gated ensemble's entropy maximum is per image) — what the reference's eval loop computes."""
         mask, entropy, win_img, coords, flat = self.selector.select(preds)
         dev = preds.device
         B = preds.shape[0]
@@ -48,7 +49,7 @@ class SparseRefiner(nn.Module):
         else:
             window_preds = torch.zeros(0, 1, grid, grid, device=dev)
         h_preds = self.HRE.concate_windows(window_preds, coords, mask)
-        outputs, ge_w = self.GE(preds, h_preds)
+        outputs, ge_w = self.GE(preds, h_preds, max_per_image=per_image)
         opt = {"mask": mask, "entropy": entropy, "h_preds": h_preds, "window_preds": window_preds, "GE_w": ge_w,
                "preds": preds, "coords_list": coords.to(dev), "h_targets": None}
         return outputs, 0, opt

@@ -176,9 +176,9 @@ class GatedEnsembler(nn.Module):
         self.fuser = nn.Sequential(nn.Conv2d(num_classes, 64, kernel_size=1), nn.ReLU(),
                                    nn.Conv2d(64, num_classes, kernel_size=1))
 
-    def forward(self, l1: torch.Tensor, l2: torch.Tensor):
+    def forward(self, l1: torch.Tensor, l2: torch.Tensor, max_per_image: bool = False):
         f0, f2 = self.fuser[0], self.fuser[2]
         return ops.coral_gated_ensemble(l1, l2, f0.weight.detach().reshape(64).float().contiguous(),
                                         f0.bias.detach().float().contiguous(),
                                         f2.weight.detach().reshape(64).float().contiguous(),
-                                        f2.bias.detach().float().contiguous())
+                                        f2.bias.detach().float().contiguous(), max_per_image=max_per_image)

@@ -206,6 +206,29 @@ def mask_scale_u8(mask_u8: torch.Tensor, mul: int = 255) -> torch.Tensor:
     return out
 
 
+def to_tensor_normalize(images_u8: torch.Tensor, mean=None, std=None) -> torch.Tensor:
+    """planar uint8 [..., C, H, W] -> fp32 of the same shape: torchvision ToTensor (+ Normalize when `mean`/`std`
+    are given), bit-exact (data/datasets/transforms.py:14-18)."""
+    _lib.require_cuda(images_u8)
+    if images_u8.dtype != torch.uint8 or images_u8.dim() < 3:
+        raise UcodError("to_tensor_normalize expects a planar uint8 tensor [..., C, H, W]")
+    x = images_u8.contiguous()
+    C, H, W = x.shape[-3:]
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    if mean is None:
+        ch, m, sd = 0, None, None
+    else:
+        if len(mean) != C or len(std) != C or C > 3:
+            raise UcodError("to_tensor_normalize: mean/std must have one entry per channel (<= 3 channels)")
+        ch = C
+        m = (ctypes.c_float * C)(*[float(v) for v in mean])
+        sd = (ctypes.c_float * C)(*[float(v) for v in std])
+    with torch.cuda.device(x.device):
+        _lib.call("ucod_to_tensor_normalize", ptr(x), ptr(out), _u64(x.numel() // (H * W)), H * W, ch, m, sd,
+                  stream_ptr(x.device))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 class _DiscW(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
@@ -387,8 +410,9 @@ def coral_scatter_windows(window_preds: torch.Tensor | None, slot_of_cell: torch
     return out
 
 
-def coral_gated_ensemble(preds: torch.Tensor, h_preds: torch.Tensor, w0, b0, w2, b2):
-    """preds [B,1,P,P], h_preds [B,1,S,S] -> (out [B,1,S,S], weight [B,1,S,S])."""
+def coral_gated_ensemble(preds: torch.Tensor, h_preds: torch.Tensor, w0, b0, w2, b2, max_per_image: bool = False):
+    """preds [B,1,P,P], h_preds [B,1,S,S] -> (out [B,1,S,S], weight [B,1,S,S]).  max_per_image: normalise the local
+    entropy by each image's own maximum (= the reference run at batch 1) instead of the batch maximum."""
     _lib.require_cuda(preds, h_preds)
     p, h = preds.float().contiguous(), h_preds.float().contiguous()
     B, _, P, _ = p.shape
@@ -400,6 +424,6 @@ def coral_gated_ensemble(preds: torch.Tensor, h_preds: torch.Tensor, w0, b0, w2,
     ws = _ws(lib.ucod_coral_gated_ensemble_workspace_bytes(B, S), dev)
     wp, wn = _aligned(ws)
     with torch.cuda.device(dev):
-        _lib.call("ucod_coral_gated_ensemble", ptr(p), P, ptr(h), B, S, ptr(w0), ptr(b0), ptr(w2), ptr(b2), ptr(out),
-                  ptr(weight), wp, wn, stream_ptr(dev))
+        _lib.call("ucod_coral_gated_ensemble", ptr(p), P, ptr(h), B, S, int(bool(max_per_image)), ptr(w0), ptr(b0),
+                  ptr(w2), ptr(b2), ptr(out), ptr(weight), wp, wn, stream_ptr(dev))
     return out, weight
