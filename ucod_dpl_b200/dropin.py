@@ -40,6 +40,16 @@ ALIASES = {
     "data.utils": "ucod_dpl_b200.data.utils",
     "data.utils.feature_extractor": "ucod_dpl_b200.data.utils.feature_extractor",
     "data.utils.found_bkg_mask": "ucod_dpl_b200.data.utils.found_bkg_mask",
+    "data.datasets": "ucod_dpl_b200.data.datasets",
+    "data.datasets.transforms": "ucod_dpl_b200.data.datasets.transforms",
+    "data.datasets.cache_manager": "ucod_dpl_b200.data.datasets.cache_manager",
+    "data.datasets.base_dataset": "ucod_dpl_b200.data.datasets.base_dataset",
+    "data.datasets.uscod_dataset": "ucod_dpl_b200.data.datasets.base_dataset",
+    "engine.utils.save_image": "ucod_dpl_b200.engine.utils.save_image",
+    "scripts": "ucod_dpl_b200.scripts",
+    "scripts.args": "ucod_dpl_b200.scripts.args",
+    "scripts.eval": "ucod_dpl_b200.scripts.eval",
+    "scripts.LTeval": "ucod_dpl_b200.scripts.LTeval",
     "generate_pseudo_label": "ucod_dpl_b200.generate_pseudo_label",
 }
 
