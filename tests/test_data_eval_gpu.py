@@ -222,3 +222,47 @@ def test_second_stage_launcher(tmp_path, monkeypatch):
         items.append(omet.per_image(gt.astype(np.float64) / 255.0, pred > 0))
     for k, v in omet.aggregate(items).items():
         assert abs(res["SETC"][k] - v) < 1e-9, (k, res["SETC"][k], v)
+
+
+def test_train_launcher_end_to_end(tmp_path, monkeypatch):
+    """`scripts.train` on a tiny image folder: builds both caches in the reference layout, runs the schedule
+    (discriminator epoch, decoder epochs, finetune switch, checkpoint, Look-Twice validation), and the checkpoint it
+    writes is found and evaluated by `scripts.eval` without --load_from."""
+    from ucod_dpl_b200.engine.utils.fileio import MetaListPickleIO
+    from ucod_dpl_b200.scripts import eval as ev
+    from ucod_dpl_b200.scripts import train as tr
+    S = 224
+    data = tmp_path / "data"
+    _write_set(data, "TR-X", 12, 0)
+    _write_set(data, "TE-X", 3, 30)
+    os.makedirs(tmp_path / "configs" / "uscod"), os.makedirs(tmp_path / "configs" / "__base__")
+    (tmp_path / "configs" / "uscod" / "tiny.py").write_text(
+        (ROOT / "configs" / "uscod" / "UCOD-DPL_dinov2.py").read_text().replace("(518, 518)", f"({S}, {S})"))
+    (tmp_path / "configs" / "__base__" / "shared_defaults.py").write_text(
+        (ROOT / "configs" / "__base__" / "shared_defaults.py").read_text()
+        .replace("TR-CAMO+TR-COD10K", "TR-X").replace("TE-CAMO", "TE-X"))
+    monkeypatch.chdir(tmp_path)
+    out = tr.main(["--config", "configs/uscod/tiny.py", "--work_dir", "work", "--dataset_dir", str(data),
+                   "--cache_dir", str(tmp_path / "cache"), "--max_epoch", "6", "--exp_name", "run0", "--no_save"])
+    # caches: reference layout, one item per image, reference item shapes
+    feats = MetaListPickleIO(base_path=tmp_path / "cache" / "features_cache" / "dinov2" / "train" / "TR-X")
+    pls = MetaListPickleIO(base_path=tmp_path / "cache" / "pseudo_label_cache" / "TR-X")
+    assert feats.mode == "r" and pls.mode == "r" and feats.len() == 12 and pls.len() == 12
+    assert tuple(feats.read_file(3).shape) == (768, 16, 16) and tuple(pls.read_file(3).shape) == (1, 16, 16)
+    assert set(pls.read_file(3).unique().tolist()) <= {0.0, 1.0}
+    # schedule: epoch 0 logs its losses; checkpoint and validation after epoch 5
+    assert len(out["losses"]) == 1 and np.isfinite(out["losses"][0])
+    run = tmp_path / "work" / "uscod" / "tiny" / "run0"
+    ck = run / "ckp" / "epoch5.pth" / "model.safetensors"
+    assert ck.exists() and sorted(os.listdir(run / "ckp")) == ["epoch5.pth"]
+    sd = load_file(str(ck))
+    ref = load_file(str(ROOT / "weights" / "UCOD_DPL_dinov2.safetensors"))
+    assert set(sd.keys()) == set(ref.keys()) and all(sd[k].shape == ref[k].shape for k in ref)
+    assert all(torch.isfinite(v).all() for v in sd.values())
+    assert not torch.equal(sd["decoder.decoupling.weight"], sd["decoder_ema.decoupling.weight"])
+    assert out["best"] is not None and 0.0 <= out["best"]["MAE"] <= 1.0
+    # the eval launcher discovers that checkpoint (no --load_from) and reproduces the validation result
+    res = ev.main(["--config", "configs/uscod/tiny.py", "--work_dir", "work", "--dataset_dir", str(data),
+                   "--datasets", "TE-X", "--exp_name", "eval0", "--no_save"])
+    for k, v in out["best"].items():
+        assert abs(res["TE-X"][k] - v) < 1e-9, (k, res["TE-X"][k], v)

@@ -49,6 +49,7 @@ ALIASES = {
     "scripts": "ucod_dpl_b200.scripts",
     "scripts.args": "ucod_dpl_b200.scripts.args",
     "scripts.eval": "ucod_dpl_b200.scripts.eval",
+    "scripts.train": "ucod_dpl_b200.scripts.train",
     "scripts.LTeval": "ucod_dpl_b200.scripts.LTeval",
     "generate_pseudo_label": "ucod_dpl_b200.generate_pseudo_label",
 }

@@ -143,3 +143,124 @@ class LookTwiceEvaluator:
             originals = images
         mask_u8 = up.to(torch.uint8)
         return self.look_twice_batch(originals, bboxes, mask_u8, layout=layout, orig_sizes=orig_sizes), bboxes
+
+
+class TrainLoop:
+    """First-stage training schedule (reference: `TrainLoop`, engine/runner/loop_UCOD_DPL.py:35-255): per epoch
+    [finetune switch] -> [discriminator epochs every `dis_intertrain` epochs until the finetune phase] -> decoder
+    epoch -> [checkpoint] -> [Look-Twice validation, best MAE kept].  Same decision methods and counters.
+
+    The reference pulls batches of cached features through a DataLoader; here the whole cache is resident in HBM
+    (`keys` bf16 [N, gh*gw, dim] token-major, `pseudo_labels` [N,1,16,16]; 4040 training images @37x37 are 8.5 GB)
+    and an epoch is a seeded device permutation cut into batches, each rank taking every world-th batch slot
+    (gradients are all-reduced inside `FirstStageTrainer.process_batch`).
+    """
+
+    def __init__(self, config, trainer, dis_trainer, keys: torch.Tensor, pseudo_labels: torch.Tensor, grid_in,
+                 validate=None, save_checkpoint=None, logger=None, seed: int = 0, rank: int = 0, world_size: int = 1):
+        self.cfg = config
+        self.trainer, self.dis_trainer = trainer, dis_trainer
+        self.keys, self.pl, self.grid_in = keys, pseudo_labels, tuple(grid_in)
+        self.validate, self.save_checkpoint, self.logger = validate, save_checkpoint, logger
+        self.rank, self.world = rank, world_size
+        tc = config.train_cfg
+        self._start_epoch = tc.start_epoch
+        self._max_epoch = tc.max_epoch
+        self._cur_epoch = 0
+        self._start_finetune = tc.start_finetune
+        self.finetune = False
+        self.global_step = 0
+        self.batch_size = int(config.dataset_cfg.trainloader_cfg.batch_size)
+        self.shuffle = bool(config.dataset_cfg.trainloader_cfg.shuffle)
+        self.enable_val = config.val_cfg.enable_val
+        self.val_interval = config.val_cfg.val_interval
+        self.dis_intertrain = tc.dis_intertrain
+        sv = config.val_cfg.start_val
+        self.val_start = self._max_epoch + sv if sv < 0 else sv
+        ss = tc.save_cfg.start_save
+        self.save_start = self._max_epoch + ss if ss < 0 else ss
+        self.save_interval = tc.save_cfg.save_interval
+        self.log_interval = config.log_cfg.log_interval
+        self.best_mae = 1000.0
+        self.best_result = None
+        self.losses: List[float] = []
+        self._gen = torch.Generator(device="cpu").manual_seed(seed)
+
+    # ---- schedule decisions (loop_UCOD_DPL.py:193-215) ----
+    def decide_to_train_dis(self) -> bool:
+        if self.cfg.train_cfg.merge_method != "dis":
+            return False
+        return self._cur_epoch % self.dis_intertrain == 0 and not self.finetune
+
+    def decide_to_finetune(self) -> bool:
+        if self._cur_epoch == self._max_epoch + self._start_finetune:
+            self.finetune = True
+            return True
+        return False
+
+    def decide_to_save(self) -> bool:
+        return self._cur_epoch >= self.save_start and self._cur_epoch % self.save_interval == 0
+
+    def decide_to_val(self) -> bool:
+        return bool(self.enable_val and self._cur_epoch >= self.val_start and self._cur_epoch % self.val_interval == 0)
+
+    # ---- data ----
+    def _batches(self):
+        """this rank's batches of one epoch: index tensors on the device."""
+        n = self.keys.shape[0]
+        order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
+        per_step = self.batch_size * self.world
+        for s in range(0, n, per_step):
+            idx = order[s + self.rank * self.batch_size: s + (self.rank + 1) * self.batch_size]
+            if idx.numel() == 0:       # ragged tail: ranks without data repeat the head of the permutation, so that
+                idx = order[: self.batch_size]  # every rank joins every gradient all-reduce
+            yield idx.to(self.keys.device)
+
+    def _log(self, msg: str) -> None:
+        if self.logger is not None:
+            self.logger.info(msg)
+
+    # ---- epochs ----
+    def Discriminator_epoch(self) -> None:
+        for idx in self._batches():
+            loss = self.dis_trainer.epoch_step(self.trainer.model, self.keys.index_select(0, idx), self.grid_in,
+                                               self.pl.index_select(0, idx), feature_size=self.trainer.fs)
+            if self._cur_epoch % self.log_interval == 0:
+                self._log("dis:loss:{:.4f}".format(float(loss)))
+
+    def Discriminator_train(self) -> None:
+        for _ in range(self.cfg.train_cfg.dis_epoch):
+            self.Discriminator_epoch()
+
+    def run_epoch(self) -> None:
+        self.trainer.cur_epoch = self._cur_epoch
+        for idx in self._batches():
+            loss = self.trainer.process_batch(self.keys.index_select(0, idx), self.grid_in, self.pl.index_select(0, idx))
+            if self._cur_epoch % self.log_interval == 0:
+                lv = float(loss)
+                self.losses.append(lv)
+                self._log(f"iter{self.global_step}:loss:{lv:.4f}")
+            self.global_step += 1
+
+    def _update_best_result(self, result) -> None:
+        if result["MAE"] < self.best_mae:
+            self.best_mae = result["MAE"]
+            self.best_result = result
+            self._log("best result: {}".format({k: [round(float(v), 4)] for k, v in result.items()}))
+
+    def run(self):
+        while self._cur_epoch < self._max_epoch:
+            if self.decide_to_finetune():
+                self.trainer.start_finetune_phase()
+                if self.dis_trainer is not None:
+                    self.dis_trainer.reset_optimizer()
+                self.global_step = 0
+            if self.decide_to_train_dis():
+                self.Discriminator_train()
+            self.run_epoch()
+            self._cur_epoch += 1
+            if self.decide_to_save() and self.save_checkpoint is not None:
+                self.save_checkpoint(self._cur_epoch)
+            if self.decide_to_val() and self.validate is not None:
+                self._update_best_result(self.validate())
+        return self.best_result

@@ -89,3 +89,61 @@ def generate_pseudo_label_cache(generator: PseudoLabelGenerator, images_u8: torc
     if rank == 0:
         return write_pseudo_label_cache(full, cache_dir)
     return 0
+
+
+@torch.no_grad()
+def generate_from_folders(generator: PseudoLabelGenerator, image_paths, cache_dir, batch: int = 256,
+                          decode_threads: int = 8) -> int:
+    """The reference's `main()` loop (:126-150) over image files: host decode on a thread pool, Pillow-exact
+    resize to 224^2 on the device, batched scoring; this rank takes `dist.shard_indices`, rank 0 writes the cache."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from . import dist as ud
+    from .data.datasets.base_dataset import read_image
+    from .data.datasets.transforms import ImageTransforms
+    tf = ImageTransforms.get_raw_transform((generator.image_size, generator.image_size))
+    idx = list(ud.shard_indices(len(image_paths)))
+    outs = []
+    with ThreadPoolExecutor(decode_threads) as pool:
+        for s in range(0, len(idx), batch):
+            imgs = list(pool.map(lambda i: read_image(image_paths[i], "RGB"), idx[s:s + batch]))
+            outs.append(generator(tf.batch(imgs)))
+    g = generator.image_size // generator.extractor.spec.patch
+    dev = generator.extractor.device
+    local = torch.cat(outs, 0) if outs else torch.zeros(0, g, g, dtype=torch.uint8, device=dev)
+    full = ud.gather_sharded_masks(local, len(image_paths))
+    if ud.world()[0] == 0:
+        return write_pseudo_label_cache(full, cache_dir)
+    return 0
+
+
+def main(argv=None) -> int:
+    """`python -m ucod_dpl_b200.generate_pseudo_label --dataset TR-CAMO+TR-COD10K` — the reference's command line."""
+    import argparse
+    import os
+    from types import SimpleNamespace
+
+    from .data.utils.feature_extractor import load_vit_state_dict
+    p = argparse.ArgumentParser(description="Generate pseudo labels for COD datasets using DINOv2")
+    p.add_argument("--dataset", type=str, default="TR-CAMO+TR-COD10K")
+    p.add_argument("--image_path", type=str, default="./datasets/RefCOD/{}/im")
+    p.add_argument("--cache_path", type=str, default="./datasets/cache/pseudo_label_cache/")
+    p.add_argument("--backbone_weights", type=str, default="./weights")
+    args = p.parse_args(argv)
+    paths = []
+    for name in args.dataset.split("+"):
+        d = args.image_path.format(name)
+        if not os.path.exists(d):
+            raise ValueError(f"Image path {d} does not exist!")
+        paths += [os.path.join(d, f) for f in os.listdir(d)]
+    paths = sorted(paths)
+    print(f"Found {len(paths)} images from {args.dataset}.")
+    sd = load_vit_state_dict(SimpleNamespace(type="dinov2", backbone="facebook/dinov2-base",
+                                             backbone_weights=args.backbone_weights))
+    n = generate_from_folders(PseudoLabelGenerator(sd, "dinov2"), paths, os.path.join(args.cache_path, args.dataset))
+    print(f"Successfully generated {n} pseudo labels and saved to cache.")
+    return n
+
+
+if __name__ == "__main__":
+    main()

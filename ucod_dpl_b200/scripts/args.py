@@ -17,4 +17,7 @@ def parse_train_args(argv=None):
     p.add_argument("--batch_size", type=int, default=64, help="images per launch sequence and GPU")
     p.add_argument("--exp_name", type=str, default=None)
     p.add_argument("--no_save", action="store_true", help="skip the PNG output")
+    p.add_argument("--cache_dir", type=str, default=None, help="overrides cfg.dataset_cfg.cache_dir")
+    p.add_argument("--max_epoch", type=int, default=None, help="overrides cfg.train_cfg.max_epoch")
+    p.add_argument("--no_val", action="store_true", help="train without the periodic Look-Twice validation")
     return p.parse_args(argv)

@@ -75,14 +75,32 @@ def _setup_run_dir(cfg, rank: int) -> logging.Logger:
     return logger
 
 
+def resolve_checkpoint(path) -> str:
+    """a safetensors file, or the directory `accelerator.save_model` writes (`.../epoch{n}.pth/model.safetensors`)."""
+    path = str(path)
+    return os.path.join(path, "model.safetensors") if os.path.isdir(path) else path
+
+
+def find_latest_checkpoint(cfg, ckp_type: str = "ckp"):
+    """`BaseRunner._find_latest_checkpoint` (runner.py:209-241): newest `*.pth` / `*.pt` entry of
+    `{dirname(log_path)}/{ckp_type}`; additionally every run directory `{work_dir}/*/{ckp_type}` is searched, since
+    that is where `save_checkpoint` (runner.py:165-185) actually puts them."""
+    roots = [os.path.join(os.path.dirname(cfg.log_cfg.log_path), ckp_type)]
+    if os.path.isdir(cfg.work_dir):
+        roots += [os.path.join(cfg.work_dir, d, ckp_type) for d in sorted(os.listdir(cfg.work_dir))]
+    found = [os.path.join(r, f) for r in roots if os.path.isdir(r) for f in os.listdir(r)
+             if f.endswith((".pth", ".pt", ".safetensors"))]
+    return max(found, key=os.path.getmtime) if found else None
+
+
 def load_first_stage(cfg, device) -> baseline:
     from safetensors.torch import load_file
 
     model = baseline(SimpleNamespace(dim=cfg.model_cfg.dim))
-    ckpt = cfg.train_cfg.get("checkpoint", None)
+    ckpt = cfg.train_cfg.get("checkpoint", None) or find_latest_checkpoint(cfg, "ckp")
     if ckpt is None:
-        raise FileNotFoundError("--load_from is required (no checkpoint discovery without a training run directory)")
-    model.load_state_dict(load_file(str(ckpt)), strict=True)
+        raise FileNotFoundError("no --load_from and no checkpoint under the work_dir")
+    model.load_state_dict(load_file(resolve_checkpoint(ckpt)), strict=True)
     return model.to(device).eval()
 
 
@@ -151,9 +169,10 @@ def main(argv=None, second_stage: bool = False) -> dict:
         from safetensors.torch import load_file
 
         refiner = SparseRefiner.from_config(cfg.model_cfg).to(device).eval()
-        if cfg.train_cfg.get("refiner_path", None) is None:
-            raise FileNotFoundError("--refiner_path is required for the second stage")
-        refiner.load_state_dict(load_file(str(cfg.train_cfg.refiner_path)), strict=True)
+        rpath = cfg.train_cfg.get("refiner_path", None) or find_latest_checkpoint(cfg, "refiner_ckp")
+        if rpath is None:
+            raise FileNotFoundError("no --refiner_path and no refiner checkpoint under the work_dir")
+        refiner.load_state_dict(load_file(resolve_checkpoint(rpath)), strict=True)
     results = {}
     for name in (args.datasets.split(",") if args.datasets else DATASET):
         if rank == 0:

@@ -151,8 +151,14 @@ class FirstStageTrainer:
         return self.lr0 * self.gamma ** (self.opt_steps // self.step_size)
 
     def start_finetune_phase(self):
+        """`Runner.start_finetune` + `TrainLoop.run` (runner.py:378-379, loop_UCOD_DPL.py:101-103): the optimiser and
+        the StepLR schedule are rebuilt (fresh AdamW moments, lr back to lr0) and global_step restarts, which also
+        restarts the EMA warm-up `1 - 1/(step+1)`."""
         self.finetune = True
         self.global_step = 0
+        self.opt_steps = 0
+        self.flat_m.zero_()
+        self.flat_v.zero_()
 
     @torch.no_grad()
     def process_batch(self, key_tokens_bf16: torch.Tensor, grid_in, pseudo_labels: torch.Tensor):
@@ -234,6 +240,12 @@ class DiscriminatorTrainer:
             self.grad_views.append(self.flat_g[o:o + sz])
             o += slot
         self.loss = torch.zeros((), device=dev)
+
+    def reset_optimizer(self):
+        """`_build_optimizer` again (runner.py:276-308, called by `start_finetune`): fresh moments and schedule."""
+        self.opt_steps = 0
+        self.flat_m.zero_()
+        self.flat_v.zero_()
 
     def _forward(self, mask):
         D = self.D
