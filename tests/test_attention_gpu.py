@@ -24,7 +24,11 @@ def reference(qkv, B, H, T, D, scale):
 
 
 @pytest.mark.parametrize("B,H,T,D", [(2, 12, 1370, 64), (1, 12, 257, 64), (3, 2, 128, 64), (1, 1, 5, 64),
-                                     (2, 3, 129, 64), (1, 2, 2917, 64), (1, 8, 400, 128)])
+                                     (2, 3, 129, 64), (1, 2, 2917, 64), (1, 8, 400, 128),
+                                     # tail handling: 1..4 leftover query rows go to the row kernel (260, 258/128),
+                                     # 5 do not (261); last key tile of exactly one / three 32-column chunks
+                                     (2, 3, 260, 64), (1, 2, 261, 64), (2, 2, 160, 64), (1, 3, 193, 64),
+                                     (2, 2, 258, 128), (4, 12, 257, 64)])
 def test_attention_matches_fp32(B, H, T, D):
     g = torch.Generator(device="cuda").manual_seed(T)
     qkv = torch.randn(B, T, 3 * H * D, device="cuda", generator=g).to(torch.bfloat16)

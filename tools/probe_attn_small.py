@@ -4,7 +4,7 @@ from pathlib import Path
 import torch
 sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from ucod_dpl_b200 import _lib
-for B, T in ((256, 257), (64, 1370)):
+for B, T in ((256, 256), (256, 257), (256, 384), (256, 128), (64, 1370)):
     H, D = 12, 64
     qkv = torch.randn(B, T, 3 * H * D, device="cuda").to(torch.bfloat16)
     ctx = torch.empty(B, T, H * D, device="cuda", dtype=torch.bfloat16)

@@ -219,14 +219,19 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             constexpr uint32_t idesc_s = umma_idesc_bf16(C::BM, C::BN);
             constexpr uint32_t idesc_o = umma_idesc_bf16(C::BM, D) | (1u << 16);  // B operand MN-major
             const uint32_t q_addr = smem_u32(sQ);
+            // the last tile only computes the 32-column chunks that hold valid keys (S with N = tail_cols, P V with
+            // tail_cols / 16 K-steps); TMA zero-fills the key rows past Tk inside the last chunk
+            const int tail_cols = ((Tk - (n_tiles - 1) * C::BN + 31) / 32) * 32;
+            const uint32_t idesc_s_tail = umma_idesc_bf16(C::BM, tail_cols);
             auto issue_s = [&](int j) {
                 const uint32_t k_addr = smem_u32(sK + (j & 1) * C::SK_BYTES);
+                const uint32_t idesc = j == n_tiles - 1 ? idesc_s_tail : idesc_s;
 #pragma unroll
                 for (int kb = 0; kb < C::NKB; ++kb)
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16_ss(tmem_s, umma_desc_kmajor_sw128(q_addr + kb * C::BLK_BYTES + k * 32),
-                                     umma_desc_kmajor_sw128(k_addr + kb * C::BLK_BYTES + k * 32), idesc_s,
+                                     umma_desc_kmajor_sw128(k_addr + kb * C::BLK_BYTES + k * 32), idesc,
                                      (kb | k) != 0);
                 umma_commit(&bar_kempty[j & 1]);
                 umma_commit(bar_s);
@@ -252,10 +257,12 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                 TL(1, j, 4);
                 tc_fence_after();
                 const uint32_t v_addr = smem_u32(sV + st * C::SV_BYTES);
+                const int ksteps = j == n_tiles - 1 ? tail_cols / 16 : C::BN / 16;
 #pragma unroll
                 for (int k = 0; k < C::BN / 16; ++k)
-                    umma_bf16_ts(tmem_o, tmem_p + k * 8, umma_desc_mnmajor_sw128(v_addr + k * 2048, C::BLK_BYTES),
-                                 idesc_o, (j | k) != 0);
+                    if (k < ksteps)
+                        umma_bf16_ts(tmem_o, tmem_p + k * 8, umma_desc_mnmajor_sw128(v_addr + k * 2048, C::BLK_BYTES),
+                                     idesc_o, (j | k) != 0);
                 umma_commit(&bar_vempty[st]);
                 umma_commit(bar_pv);
                 TL(1, j, 5);
@@ -269,7 +276,7 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         float m_ref = 0.f, l_run = 0.f;
 
-        for (int j = 0; j < n_tiles; ++j) {
+        for (int j = 0; j < n_tiles - 1; ++j) {
             TL(2, j, 0);
             mbar_wait(bar_s, j & 1);
             TL(2, j, 1);
@@ -281,12 +288,6 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             TL(2, j, 2);
             tc_fence_before();
             mbar_arrive(bar_sfree);
-            const int valid = Tk - j * C::BN;  // keys valid in this tile (>= 1)
-            if (valid < C::BN) {
-#pragma unroll
-                for (int i = 0; i < 128; ++i)
-                    if (i >= valid) u[i] = 0xff800000u;  // -inf
-            }
             // ---- row maximum (4 independent chains) ----
             float mx[4];
 #pragma unroll
@@ -350,6 +351,79 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             TL(2, j, 6);
         }
 
+        {
+            // ---- last tile: only the nch 32-column chunks that hold valid keys are loaded, exponentiated and
+            //      published (warp-uniform guards; everything past `valid` is -inf -> probability 0) ----
+            const int j = n_tiles - 1;
+            const int valid = Tk - j * C::BN;  // keys valid in this tile (>= 1)
+            const int nch = (valid + 31) >> 5;
+            mbar_wait(bar_s, j & 1);
+            tc_fence_after();
+            uint32_t u[128];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < nch) tmem_ld32(tmem_s + lane_off + c * 32, reinterpret_cast<uint32_t(&)[32]>(u[32 * c]));
+            tmem_wait_ld();
+            tc_fence_before();
+            mbar_arrive(bar_sfree);
+#pragma unroll
+            for (int i = 0; i < 128; ++i)
+                if (i >= valid) u[i] = 0xff800000u;  // -inf (also the chunks that were not loaded)
+            float mx = __uint_as_float(u[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < nch) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(u[32 * c + i]));
+                }
+            const float ms = mx * scale_log2e;
+            float alpha = 1.f;
+            bool grow = false;
+            if (j == 0) {
+                m_ref = ms;
+            } else if (ms > m_ref + 8.f) {
+                alpha = ex2_approx(m_ref - ms);
+                m_ref = ms;
+                grow = true;
+            }
+            const float neg_m = -m_ref;
+            float ls = 0.f;
+            uint32_t pk[64];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < nch) {
+#pragma unroll
+                    for (int i = 16 * c; i < 16 * c + 16; ++i) {
+                        const float p0 = ex2_approx(fmaf(__uint_as_float(u[2 * i]), scale_log2e, neg_m));
+                        const float p1 = ex2_approx(fmaf(__uint_as_float(u[2 * i + 1]), scale_log2e, neg_m));
+                        ls += p0 + p1;
+                        pk[i] = pack_bf16x2(p0, p1);
+                    }
+                }
+            l_run = l_run * alpha + ls;
+            if (j > 0) {
+                mbar_wait(bar_pv, (j - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, grow)) {
+#pragma unroll 1
+                    for (int c = 0; c < D / 32; ++c) {
+                        uint32_t o[32];
+                        tmem_ld32(tmem_o + lane_off + c * 32, o);
+                        tmem_wait_ld();
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+                        tmem_st32(tmem_o + lane_off + c * 32, o);
+                    }
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (c < nch) tmem_st16(tmem_p + lane_off + c * 16, reinterpret_cast<uint32_t(&)[16]>(pk[16 * c]));
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_p);
+        }
+
         // ---- epilogue: O / l -> bf16 ctx ----
         mbar_wait(bar_pv, (n_tiles - 1) & 1);
         tc_fence_after();
@@ -380,6 +454,112 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     if (warp == 1) tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// A few query rows on CUDA cores: when tokens_q = n * 128 + (1..4) (a ViT's 256 patches + CLS), a whole 128-row
+// tile for the leftover rows would cost as much as a full one; this kernel does them instead, one CTA per
+// (row, batch*head): fp32 scores in shared memory, block max / sum, then the probability-weighted V sum.
+// It is bound by re-reading K and V once (HBM/L2): T = 257, 256 images: tiles 0.169 ms + rows 0.058 ms, against
+// 0.257 ms with a third q-tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRowsMax = 4;
+
+template <int D>
+__global__ void __launch_bounds__(128)
+    attention_rows_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ k,
+                          const __nv_bfloat16* __restrict__ v, int ld_kv, __nv_bfloat16* __restrict__ ctx, int ld_ctx,
+                          int Tq, int Tk, int H, int row0, float scale, const int* __restrict__ kv_map) {
+    extern __shared__ float sm_rows[];
+    float* sq = sm_rows;          // [D]
+    float* part = sq + D;         // [128 / (D/2)][D] = 256 partial sums
+    float* red = part + 256;      // [4]
+    float* sc = red + 4;          // [Tk]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = row0 + blockIdx.x;
+    const int b = blockIdx.y / H, h = blockIdx.y - b * H;
+    const int bkv = kv_map != nullptr ? __ldg(kv_map + b) : b;
+    const __nv_bfloat16* qr = q + ((size_t)b * Tq + row) * (size_t)ld_q + h * D;
+    const __nv_bfloat16* kb = k + (size_t)bkv * Tk * (size_t)ld_kv + h * D;
+    const __nv_bfloat16* vb = v + (size_t)bkv * Tk * (size_t)ld_kv + h * D;
+    if (tid < D) sq[tid] = __bfloat162float(qr[tid]);
+    __syncthreads();
+    // scores
+    float mx = -INFINITY;
+#pragma unroll 2
+    for (int t = tid; t < Tk; t += 128) {
+        const uint4* kr = reinterpret_cast<const uint4*>(kb + (size_t)t * ld_kv);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < D / 8; ++c) {
+            const uint4 w = __ldg(kr + c);
+            const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ww[e]));
+                acc = fmaf(f.x, sq[c * 8 + 2 * e], acc);
+                acc = fmaf(f.y, sq[c * 8 + 2 * e + 1], acc);
+            }
+        }
+        acc *= scale;
+        sc[t] = acc;
+        mx = fmaxf(mx, acc);
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int t = tid; t < Tk; t += 128) {
+        const float p = __expf(sc[t] - mx);
+        sc[t] = p;
+        sum += p;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    const float inv = 1.0f / (red[0] + red[1] + red[2] + red[3]);
+    __syncthreads();
+    // ctx[d] = sum_t p[t] * V[t][d]: thread = (dim pair, key slice)
+    constexpr int DP = D / 2, SL = 128 / DP;
+    const int dp = tid % DP, sl = tid / DP;
+    float a0 = 0.f, a1 = 0.f;
+    const __nv_bfloat16* vcol = vb + 2 * dp;
+    int t = sl;
+    for (; t + 7 * SL < Tk; t += 8 * SL) {  // 8 independent loads in flight per thread
+        uint32_t w[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            w[u] = __ldg(reinterpret_cast<const unsigned int*>(vcol + (size_t)(t + u * SL) * ld_kv));
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[u]));
+            const float p = sc[t + u * SL];
+            a0 = fmaf(p, f.x, a0);
+            a1 = fmaf(p, f.y, a1);
+        }
+    }
+    for (; t < Tk; t += SL) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(vcol + (size_t)t * ld_kv));
+        const float p = sc[t];
+        a0 = fmaf(p, f.x, a0);
+        a1 = fmaf(p, f.y, a1);
+    }
+    part[sl * D + 2 * dp] = a0;
+    part[sl * D + 2 * dp + 1] = a1;
+    __syncthreads();
+    if (tid < DP) {
+        __nv_bfloat16* out = ctx + ((size_t)b * Tq + row) * (size_t)ld_ctx + h * D;
+        float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+        for (int s2 = 0; s2 < SL; ++s2) {
+            o0 += part[s2 * D + 2 * tid];
+            o1 += part[s2 * D + 2 * tid + 1];
+        }
+        *reinterpret_cast<__nv_bfloat162*>(out + 2 * tid) = __floats2bfloat162_rn(o0 * inv, o1 * inv);
+    }
+}
+
 template <int D>
 int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
     using C = AttCfg<D>;
@@ -400,12 +580,23 @@ int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
         UCOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
         configured = true;
     }
-    dim3 grid((unsigned)ceil_div(a.tokens_q, C::BM), (unsigned)(a.batch * a.heads));
+    // a query tail of 1..kRowsMax rows goes to the CUDA-core row kernel instead of a whole extra q-tile
+    const int q_tail = a.tokens_q % C::BM;
+    const size_t rows_smem = ((size_t)D + 256 + 4 + a.tokens_kv) * sizeof(float);
+    const bool split_tail = a.tokens_q > C::BM && q_tail > 0 && q_tail <= kRowsMax && rows_smem <= 48 * 1024;
+    dim3 grid((unsigned)(split_tail ? a.tokens_q / C::BM : ceil_div(a.tokens_q, C::BM)), (unsigned)(a.batch * a.heads));
     {
         ProfScope ps(KC_ATTENTION, stream, 4.0 * a.batch * a.heads * (double)a.tokens_q * a.tokens_kv * a.head_dim_real);
         kern<<<grid, C::THREADS, C::SMEM, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(a.ctx), a.tokens_q,
                                                      a.tokens_kv, a.heads, a.ld_ctx, a.scale * 1.4426950408889634f,
                                                      a.kv_batch_map);
+    }
+    if (split_tail) {
+        ProfScope ps(KC_ATTENTION, stream, 0.0);  // its flops are counted with the tile kernel above
+        attention_rows_kernel<D><<<dim3((unsigned)q_tail, grid.y), 128, rows_smem, stream>>>(
+                static_cast<const __nv_bfloat16*>(a.q), a.ld_q, static_cast<const __nv_bfloat16*>(a.k),
+                static_cast<const __nv_bfloat16*>(a.v), a.ld_kv, reinterpret_cast<__nv_bfloat16*>(a.ctx), a.ld_ctx,
+            a.tokens_q, a.tokens_kv, a.heads, a.tokens_q - q_tail, a.scale, a.kv_batch_map);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
