@@ -49,6 +49,74 @@ __global__ void im2col_patch_kernel(const TIn* __restrict__ img, __nv_bfloat16* 
     }
 }
 
+// Same mapping, staged through shared memory: one CTA per (image, patch row) gathers the 3 x p image rows with
+// coalesced loads into the [gw, Kpad] output layout in smem, then streams the patch rows out with 16-byte stores
+// (the direct version writes 2p-byte fragments: 0.36 ms per 64 images @518^2, 7 % of the HBM roofline).
+template <typename TIn>
+__global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int Hh,
+                                         int Ww, int p, int Kpad, float3 mean, float3 inv_std) {
+    extern __shared__ __align__(16) uint8_t im2col_smem[];
+    __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(im2col_smem);
+    const int gw = Ww / p, gh = Hh / p;
+    const int b = blockIdx.y, py = blockIdx.x;
+    const int kvalid = 3 * p * p;
+    const int wused = gw * p;
+    for (int idx = threadIdx.x; idx < gw * (Kpad - kvalid); idx += blockDim.x) {
+        const int px = idx / (Kpad - kvalid), k = kvalid + idx % (Kpad - kvalid);
+        tile[px * Kpad + k] = __float2bfloat16_rn(0.f);
+    }
+    if constexpr (sizeof(TIn) == 1) {
+        // uint8 input: the p image rows of one channel are one contiguous span of p * Ww bytes; read it with 16-byte
+        // loads from the aligned-down address (byte loads keep only 32 B per warp request in flight) and walk the
+        // (row, x, patch, column) indices incrementally
+        for (int c = 0; c < 3; ++c) {
+            const uint8_t* span = reinterpret_cast<const uint8_t*>(img) + (((size_t)b * 3 + c) * Hh + (size_t)py * p) * Ww;
+            const int nbytes = p * Ww;
+            const int head = (int)(reinterpret_cast<uintptr_t>(span) & 15);
+            const uint4* base = reinterpret_cast<const uint4*>(span - head);
+            const int nvec = (head + nbytes + 15) >> 4;
+            const float m = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
+            const float sd = c == 0 ? inv_std.x : (c == 1 ? inv_std.y : inv_std.z);
+            __nv_bfloat16* tc = tile + c * p * p;
+            for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+                const uint4 w = __ldg(base + v);
+                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+                const int o = v * 16 - head;  // span offset of byte 0 of this vector
+                const int first = o < 0 ? -o : 0;
+                int i = (o + first) / Ww;
+                int x = (o + first) - i * Ww;
+                int px = x / p;
+                int j = x - px * p;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k >= first && o + k < nbytes) {
+                        if (x < wused) {
+                            const float f = (float)((ww[k >> 2] >> (8 * (k & 3))) & 0xffu);
+                            tc[px * Kpad + i * p + j] = __float2bfloat16_rn((f / 255.0f - m) * sd);
+                        }
+                        ++x;
+                        if (++j == p) j = 0, ++px;
+                        if (x == Ww) x = 0, px = 0, j = 0, ++i;
+                    }
+                }
+            }
+        }
+    } else {
+        for (int idx = threadIdx.x; idx < 3 * p * wused; idx += blockDim.x) {
+            const int x = idx % wused;
+            const int ci = idx / wused;  // c*p + i
+            const int c = ci / p, i = ci - c * p;
+            const float v = static_cast<float>(img[(((size_t)b * 3 + c) * Hh + (size_t)py * p + i) * Ww + x]);
+            const int px = x / p, j = x - px * p;
+            tile[px * Kpad + c * p * p + i * p + j] = __float2bfloat16_rn(v);
+        }
+    }
+    __syncthreads();
+    uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * gh * gw + (size_t)py * gw) * Kpad);
+    const uint4* src = reinterpret_cast<const uint4*>(tile);
+    for (int idx = threadIdx.x; idx < gw * Kpad / 8; idx += blockDim.x) dst[idx] = src[idx];
+}
+
 // x[b*T + 0, :] = cls + pos[0, :]
 __global__ void cls_init_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
                                 int T, int D) {
@@ -259,7 +327,23 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
     const float3 istd = make_float3(1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f);
     dim3 g_im(gh, B);
     prof_pre(KC_EMBED, stream, (double)B * 3 * img_h * img_w * (image_dtype ? 1 : 4) + (double)B * P * c.patch_kpad * 2);
-    if (image_dtype == 0)
+    const size_t im_smem = (size_t)gw * c.patch_kpad * sizeof(__nv_bfloat16);
+    if (im_smem <= 200 * 1024 && c.patch_kpad % 8 == 0) {
+        static bool im_configured = false;
+        if (!im_configured) {
+            UCOD_CHECK_CUDA(cudaFuncSetAttribute(im2col_patch_smem_kernel<float>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            UCOD_CHECK_CUDA(cudaFuncSetAttribute(im2col_patch_smem_kernel<uint8_t>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            im_configured = true;
+        }
+        if (image_dtype == 0)
+            im2col_patch_smem_kernel<float><<<g_im, 512, im_smem, stream>>>(static_cast<const float*>(images), w.patches,
+                                                                           B, img_h, img_w, p, c.patch_kpad, mean, istd);
+        else
+            im2col_patch_smem_kernel<uint8_t><<<g_im, 512, im_smem, stream>>>(
+                static_cast<const uint8_t*>(images), w.patches, B, img_h, img_w, p, c.patch_kpad, mean, istd);
+    } else if (image_dtype == 0)
         im2col_patch_kernel<float><<<g_im, 256, 0, stream>>>(static_cast<const float*>(images), w.patches, B, img_h,
                                                              img_w, p, c.patch_kpad, mean, istd);
     else
