@@ -140,7 +140,10 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q0 = blockIdx.x * C::BM;
-    const int b = blockIdx.y / H, h = blockIdx.y - b * H;
+    // (batch, head) pairs are walked from the end: the QKV GEMM finished with the last images (their rows are the
+    // ones still in L2) and the out-projection GEMM starts with the first images' ctx rows
+    const int bh = (int)gridDim.y - 1 - (int)blockIdx.y;
+    const int b = bh / H, h = bh - b * H;
     const int col0 = h * D;
     const int n_tiles = (Tk + C::BN - 1) / C::BN;
 #ifdef UCOD_ATT_TIMELINE

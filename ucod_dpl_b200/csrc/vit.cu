@@ -132,9 +132,11 @@ __global__ void layernorm_bf16_kernel(const float* __restrict__ x, const float* 
                                       const float* __restrict__ bsh, __nv_bfloat16* __restrict__ y, int rows,
                                       float eps) {
     constexpr int V = D / 128;  // float4 per lane
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    // rows are walked from the end: the GEMM that produced x finished with its last rows (still in the 126 MB L2),
+    // and the GEMM that consumes y starts with the first rows, which are then the ones written last
+    const int row = rows - 1 - (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    if (row < 0) return;
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * D);
     float4 v[V];
     float s = 0.f;
