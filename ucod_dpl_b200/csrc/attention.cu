@@ -18,7 +18,8 @@
 // retire every ~74 clk (latency-bound chain), S MMAs every 67 clk.  Tried and rejected (measured slower): a
 // TMA L2 prefetch of K/V, the MMA issuer in the high warp ids, 25 % of the exponentials as an FMA-pipe polynomial
 // (UCOD_ATT_POLY_EVERY), two softmax threads per row (8 softmax warps, shared-memory max/sum exchange), and
-// staggering the two co-resident CTAs by half a tile period (no effect: the exp phases are not MUFU-contended).
+// staggering the two co-resident CTAs by half a tile period, a persistent work-item loop, and a fused two-pipeline
+// CTA with an explicit MUFU-phase token (no gain: see DESIGN.md section 4 for the measurements).
 // TMEM: S fp32 [0,128) | P bf16-packed [128,192) | O fp32 [192,192+D).
 //   S_j  = Q K_j^T                (SS MMA, both operands K-major SW128 tiles)
 //   P_j  = exp2(S_j*c - m_ref)    (written back to TMEM as packed bf16; never touches shared memory)
