@@ -89,3 +89,16 @@ def test_launcher_config_and_work_dir(tmp_path, monkeypatch):
     assert cfg.mode == "eval" and cfg.dataset_cfg.valset_cfg.keep_size is True
     assert cfg.train_cfg.checkpoint == "a.safetensors" and cfg.train_cfg.refiner_path == "r.safetensors"
     assert ev.DATASET == ["CHAMELEON", "TE-CAMO", "TE-COD10K", "NC4K"]
+
+
+def test_async_mask_writer(tmp_path):
+    from ucod_dpl_b200.engine.utils.save_image import AsyncMaskWriter
+    w = AsyncMaskWriter(workers=2)
+    for i in range(5):
+        m = torch.zeros(7, 9, dtype=torch.uint8)
+        m[i, :] = 1
+        w.submit(m, str(tmp_path / "p" / f"im{i}.jpg"))
+    w.close()
+    for i in range(5):
+        arr = np.asarray(Image.open(tmp_path / "p" / f"im{i}.png"))
+        assert arr.shape == (7, 9) and (arr[i] == 255).all() and int((arr > 0).sum()) == 9

@@ -127,14 +127,24 @@ class BaseCODDataset(torch.utils.data.Dataset):
         "images" (uint8 [b,3,S,S] on the GPU, resized like `transform_image` but not yet normalised — the ViT
         kernels fuse that step), "labels" (list of uint8 [H,W] arrays, only `with_labels`)}."""
         idx = list(range(len(self))) if indices is None else list(indices)
-        for s in range(0, len(idx), batch_size):
-            chunk = idx[s:s + batch_size]
+        chunks = [idx[s:s + batch_size] for s in range(0, len(idx), batch_size)]
+
+        def decode(chunk):
             originals = self.decode_many([self.image_paths[i] for i in chunk], "RGB")
-            item = {"index": chunk, "img_path": [str(self.image_paths[i]) for i in chunk], "originals": originals,
-                    "images": self.transform_raw.batch(originals)}
-            if with_labels:
-                item["labels"] = self.decode_many([self.label_paths[i] for i in chunk], "L")
-            yield item
+            labels = self.decode_many([self.label_paths[i] for i in chunk], "L") if with_labels else None
+            return originals, labels
+
+        # the next batch is decoded on host threads while the GPU works on the current one
+        with ThreadPoolExecutor(1) as ahead:
+            pending = ahead.submit(decode, chunks[0]) if chunks else None
+            for n, chunk in enumerate(chunks):
+                originals, labels = pending.result()
+                pending = ahead.submit(decode, chunks[n + 1]) if n + 1 < len(chunks) else None
+                item = {"index": chunk, "img_path": [str(self.image_paths[i]) for i in chunk],
+                        "originals": originals, "images": self.transform_raw.batch(originals)}
+                if with_labels:
+                    item["labels"] = labels
+                yield item
 
     def _prepare_cache(self) -> None:
         """fill the features cache (base_dataset.py:118-139), `extract_batch` images per launch sequence."""

@@ -39,3 +39,24 @@ def save_tensor_binary_mask_as_image(binary_mask: torch.Tensor, save_path: str) 
         _write_png(_to_u8(m), save_path.replace(".jpg", ".png"))
     except Exception as e:  # the reference reports and carries on
         print(f"Error saving mask to {save_path}: {e}")
+
+
+class AsyncMaskWriter:
+    """PNG encoding off the critical path: `submit(mask, path)` copies the mask to the host and hands the encode to a
+    thread pool (zlib releases the GIL); `close()` waits for the files.  Same naming rules as
+    `save_tensor_binary_mask_as_image`."""
+
+    def __init__(self, workers: int = 8):
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(workers)
+        self._pending = []
+
+    def submit(self, binary_mask: torch.Tensor, save_path: str) -> None:
+        host = binary_mask.detach().to("cpu")
+        self._pending.append(self._pool.submit(save_tensor_binary_mask_as_image, host, save_path))
+
+    def close(self) -> None:
+        for f in self._pending:
+            f.result()
+        self._pending.clear()
+        self._pool.shutdown()

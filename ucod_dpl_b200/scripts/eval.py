@@ -29,7 +29,7 @@ from ..engine.config import CfgNode
 from ..engine.runner.loop_CORAL import CoralEvaluator
 from ..engine.runner.loop_UCOD_DPL import LookTwiceEvaluator
 from ..engine.utils.metrics.metric import statistics
-from ..engine.utils.save_image import save_tensor_binary_mask_as_image
+from ..engine.utils.save_image import AsyncMaskWriter
 from ..models.UDLR import SparseRefiner
 from ..models.uscod import baseline
 from .args import parse_train_args
@@ -122,6 +122,7 @@ def evaluate_dataset(cfg, name: str, extractor, model, refiner, args, logger) ->
                                 window_length=int(cfg.model_cfg.get("window_length", 56)),
                                 require_m_patches=bool(cfg.dataset_cfg.valset_cfg.get("require_m_patches", False)))
     stats = statistics(device=device)
+    writer = None if args.no_save else AsyncMaskWriter()
     out_dir = os.path.join(cfg.log_cfg.log_path, "preds", name)
     shard = udist.shard_indices(len(ds))
     for batch in ds.iter_image_batches(args.batch_size, indices=shard, with_labels=True):
@@ -144,8 +145,10 @@ def evaluate_dataset(cfg, name: str, extractor, model, refiner, args, logger) ->
         for i, m in enumerate(masks):
             gt = ds.transform_label(batch["labels"][i])  # ToTensor only (keep_size): [1,h,w] = label / 255
             stats.step(gt, m[None])
-            if not args.no_save:
-                save_tensor_binary_mask_as_image(m, os.path.join(out_dir, os.path.basename(batch["img_path"][i])))
+            if writer is not None:
+                writer.submit(m, os.path.join(out_dir, os.path.basename(batch["img_path"][i])))
+    if writer is not None:
+        writer.close()
     result = stats.get_result()
     table = {k: [round(float(v), 4)] for k, v in result.items()}
     logger.info("%s (%d images): %s", name, len(ds), table)
