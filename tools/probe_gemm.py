@@ -45,5 +45,6 @@ if __name__ == "__main__":
     run(M, 2304, 768, 0)
     run(M, 768, 768, 2)
     run(M, 3072, 768, 1)
+    run(M, 3072, 768, 0)
     run(M, 768, 3072, 2)
     run(64 * 1369, 128, 768, 5)

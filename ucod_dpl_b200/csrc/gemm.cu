@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(192, 1)
                 const int m0 = (tile / n_tiles) * Cfg::BM;
                 const int n0 = (tile % n_tiles) * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    mbar_wait_parked(&bar_empty[stage], phase ^ 1);
                     mbar_arrive_expect_tx(&bar_full[stage], Cfg::STAGE_BYTES);
                     tma_load_2d(sA + stage * Cfg::A_BYTES, &tmap_a, &bar_full[stage], kb * Cfg::BK, m0);
                     tma_load_2d(sB + stage * Cfg::B_BYTES, &tmap_b, &bar_full[stage], kb * Cfg::BK, n0);
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(192, 1)
                 const long long tl0 = clock64();
                 long long tl_full = 0;
 #endif
-                mbar_wait(&bar_tempty[as], aphase ^ 1);  // epilogue has drained this accumulator stage
+                mbar_wait_parked(&bar_tempty[as], aphase ^ 1);  // epilogue has drained this accumulator stage
 #ifdef UCOD_GEMM_TIMELINE
                 const long long tl1 = clock64();
 #endif
@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(192, 1)
 #ifdef UCOD_GEMM_TIMELINE
                     const long long tw = clock64();
 #endif
-                    mbar_wait(&bar_full[stage], phase);
+                    mbar_wait_parked(&bar_full[stage], phase);
 #ifdef UCOD_GEMM_TIMELINE
                     tl_full += clock64() - tw;
 #endif
@@ -391,14 +391,15 @@ struct Gemm2Cfg {
     static constexpr int BM = 128;   // rows per CTA (256 per pair)
     static constexpr int BN = 256;
     static constexpr int BK = 64;
-    static constexpr int STAGES = 6;
+    static constexpr int STAGES = 5;
+    static constexpr int OUT_BUFS = 4;  // staged output boxes in flight: a TMA store queues behind the ring's loads
     static constexpr int A_BYTES = BM * BK * 2;        // 16 KB
     static constexpr int B_BYTES = (BN / 2) * BK * 2;  // 16 KB (this CTA's half of the B tile)
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int OUT_BYTES = BM * 128;
     static constexpr int BIAS_BYTES = BN * 4;
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * OUT_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + OUT_BUFS * OUT_BYTES + BIAS_BYTES + BAR_BYTES + 1024;
     static constexpr int TMEM_COLS = 512;
     static constexpr int THREADS = 192;
 };
@@ -466,7 +467,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * Cfg::A_BYTES;
     uint8_t* sOut = smem + STAGES * Cfg::STAGE_BYTES;
-    float* sBias = reinterpret_cast<float*>(sOut + 2 * Cfg::OUT_BYTES);
+    float* sBias = reinterpret_cast<float*>(sOut + Cfg::OUT_BUFS * Cfg::OUT_BYTES);
     uint64_t* bar_full = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
     uint64_t* bar_empty = bar_full + STAGES;
     uint64_t* bar_tfull = bar_empty + STAGES;
@@ -518,7 +519,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
                 const int m0 = (tile / n_tiles) * 2 * Cfg::BM + (int)rank * Cfg::BM;
                 const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&bar_empty[stage], phase ^ 1);
+                    mbar_wait_parked(&bar_empty[stage], phase ^ 1);
                     const uint32_t full_leader = mapa_u32(smem_u32(&bar_full[stage]), 0);
                     mbar_arrive_expect_tx_cluster(full_leader, Cfg::STAGE_BYTES);
                     tma_load_2d_pair(sA + stage * Cfg::A_BYTES, &tmap_a, full_leader, kb * Cfg::BK, m0);
@@ -537,11 +538,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
             for (int tile = cluster_id; tile < total_tiles; tile += n_clusters, ++it) {
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
-                mbar_wait(&bar_tempty[as], aphase ^ 1);  // both CTAs' epilogues have drained this accumulator stage
+                mbar_wait_parked(&bar_tempty[as], aphase ^ 1);  // both CTAs' epilogues have drained this accumulator stage
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BN;
                 for (int kb = 0; kb < k_blocks; ++kb) {
-                    mbar_wait(&bar_full[stage], phase);
+                    mbar_wait_parked(&bar_full[stage], phase);
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + stage * Cfg::A_BYTES);
                     const uint32_t b_addr = smem_u32(sB + stage * Cfg::B_BYTES);
@@ -575,13 +576,69 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
             mbar_wait(&bar_tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-            if constexpr (epi_uses_tma(MODE)) {
+            if constexpr (epi_uses_tma(MODE) && MODE != EPI_RESID_F32) {
+                // bf16 outputs: 64-column boxes = two 32-column TMEM chunks.  The TMEM load of the next chunk is issued
+                // before the current one is processed, so its latency (long while the tensor pipe is writing the other
+                // accumulator stage) overlaps the bias / GELU / pack work instead of preceding it.
+                constexpr int BOX = epi_box_cols(MODE);
+                constexpr int NSUB = BN / BOX;
+                static_assert(BOX == 64, "two chunks per box");
+                auto process = [&](const uint32_t (&r)[32], const float* bias, uint8_t* srow, int rx, int c) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    add_bias32(bias, v);
+                    if constexpr (MODE == EPI_BIAS_GELU_BF16) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+                    }
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        uint4 t;
+                        t.x = pack_bf16x2(v[8 * g + 0], v[8 * g + 1]);
+                        t.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+                        t.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+                        t.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+                        *reinterpret_cast<uint4*>(srow + (((c * 4 + g) ^ rx) << 4)) = t;
+                    }
+                };
+                uint32_t rA[32], rB[32];
+                tmem_ld32(taddr, rA);
+#pragma unroll 1
+                for (int sidx = 0; sidx < NSUB; ++sidx, ++sub_count) {
+                    uint8_t* stage_out = sOut + (sub_count % Cfg::OUT_BUFS) * Cfg::OUT_BYTES;
+                    if (leader) bulk_wait_read<Cfg::OUT_BUFS - 1>();
+                    epi_bar_sync();
+                    uint8_t* srow = stage_out + row * 128;
+                    const int rx = row & 7;
+                    tmem_wait_ld();
+                    tmem_ld_consume32(rA);
+                    tmem_ld32(taddr + sidx * BOX + 32, rB);
+                    process(rA, sBias + sidx * BOX, srow, rx, 0);
+                    tmem_wait_ld();
+                    tmem_ld_consume32(rB);
+                    if (sidx == NSUB - 1) {  // accumulator stage fully read
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty_leader);
+                    } else {
+                        tmem_ld32(taddr + (sidx + 1) * BOX, rA);
+                    }
+                    process(rB, sBias + sidx * BOX + 32, srow, rx, 1);
+                    fence_proxy_async_smem();
+                    epi_bar_sync();
+                    if (leader) {
+                        tma_store_2d(&tmap_out, stage_out, n0 + sidx * BOX, m0);
+                        bulk_commit();
+                    }
+                }
+            } else if constexpr (epi_uses_tma(MODE)) {
                 constexpr int BOX = epi_box_cols(MODE);
                 constexpr int NSUB = BN / BOX;
 #pragma unroll 1
                 for (int sidx = 0; sidx < NSUB; ++sidx, ++sub_count) {
-                    uint8_t* stage_out = sOut + (sub_count & 1) * Cfg::OUT_BYTES;
-                    if (leader) bulk_wait_read<1>();
+                    uint8_t* stage_out = sOut + (sub_count % Cfg::OUT_BUFS) * Cfg::OUT_BYTES;
+                    if (leader) bulk_wait_read<Cfg::OUT_BUFS - 1>();
                     epi_bar_sync();
                     uint8_t* srow = stage_out + row * 128;
                     const int rx = row & 7;
