@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(192, 1)
 #endif
             // bias tile -> shared (the previous tile's readers are all past their last barrier)
             for (int i = et; i < BN; i += 128) sBias[i] = ep.bias != nullptr ? __ldg(ep.bias + n0 + i) : 0.f;
-            mbar_wait(&bar_tfull[as], aphase);
+            mbar_wait_parked(&bar_tfull[as], aphase);
 #ifdef UCOD_GEMM_TIMELINE
             const long long te1 = clock64();
 #endif
@@ -573,7 +573,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
             const int n0 = (tile % n_tiles) * BN;
             const uint32_t tempty_leader = mapa_u32(smem_u32(&bar_tempty[as]), 0);
             for (int i = et; i < BN; i += 128) sBias[i] = ep.bias != nullptr ? __ldg(ep.bias + n0 + i) : 0.f;
-            mbar_wait(&bar_tfull[as], aphase);
+            mbar_wait_parked(&bar_tfull[as], aphase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
             if constexpr (epi_uses_tma(MODE) && MODE != EPI_RESID_F32) {
