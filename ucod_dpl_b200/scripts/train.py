@@ -145,7 +145,9 @@ def main(argv=None):
     loop = TrainLoop(cfg, trainer, dis_trainer, keys, pls, grid_in, validate=validate if not args.no_val else None,
                      save_checkpoint=save_checkpoint, logger=logger, seed=42, rank=rank, world_size=world)
     best = loop.run()
-    return {"best": best, "losses": loop.losses, "log_path": cfg.log_cfg.log_path}
+    # per-rank fingerprint of the trained weights (data-parallel ranks must agree bit for bit)
+    digest = float(sum(v.double().abs().sum() for v in model.state_dict().values()))
+    return {"best": best, "losses": loop.losses, "log_path": cfg.log_cfg.log_path, "weights_l1": digest}
 
 
 if __name__ == "__main__":
