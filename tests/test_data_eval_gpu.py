@@ -266,3 +266,38 @@ def test_train_launcher_end_to_end(tmp_path, monkeypatch):
                    "--datasets", "TE-X", "--exp_name", "eval0", "--no_save"])
     for k, v in out["best"].items():
         assert abs(res["TE-X"][k] - v) < 1e-9, (k, res["TE-X"][k], v)
+
+
+def test_lr_dataset_patch_caches(tmp_path):
+    """`LRDataset` (second-stage dataset): window / m-patch caches in the reference layout and shapes; a window's keys
+    equal the backbone run on that window of the 3x-resized image."""
+    from ucod_dpl_b200.data.datasets import LRDataset
+    from ucod_dpl_b200.engine.utils.fileio import MetaListPickleIO
+    S = 224
+    data = tmp_path / "data"
+    os.makedirs(data / "TR-L" / "im")
+    shapes = [(300, 340), (260, 333), (300, 340)]
+    for i, (h, w) in enumerate(shapes):
+        Image.fromarray(_img(50 + i, h, w)).save(data / "TR-L" / "im" / f"l{i}.png")
+    fe_cfg = SimpleNamespace(type="dinov2", backbone="facebook/dinov2-base", backbone_type="huggingface")
+    cfg = SimpleNamespace(DATASET="TR-L", image_size=(S, S), require_label=False, require_m_patches=False, use_cache=True)
+    ds = LRDataset(cfg, fe_cfg, "train", str(data), str(tmp_path / "cache"), window_size=3)
+    patch = MetaListPickleIO(base_path=tmp_path / "cache" / "patch_cache" / "dinov2" / "train" / "TR-L")
+    mpatch = MetaListPickleIO(base_path=tmp_path / "cache" / "m_patch_cache" / "dinov2" / "train" / "TR-L")
+    assert patch.mode == "r" and patch.len() == 3 and mpatch.mode == "r" and mpatch.len() == 3   # train mode: m-patches
+    item = ds[1]
+    assert list(item.keys()) == ["pseudo_label", "label_tensor", "features", "img_path", "m_inputs", "h_inputs", "index"]
+    assert tuple(item["h_inputs"].shape) == (9, 768, 16, 16) and tuple(item["m_inputs"].shape) == (4, 768, 36, 36)
+    assert tuple(item["features"].shape) == (768, 16, 16) and item["index"] == [1]
+    # window (row 1, col 2) of image 1: resize to 3S x 3S (Pillow-exact), cut, backbone
+    img = np.asarray(Image.open(ds.image_paths[1]).convert("RGB"))
+    big = ImageTransforms.get_raw_transform((3 * S, 3 * S))(img)
+    win = big[:, S:2 * S, 2 * S:3 * S].contiguous()
+    _, key = ds.feature_extractor(win[None])
+    d = (key[0].cpu() - item["h_inputs"][1 * 3 + 2]).abs()
+    assert d.max().item() < 5e-2 and d.mean().item() < 2e-3, (d.max().item(), d.mean().item())
+    # reference-compatible per-image entry
+    patches, m = ds.get_features(str(ds.image_paths[1]))
+    assert len(patches) == 9 and tuple(patches[0].shape) == (768, 16, 16) and tuple(m.shape) == (1, 4, 768, 36, 36)
+    key_c, h_c, _ = ds.get_features(str(ds.image_paths[1]), crop_center=True)
+    assert tuple(key_c.shape) == (1, 768, 16, 16) and tuple(h_c.shape) == (1, 9, 768, 16, 16)

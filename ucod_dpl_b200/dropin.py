@@ -45,6 +45,7 @@ ALIASES = {
     "data.datasets.cache_manager": "ucod_dpl_b200.data.datasets.cache_manager",
     "data.datasets.base_dataset": "ucod_dpl_b200.data.datasets.base_dataset",
     "data.datasets.uscod_dataset": "ucod_dpl_b200.data.datasets.base_dataset",
+    "data.datasets.lr_dataset": "ucod_dpl_b200.data.datasets.lr_dataset",
     "engine.utils.save_image": "ucod_dpl_b200.engine.utils.save_image",
     "scripts": "ucod_dpl_b200.scripts",
     "scripts.args": "ucod_dpl_b200.scripts.args",
