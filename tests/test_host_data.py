@@ -102,3 +102,25 @@ def test_async_mask_writer(tmp_path):
     for i in range(5):
         arr = np.asarray(Image.open(tmp_path / "p" / f"im{i}.png"))
         assert arr.shape == (7, 9) and (arr[i] == 255).all() and int((arr > 0).sum()) == 9
+
+
+def test_dataloader_factory_on_cached_features(tmp_path, monkeypatch):
+    """`DataLoaderFactory.create_train_loader` over existing caches (no GPU work needed: nothing to extract)."""
+    from ucod_dpl_b200.data.datasets import DataLoaderFactory, init_trainloader
+    from ucod_dpl_b200.engine.config import CfgNode
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.chdir(root)
+    cfg = CfgNode(CfgNode.load_with_base("configs/uscod/UCOD-DPL_dinov2.py")).dataset_cfg
+    _make_set(tmp_path / "data", "TR-F", [f"i{k}" for k in range(5)], with_gt=False)
+    cfg.trainset_cfg.DATASET = "TR-F"
+    cfg.dataset_dir, cfg.cache_dir = str(tmp_path / "data"), str(tmp_path / "cache")
+    cfg.trainloader_cfg.batch_size, cfg.trainloader_cfg.shuffle = 2, False
+    mgr = MultiCacheManager(cfg.cache_dir, "dinov2", "train", "TR-F")
+    mgr.get_features_cache().dump_list([torch.full((768, 2, 2), float(k)) for k in range(5)])
+    mgr.get_pseudo_label_cache().dump_list([torch.full((1, 16, 16), float(k % 2)) for k in range(5)])
+    loader = DataLoaderFactory.create_train_loader(cfg)
+    batches = list(loader)
+    assert len(loader) == 3 and [b["features"].shape[0] for b in batches] == [2, 2, 1]
+    assert batches[1]["features"][0, 0, 0, 0].item() == 2.0 and batches[1]["pseudo_label"].shape == (2, 1, 16, 16)
+    assert batches[0]["label_tensor"] == [None, None] and len(batches[2]["img_path"]) == 1
+    assert len(init_trainloader(cfg)) == 3

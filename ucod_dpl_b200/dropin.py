@@ -46,6 +46,7 @@ ALIASES = {
     "data.datasets.base_dataset": "ucod_dpl_b200.data.datasets.base_dataset",
     "data.datasets.uscod_dataset": "ucod_dpl_b200.data.datasets.base_dataset",
     "data.datasets.lr_dataset": "ucod_dpl_b200.data.datasets.lr_dataset",
+    "data.datasets.dataloader_utils": "ucod_dpl_b200.data.datasets.dataloader_utils",
     "engine.utils.save_image": "ucod_dpl_b200.engine.utils.save_image",
     "scripts": "ucod_dpl_b200.scripts",
     "scripts.args": "ucod_dpl_b200.scripts.args",
