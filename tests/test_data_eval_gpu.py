@@ -301,3 +301,26 @@ def test_lr_dataset_patch_caches(tmp_path):
     assert len(patches) == 9 and tuple(patches[0].shape) == (768, 16, 16) and tuple(m.shape) == (1, 4, 768, 36, 36)
     key_c, h_c, _ = ds.get_features(str(ds.image_paths[1]), crop_center=True)
     assert tuple(key_c.shape) == (1, 768, 16, 16) and tuple(h_c.shape) == (1, 9, 768, 16, 16)
+
+
+def test_pseudo_label_command_line(tmp_path):
+    """`python -m ucod_dpl_b200.generate_pseudo_label` arguments of the reference's `main()`: cache in the reference
+    layout, one `[1,16,16]` {0,1} CPU float tensor per image in sorted path order, equal to the batched generator."""
+    from ucod_dpl_b200 import generate_pseudo_label as gpl
+    from ucod_dpl_b200.engine.utils.fileio import MetaListPickleIO
+    data = tmp_path / "RefCOD"
+    _write_set(data, "TR-A", 5, 0)
+    _write_set(data, "TR-B", 3, 7)
+    n = gpl.main(["--dataset", "TR-A+TR-B", "--image_path", str(data / "{}" / "im"), "--cache_path",
+                  str(tmp_path / "plc"), "--backbone_weights", str(tmp_path / "none")])
+    assert n == 8
+    io = MetaListPickleIO(base_path=tmp_path / "plc" / "TR-A+TR-B")
+    assert io.mode == "r" and io.len() == 8
+    paths = sorted([str(p) for d in ("TR-A", "TR-B") for p in (data / d / "im").iterdir()])
+    gen = gpl.PseudoLabelGenerator(random_vit_state_dict(spec_for("dinov2"), seed=0), "dinov2")
+    tf = ImageTransforms.get_raw_transform((224, 224))
+    want = gen(tf.batch([np.asarray(Image.open(p).convert("RGB")) for p in paths])).cpu()
+    for i in range(8):
+        item = io.read_file(i)
+        assert tuple(item.shape) == (1, 16, 16) and item.dtype == torch.float32 and item.device.type == "cpu"
+        assert torch.equal(item[0], want[i].float())
