@@ -36,7 +36,7 @@ VIT_GFLOP_PER_IMAGE = 279.6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel class from the round's
 # `ncu --set full` capture of this very command at batch 64 (profiles/r01_gemm2_ncu_summary.txt: mean over the 47
 # GEMM launches of a step; per shape 488 / 630 / 616 / 1058 MB, each <= the algorithmic bytes).  None = no capture.
-NCU_TRAFFIC_BYTES = {"gemm": 6.73e8, "attention": None}
+NCU_TRAFFIC_BYTES = {"gemm": 6.73e8, "attention": 5.21e8}  # attention: profiles/r01_attention_final_ncu_summary.txt
 
 
 def _peaks():
