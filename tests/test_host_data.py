@@ -124,3 +124,31 @@ def test_dataloader_factory_on_cached_features(tmp_path, monkeypatch):
     assert batches[1]["features"][0, 0, 0, 0].item() == 2.0 and batches[1]["pseudo_label"].shape == (2, 1, 16, 16)
     assert batches[0]["label_tensor"] == [None, None] and len(batches[2]["img_path"]) == 1
     assert len(init_trainloader(cfg)) == 3
+
+
+def test_checkpoint_discovery(tmp_path):
+    """`find_latest_checkpoint` / `resolve_checkpoint`: newest `*.pth|*.pt|*.safetensors` entry of any run directory's
+    `ckp` (or `refiner_ckp`) folder; a directory entry (what `accelerator.save_model` writes) resolves to its
+    `model.safetensors` (reference: runner.py:165-241)."""
+    import time
+    from types import SimpleNamespace as NS
+
+    from ucod_dpl_b200.scripts.eval import find_latest_checkpoint, resolve_checkpoint
+    work = tmp_path / "work" / "uscod" / "cfg"
+    cfg = NS(work_dir=str(work), log_cfg=NS(log_path=str(work / "eval_run")))
+    os.makedirs(work / "eval_run")
+    assert find_latest_checkpoint(cfg, "ckp") is None
+    for k, name in enumerate(["epoch5.pth", "epoch10.pth"]):
+        d = work / "train_run" / "ckp" / name
+        os.makedirs(d)
+        (d / "model.safetensors").write_bytes(b"x")
+        t = time.time() - 100 + 10 * k
+        os.utime(d, (t, t))
+    (work / "train_run" / "ckp" / "notes.txt").write_text("ignored")
+    os.makedirs(work / "train_run" / "refiner_ckp")
+    (work / "train_run" / "refiner_ckp" / "epoch8.pth").write_bytes(b"y")
+    found = find_latest_checkpoint(cfg, "ckp")
+    assert found.endswith(os.path.join("ckp", "epoch10.pth"))
+    assert resolve_checkpoint(found).endswith(os.path.join("epoch10.pth", "model.safetensors"))
+    r = find_latest_checkpoint(cfg, "refiner_ckp")
+    assert r.endswith("epoch8.pth") and resolve_checkpoint(r) == r
