@@ -10,7 +10,7 @@
 //
 // CTA = 256 threads = two warpgroups:
 //   WG0: warp 0 = TMA producer (Q once; K_j / V_j double buffered, separately released), warp 1 = single-thread
-//        MMA issuer (+ TMEM allocator); registers trimmed with setmaxnreg.dec (80: no spills in the issue loop).
+//        S issuer (+ TMEM allocator), warp 2 = single-thread P V issuer; registers trimmed with setmaxnreg.dec (80).
 //   WG1: 4 softmax warps, one thread per query row (= TMEM lane), registers raised with setmaxnreg.inc (176) so
 //        the whole 128-wide S row lives in registers (S is read from TMEM exactly once).
 // Measured on B200 (tools/att_timeline.py, tools/ubench/mma_rate.cu): the softmax warps are busy ~85 % of a tile
@@ -39,8 +39,8 @@
 namespace ucod {
 
 #ifdef UCOD_ATT_TIMELINE
-__device__ long long g_att_tl[3][16][8];
-#define TL(role, j, slot) do { if (tl_on && (j) < 16) g_att_tl[role][j][slot] = clock64() - tl_t0; } while (0)
+__device__ long long g_att_tl[6][16][8];  // roles: 0 producer, 1 issuer, 2..5 softmax warps 4..7
+#define TL(role, j, slot) do { if (tl_on && (j) < 16) g_att_tl[(role) == 2 ? 2 + (warp & 3) : (role)][j][slot] = clock64() - tl_t0; } while (0)
 #else
 #define TL(role, j, slot) do {} while (0)
 #endif
@@ -95,17 +95,71 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // exp2 on the FMA pipe (Cody-Waite split + degree-3 minimax of 2^f on [-0.5, 0.5], relative error 7.5e-5 — far
 // below the bf16 resolution of P).  Used for a fixed fraction of the probabilities so that the 16-lane MUFU unit,
 // which bounds the softmax phase at head_dim 64, is not the only exponential engine.  x <= 8 on this path.
-__device__ __forceinline__ float ex2_poly(float x) {
-    x = fmaxf(x, -126.f);
-    const float t = x + 12582912.f;                 // 1.5 * 2^23: round-to-nearest integer lands in the mantissa
-    const float f = x - (t - 12582912.f);           // in [-0.5, 0.5]
-    float p = fmaf(0.05517121031880379f, f, 0.24261027574539185f);
-    p = fmaf(p, f, 0.6932609677314758f);
-    p = fmaf(p, f, 0.9999281167984009f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+// Measured pipe rates per SM sub-partition (tools/ubench/pipe_rate.cu): MUFU.EX2 8 clk per warp instruction,
+// FFMA / FADD 1, FFMA2 / FADD2 2 (no arithmetic gain, half the issue slots), F2FP pack 2, FMNMX 1, FMNMX3 2.
+// One polynomial exponential costs 6 clk of FMA pipe (3 adds + 3 FMAs) against 8 clk of MUFU, so the two engines
+// balance at ~3/8 of the elements on the FMA pipe (tools/ubench/softmax_rate.cu: 1218 -> 1005 clk per tile per SM).
+__device__ __forceinline__ uint64_t pack2f(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
-#ifndef UCOD_ATT_POLY_EVERY
-#define UCOD_ATT_POLY_EVERY 0  // every n-th exponential goes to the FMA pipe (0 = all on MUFU; measured: 4 is 6 % slower)
+__device__ __forceinline__ void unpack2f(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// 2^x for a pair of values, packed f32x2 arithmetic
+__device__ __forceinline__ void ex2_poly2(float x0, float x1, float& p0, float& p1) {
+    x0 = fmaxf(x0, -126.f);
+    x1 = fmaxf(x1, -126.f);
+    const uint64_t x = pack2f(x0, x1);
+    const uint64_t t = fadd2(x, pack2f(12582912.f, 12582912.f));  // 1.5 * 2^23: round-to-nearest integer in the mantissa
+    const uint64_t r = fadd2(t, pack2f(-12582912.f, -12582912.f));
+    float r0, r1;
+    unpack2f(r, r0, r1);
+    const uint64_t f = fadd2(x, pack2f(-r0, -r1));  // in [-0.5, 0.5]
+    uint64_t p = ffma2(pack2f(0.05517121031880379f, 0.05517121031880379f), f,
+                       pack2f(0.24261027574539185f, 0.24261027574539185f));
+    p = ffma2(p, f, pack2f(0.6932609677314758f, 0.6932609677314758f));
+    p = ffma2(p, f, pack2f(0.9999281167984009f, 0.9999281167984009f));
+    float q0, q1, t0, t1;
+    unpack2f(p, q0, q1);
+    unpack2f(t, t0, t1);
+    p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+    p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
+#ifndef UCOD_ATT_POLY8
+#define UCOD_ATT_POLY8 3  // pairs out of every 8 (16 elements) whose exponentials go to the FMA pipe (0 = all on MUFU)
+#endif
+// Non-blocking phase test: issued early, its result is consumed later, so the ~100 clk barrier round trip overlaps
+// arithmetic instead of sitting between two phases of a softmax warp's tile.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+#ifndef UCOD_ATT_EARLY
+#define UCOD_ATT_EARLY 1  // early (hidden) barrier polls in the softmax warps
+#endif
+#ifndef UCOD_ATT_MAXCH
+#define UCOD_ATT_MAXCH 8  // independent chains of the row maximum
 #endif
 template <int N>
 __device__ __forceinline__ void reg_dec() {
@@ -219,15 +273,24 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                                 j * C::BN, bkv);
             }
         } else if (warp == 1 && lane == 0) {
-            // ===================== MMA issuer =====================
+            // ===================== S = Q K^T issuer =====================
+            // Two issuing lanes (this one and the P V issuer in warp 2): one tcgen05.mma takes 50-60 clk to issue and
+            // blocks behind the co-resident CTA's MMAs, so a single lane issuing S_{j+1} and then P_j V_j spent
+            // ~1500 clk per tile in issue plus four barrier wake-ups — as long as the softmax warps' own tile period
+            // (timeline, round 2).  S and P V only share read-only operands, so they need no mutual ordering.
             constexpr uint32_t idesc_s = umma_idesc_bf16(C::BM, C::BN);
-            constexpr uint32_t idesc_o = umma_idesc_bf16(C::BM, D) | (1u << 16);  // B operand MN-major
             const uint32_t q_addr = smem_u32(sQ);
             // the last tile only computes the 32-column chunks that hold valid keys (S with N = tail_cols, P V with
             // tail_cols / 16 K-steps); TMA zero-fills the key rows past Tk inside the last chunk
             const int tail_cols = ((Tk - (n_tiles - 1) * C::BN + 31) / 32) * 32;
             const uint32_t idesc_s_tail = umma_idesc_bf16(C::BM, tail_cols);
-            auto issue_s = [&](int j) {
+            mbar_wait_parked(bar_q, 0);
+            for (int j = 0; j < n_tiles; ++j) {
+                mbar_wait_parked(&bar_kfull[j & 1], (j >> 1) & 1);
+                TL(1, j, 0);
+                if (j > 0) mbar_wait_parked(bar_sfree, (j - 1) & 1);  // S_{j-1} is in the softmax warps' registers
+                TL(1, j, 1);
+                tc_fence_after();
                 const uint32_t k_addr = smem_u32(sK + (j & 1) * C::SK_BYTES);
                 const uint32_t idesc = j == n_tiles - 1 ? idesc_s_tail : idesc_s;
 #pragma unroll
@@ -239,22 +302,14 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
                                      (kb | k) != 0);
                 umma_commit(&bar_kempty[j & 1]);
                 umma_commit(bar_s);
-            };
-            mbar_wait_parked(bar_q, 0);
-            mbar_wait_parked(&bar_kfull[0], 0);
-            tc_fence_after();
-            issue_s(0);
+                TL(1, j, 2);
+            }
+        } else if (warp == 2 && lane == 0) {
+            // ===================== O += P V issuer =====================
+            constexpr uint32_t idesc_o = umma_idesc_bf16(C::BM, D) | (1u << 16);  // B operand MN-major
+            const int tail_cols = ((Tk - (n_tiles - 1) * C::BN + 31) / 32) * 32;
             for (int j = 0; j < n_tiles; ++j) {
                 const int st = j & 1;
-                if (j + 1 < n_tiles) {
-                    mbar_wait_parked(&bar_kfull[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                    TL(1, j, 0);
-                    mbar_wait_parked(bar_sfree, j & 1);  // S_j is in the softmax warps' registers
-                    TL(1, j, 1);
-                    tc_fence_after();
-                    issue_s(j + 1);
-                    TL(1, j, 2);
-                }
                 mbar_wait_parked(&bar_vfull[st], (j >> 1) & 1);
                 TL(1, j, 3);
                 mbar_wait_parked(bar_p, j & 1);  // P_j published
@@ -279,10 +334,11 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
         const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
         const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
         float m_ref = 0.f, l_run = 0.f;
+        bool s_ready = false;  // S_j already seen complete by the early poll of the previous tile
 
         for (int j = 0; j < n_tiles - 1; ++j) {
             TL(2, j, 0);
-            mbar_wait(bar_s, j & 1);
+            if (!s_ready) mbar_wait(bar_s, j & 1);
             TL(2, j, 1);
             tc_fence_after();
             uint32_t u[128];
@@ -292,17 +348,22 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             TL(2, j, 2);
             tc_fence_before();
             mbar_arrive(bar_sfree);
-            // ---- row maximum (4 independent chains) ----
-            float mx[4];
+            // ---- row maximum (UCOD_ATT_MAXCH independent chains of 3-input maxima) ----
+            constexpr int MC = UCOD_ATT_MAXCH, ML = 128 / MC;
+            float mx[MC];
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                mx[c] = __uint_as_float(u[32 * c]);
+            for (int c = 0; c < MC; ++c) {
+                mx[c] = __uint_as_float(u[ML * c]);
 #pragma unroll
-                for (int i = 1; i < 32; i += 2)
-                    mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(u[32 * c + i]),
-                                               __uint_as_float(u[32 * c + (i + 1 < 32 ? i + 1 : i)])));
+                for (int i = 1; i < ML; i += 2)
+                    mx[c] = fmaxf(mx[c], fmaxf(__uint_as_float(u[ML * c + i]),
+                                               __uint_as_float(u[ML * c + (i + 1 < ML ? i + 1 : i)])));
             }
-            const float ms = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3])) * scale_log2e;
+#pragma unroll
+            for (int w = MC / 2; w > 0; w >>= 1)
+#pragma unroll
+                for (int c = 0; c < w; ++c) mx[c] = fmaxf(mx[c], mx[c + w]);
+            const float ms = mx[0] * scale_log2e;
             float alpha = 1.f;
             bool grow = false;
             if (j == 0) {
@@ -315,23 +376,32 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             TL(2, j, 3);
             // ---- probabilities -> packed bf16 (registers) ----
             const float neg_m = -m_ref;
-            float ls[4] = {0.f, 0.f, 0.f, 0.f};
+            uint64_t ls[4] = {0ull, 0ull, 0ull, 0ull};
             uint32_t pk[64];
+            const uint64_t sc2 = pack2f(scale_log2e, scale_log2e), nm2 = pack2f(neg_m, neg_m);
+            bool pv_done = (j == 0);
 #pragma unroll
             for (int i = 0; i < 64; ++i) {
-                const float x0 = fmaf(__uint_as_float(u[2 * i]), scale_log2e, neg_m);
-                const float x1 = fmaf(__uint_as_float(u[2 * i + 1]), scale_log2e, neg_m);
-                const float p0 = ex2_approx(x0);
-                // every UCOD_ATT_POLY_EVERY-th exponential (the odd element of every (EVERY/2)-th pair) on the FMA pipe
-                const float p1 = (UCOD_ATT_POLY_EVERY >= 2 && (i % (UCOD_ATT_POLY_EVERY / 2)) == 0) ? ex2_poly(x1)
-                                                                                                   : ex2_approx(x1);
-                ls[i & 3] += p0 + p1;
+                if (UCOD_ATT_EARLY && i == 40 && j > 0) pv_done = mbar_test(bar_pv, (j - 1) & 1);
+                const uint64_t x = ffma2(pack2f(__uint_as_float(u[2 * i]), __uint_as_float(u[2 * i + 1])), sc2, nm2);
+                float x0, x1, p0, p1;
+                unpack2f(x, x0, x1);
+                if ((i & 7) < UCOD_ATT_POLY8) {
+                    ex2_poly2(x0, x1, p0, p1);
+                } else {
+                    p0 = ex2_approx(x0);
+                    p1 = ex2_approx(x1);
+                }
+                ls[i & 3] = fadd2(ls[i & 3], pack2f(p0, p1));
                 pk[i] = pack_bf16x2(p0, p1);
             }
-            l_run = l_run * alpha + (ls[0] + ls[1]) + (ls[2] + ls[3]);
+            float ls_lo, ls_hi;
+            unpack2f(fadd2(fadd2(ls[0], ls[1]), fadd2(ls[2], ls[3])), ls_lo, ls_hi);
+            l_run = l_run * alpha + (ls_lo + ls_hi);
+            TL(2, j, 7);
             // ---- the previous P V must have retired before P is overwritten / O is rescaled ----
             if (j > 0) {
-                mbar_wait(bar_pv, (j - 1) & 1);
+                if (!pv_done) mbar_wait(bar_pv, (j - 1) & 1);
                 TL(2, j, 4);
                 tc_fence_after();
                 if (__any_sync(0xffffffffu, grow)) {
@@ -349,6 +419,8 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             tmem_st32(tmem_p + lane_off, reinterpret_cast<uint32_t(&)[32]>(pk[0]));
             tmem_st32(tmem_p + lane_off + 32, reinterpret_cast<uint32_t(&)[32]>(pk[32]));
             TL(2, j, 5);
+            // S_{j+1} was issued when this tile's scores had been pulled into registers: poll it while the P store drains
+            if (UCOD_ATT_EARLY) s_ready = mbar_test(bar_s, (j + 1) & 1);
             tmem_wait_st();
             tc_fence_before();
             mbar_arrive(bar_p);
@@ -361,7 +433,7 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
             const int j = n_tiles - 1;
             const int valid = Tk - j * C::BN;  // keys valid in this tile (>= 1)
             const int nch = (valid + 31) >> 5;
-            mbar_wait(bar_s, j & 1);
+            if (!s_ready) mbar_wait(bar_s, j & 1);
             tc_fence_after();
             uint32_t u[128];
 #pragma unroll
@@ -610,7 +682,7 @@ int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
 
 #ifdef UCOD_ATT_TIMELINE
 extern "C" int ucod_debug_att_timeline(long long* out) {
-    return (int)cudaMemcpyFromSymbol(out, g_att_tl, sizeof(long long) * 3 * 16 * 8);
+    return (int)cudaMemcpyFromSymbol(out, g_att_tl, sizeof(long long) * 6 * 16 * 8);
 }
 #endif
 

@@ -130,8 +130,9 @@ def evaluate_dataset(cfg, name: str, extractor, model, refiner, args, logger) ->
         if refiner is None:
             canvas, sizes = pack_padded(batch["originals"], device)
             final, _ = looker(batch["images"], originals=canvas, layout="HWC", orig_sizes=sizes)
-            # loop_UCOD_DPL.py:310-311: bilinear to the label size, > 0.5
-            masks = [ops.upsample_bilinear(final[i], label_sizes[i], binarize=True) for i in range(len(label_sizes))]
+            # loop_UCOD_DPL.py:315-317: `final` is a [0,1] mask (pasted second looks / 255); bilinear to the label
+            # size, then `> 0.5` on the interpolated value itself (binarize = 3; mode 1 would threshold sigmoid(.))
+            masks = [ops.upsample_bilinear(final[i], label_sizes[i], binarize=3) for i in range(len(label_sizes))]
         else:
             groups: dict = {}
             for i, im in enumerate(batch["originals"]):  # CORAL windows need equal-size originals per launch
