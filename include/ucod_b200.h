@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UCOD_B200_ABI_VERSION 3
+#define UCOD_B200_ABI_VERSION 4
 
 /* Last error message of the calling thread ("" if none). */
 const char* ucod_last_error(void);
@@ -103,6 +103,15 @@ int ucod_vit_keys(void* handle, const void* images, int image_dtype, int batch, 
                   const float* pos_emb, void* workspace, uint64_t workspace_bytes, float* keys_f32, void* keys_bf16,
                   float* cls_attn, int keep_cls, void* stream);
 
+/* Same call with a DEVICE-side image count: `batch` is the capacity the buffers are sized for, *batch_dev (device
+ * int32, <= batch) the number of leading images that are processed; every kernel of the pass reads it on the device,
+ * so a pass whose size was decided by an earlier kernel (the second Look-Twice pass over the crops,
+ * engine/runner/loop_UCOD_DPL.py:331-346) needs no host synchronisation.  Rows of images >= *batch_dev are left
+ * untouched or undefined. */
+int ucod_vit_keys_dyn(void* handle, const void* images, int image_dtype, int batch, const int32_t* batch_dev, int img_h,
+                      int img_w, const float* pos_emb, void* workspace, uint64_t workspace_bytes, float* keys_f32,
+                      void* keys_bf16, float* cls_attn, int keep_cls, void* stream);
+
 /* ---- Dual-Branch Adversarial decoder ------------------------------------------------------------
  * Replaces `RevDecoder.forward` (models/modules/DBA.py:31-59) incl. the preceding bilinear feature upsample
  * of engine/runner/loop_UCOD_DPL.py:153,236,305 (commuted past the 1x1 conv) and `calc_orthogonal_loss`
@@ -115,6 +124,12 @@ int ucod_decoder_fwd(const void* keys_bf16, int batch, int dim, int gin_h, int g
                      const void* w_dec, const float* b_dec, const float* emb, const float* w_fg, const float* b_fg,
                      const float* w_bg, const float* b_bg, float* fg, float* bg, float* ortho, void* workspace,
                      uint64_t workspace_bytes, void* stream);
+
+/* Eval-only variant with a device-side image count (see ucod_vit_keys_dyn); no orthogonality loss. */
+int ucod_decoder_fwd_dyn(const void* keys_bf16, int batch, const int32_t* batch_dev, int dim, int gin_h, int gin_w,
+                         int out_h, int out_w, const void* w_dec, const float* b_dec, const float* emb,
+                         const float* w_fg, const float* b_fg, const float* w_bg, const float* b_bg, float* fg,
+                         float* bg, void* workspace, uint64_t workspace_bytes, void* stream);
 
 /* [batch, channels, pixels] fp32 with element strides (sb, sc, sp) -> token-major bf16 [batch, pixels, channels].
  * Lets `baseline.forward` accept the reference's NCHW feature tensors (models/uscod.py:16-22). */
@@ -178,6 +193,34 @@ uint64_t ucod_paste_bicubic_workspace_bytes(int njobs, int g_h, int out_cap);
 int ucod_paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const int32_t* jobs, int max_rank,
                        uint8_t* mask, int n_images, int s_h, int s_w, int out_cap, void* workspace,
                        uint64_t workspace_bytes, int32_t* err_flag, void* stream);
+/* Look-Twice job tables built ON THE DEVICE from ucod_lt_boxes output — the host loop of
+ * engine/runner/loop_UCOD_DPL.py:331-342 and `resize_bbox` (:387-397, CPython float arithmetic + int() truncation in
+ * exact fp64).  Image b contributes max(nbox[b], 0) jobs, image-major, rank = position in its sorted box list.
+ * orig_sizes: device int32 [batch,2] (h, w) of every original image, or NULL when all are src_h x src_w.
+ * crop_jobs int32 [capacity,5] (image, x, y, w, h in original pixels); paste_jobs int32 [capacity,6]
+ * (image, x, y, w, h, rank in mask pixels); counts int32[4]: [0] jobs written (<= capacity), [1] status bits
+ * (1: an image's box maths raised ValueError, 2: more than `capacity` jobs — the rest dropped, 4: a box or crop with
+ * w or h <= 0, where PIL raises in the reference), [2] jobs requested; chunk_counts int32 [ceil(capacity / chunk)]:
+ * valid jobs of every `chunk`-sized slice, the device-side counts of the *_dyn calls that process the slices. */
+int ucod_lt_build_jobs(const int32_t* boxes, const int32_t* nbox, int batch, int s_h, int s_w, int src_h, int src_w,
+                       const int32_t* orig_sizes, int32_t* crop_jobs, int32_t* paste_jobs, int capacity,
+                       int32_t* counts, int chunk, int32_t* chunk_counts, void* stream);
+/* ucod_roi_crop_resize for a job slice whose length lives on the device (*njobs_dev <= capacity).  Any crop of the
+ * src_h x src_w sources is supported (no tap-count limit); err_flag as above. */
+uint64_t ucod_roi_crop_resize_dyn_workspace_bytes(int capacity, int src_h, int src_w, int out_h, int out_w);
+int ucod_roi_crop_resize_dyn(const uint8_t* images, int n_images, int src_h, int src_w, int64_t image_stride,
+                             int64_t channel_stride, int64_t row_stride, int64_t pixel_stride, const int32_t* jobs,
+                             int capacity, const int32_t* njobs_dev, uint8_t* out, int out_h, int out_w,
+                             void* workspace, uint64_t workspace_bytes, int32_t* err_flag, void* stream);
+/* ucod_paste_bicubic for the slice [first_index, first_index + *njobs_dev) of an image-major, rank-ascending paste
+ * table of min(n_all, *n_all_dev) entries.  A pixel is written by the LAST job of its image that covers it (what the
+ * reference's sequential pastes leave behind), so slices can be pasted in one launch each and in any order.
+ * Jobs wider or taller than out_cap set err_flag bit 1 and are skipped. */
+uint64_t ucod_paste_bicubic_dyn_workspace_bytes(int capacity, int g_h, int g_w, int out_cap);
+int ucod_paste_bicubic_dyn(const float* logits, int capacity, const int32_t* njobs_dev, int g_h, int g_w,
+                           const int32_t* all_jobs, int first_index, int n_all, const int32_t* n_all_dev,
+                           uint8_t* mask, int n_images, int s_h, int s_w, int out_cap, void* workspace,
+                           uint64_t workspace_bytes, int32_t* err_flag, void* stream);
 /* out[i] = in[i] ? mul : 0  ({0,1} mask -> {0,255} canvas, loop_UCOD_DPL.py:330). */
 int ucod_mask_scale_u8(const uint8_t* in, uint8_t* out, uint64_t n, int mul, void* stream);
 

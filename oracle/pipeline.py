@@ -64,3 +64,37 @@ def coral_eval(vit_sd, spec, dec_sd, ref_sd, image_u8_hwc, image_size: int, labe
     if crop:
         out = oc.center_pad(out)
     return {"coarse": coarse, "crop": crop, "refined": out, "mask": oc.process_preds(out, label_size), "opt": opt}
+
+
+@torch.no_grad()
+def look_twice_eval(vit_sd, spec, dec_sd, images_u8: torch.Tensor, image_size, feature_size: int = 68,
+                    look_twice_th: float = 0.15, expand_type: str = "dynamic", first_logits=None, label_size=None):
+    """First-stage eval WITH Look-Twice for a batch whose originals are the network-size images themselves
+    (engine/runner/loop_UCOD_DPL.py:297-317, per image like the reference): first look -> process_preds -> second look
+    over the boxes -> final bilinear resize to `label_size` -> `> 0.5`.
+    first_logits (optional [B,1,fs,fs]): replaces the first-look prediction as process_preds' input — the SURVEY 8(d)
+    "LT" benchmark plants two small objects per image this way; the first look is still computed.
+    Returns dict(final uint8 [B,h,w], first uint8 [B,S,S], bboxes list)."""
+    import torch.nn.functional as F
+
+    from . import looktwice as olt
+
+    S = tuple(image_size)
+    label_size = S if label_size is None else tuple(label_size)
+
+    def seg(x):  # backbone + student decoder on the raw token grid (:343-345)
+        keys = ovit.keys_to_map(ovit.vit_forward(vit_sd, spec, x)["key_tokens"])
+        return odec.baseline_forward(dec_sd, keys, want_ortho=False)[0]
+
+    finals, firsts, boxes = [], [], []
+    for i in range(images_u8.shape[0]):
+        first = first_stage_eval(vit_sd, spec, dec_sd, images_u8[i:i + 1], S, feature_size)
+        logits = first["logits"] if first_logits is None else first_logits[i:i + 1]
+        up, bb = olt.process_preds(logits, S, look_twice_th, expand_type)
+        firsts.append(up.to(torch.uint8))
+        boxes.append(bb)
+        if bb is not None:
+            up = olt.look_twice(images_u8[i].permute(1, 2, 0).contiguous().numpy(), bb, up, S, seg)
+        fin = F.interpolate(up.reshape(1, 1, *S).float(), size=label_size, mode="bilinear", align_corners=False)
+        finals.append((fin[0, 0] > 0.5).to(torch.uint8))
+    return {"final": torch.stack(finals), "first": torch.cat(firsts), "bboxes": boxes}

@@ -179,3 +179,149 @@ def test_look_twice_end_to_end_small():
     for (x, y, w, h) in bboxes:
         outside[y:y + h, x:x + w] = False
     assert torch.equal(new.cpu()[0][outside], old[0].float()[outside])
+
+
+# ---- device-resident control flow (round 2): job tables, device-side counts, order-independent paste ----
+def _tiny_evaluator(S=224, **kw):
+    from types import SimpleNamespace
+    from pathlib import Path
+    from safetensors.torch import load_file
+    from ucod_dpl_b200.engine.runner.loop_UCOD_DPL import LookTwiceEvaluator
+    from ucod_dpl_b200.models.uscod import baseline
+    from ucod_dpl_b200.synth import random_vit_state_dict
+    from ucod_dpl_b200.vit import VitKeyExtractor, spec_for
+    sd = random_vit_state_dict(spec_for("dinov2"), seed=0)
+    dec_sd = load_file(str(Path(__file__).resolve().parents[1] / "weights" / "UCOD_DPL_dinov2.safetensors"))
+    model = baseline(SimpleNamespace(dim=768)).cuda().eval()
+    model.load_state_dict(dec_sd)
+    return LookTwiceEvaluator(VitKeyExtractor(sd, spec_for("dinov2")), model, (S, S), 68, 0.15, "dynamic", **kw)
+
+
+def test_build_jobs_matches_host_loop():
+    """`ucod_lt_build_jobs` == the reference's host loop (`resize_bbox` in CPython floats, image-major, rank order),
+    including ragged original sizes, empty / None images, the capacity clamp and the per-chunk counts."""
+    from ucod_dpl_b200.engine.runner.loop_UCOD_DPL import resize_bbox
+    S = 518
+    rng = np.random.default_rng(5)
+    lg = torch.cat([blob_logits(int(rng.integers(0, 5)), seed=100 + t, size=(0.03, 0.1)) for t in range(12)], 0)
+    mask = ops.upsample_bilinear(lg[:, 0].cuda(), (S, S), binarize=True)
+    boxes, nbox, _, _ = ops.lt_boxes(mask, 0.15, "dynamic")
+    sizes = torch.tensor([[int(rng.integers(300, 1400)), int(rng.integers(300, 1400))] for _ in range(12)])
+    for cap, chunk in ((64, 16), (7, 4)):
+        crop, paste, counts, chunks = ops.lt_build_jobs(boxes, nbox, (S, S), None, sizes, capacity=cap, chunk=chunk)
+        want_c, want_p = [], []
+        for b, n in enumerate(nbox.cpu().tolist()):
+            for r in range(max(n, 0)):
+                bb = boxes[b, r].cpu().tolist()
+                H0, W0 = sizes[b].tolist()
+                want_c.append([b] + resize_bbox(bb, S, S, W0, H0))
+                want_p.append([b] + bb + [r])
+        kept, status, wanted, _ = counts.cpu().tolist()
+        assert wanted == len(want_c) and kept == min(cap, wanted) and bool(status & 2) == (wanted > cap)
+        assert crop[:kept].cpu().tolist() == want_c[:kept]
+        assert paste[:kept].cpu().tolist() == want_p[:kept]
+        assert chunks.cpu().tolist() == [max(0, min(chunk, kept - c * chunk)) for c in range((cap + chunk - 1) // chunk)]
+        assert wanted > 7  # the clamp case is exercised
+
+
+def test_vit_and_decoder_device_count():
+    """`count_dev` variants: the first n images equal the plain call bit for bit, for n = 0 .. capacity."""
+    from ucod_dpl_b200.synth import synth_batch_u8
+    ev = _tiny_evaluator()
+    imgs = synth_batch_u8(3, 5, 224, 224).cuda()
+    _, k_ref, _ = ev.extractor.keys(imgs, want_f32=False, want_bf16=True)
+    fg_ref, _, _ = ev.model.decoder.forward_tokens(k_ref, (16, 16), (16, 16), want_bg=False)
+    for n in (0, 1, 3, 5):
+        cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+        _, k, _ = ev.extractor.keys(imgs, want_f32=False, want_bf16=True, count_dev=cnt)
+        fg, _, _ = ev.model.decoder.forward_tokens(k, (16, 16), (16, 16), want_bg=False, count_dev=cnt)
+        assert torch.equal(k[:n], k_ref[:n]), n
+        # the decoder's per-channel sum of squares is accumulated with float atomics: equal up to summation order
+        assert torch.allclose(fg[:n], fg_ref[:n], rtol=1e-5, atol=1e-5), n
+
+
+def test_paste_order_independent_overlaps():
+    """`paste_bicubic_dyn` (one launch per chunk, later boxes win per pixel) == sequential PIL pastes, with boxes that
+    overlap each other, stick out of the mask and straddle a chunk boundary."""
+    S, g = 296, 37
+    rng = np.random.default_rng(11)
+    base = (rng.random((3, S, S)) < 0.3).astype(np.uint8)
+    geo = [(0, 10, 20, 200, 150), (0, 100, 60, 137, 137), (0, 150, 100, 100, 160), (1, -20, 200, 150, 120),
+           (1, 0, 0, 296, 296), (1, 40, 40, 3, 2), (2, 250, 250, 12, 9), (2, 255, 245, 60, 70), (2, 200, 230, 90, 30)]
+    jobs, rank = [], {}
+    for (im, x, y, w, h) in geo:
+        jobs.append([im, x, y, w, h, rank.get(im, 0)])
+        rank[im] = rank.get(im, 0) + 1
+    lg = rng.normal(0, 1, (len(geo), g, g)).astype(np.float32)
+    want = base * 255
+    for (im, x, y, w, h, r), l in zip(jobs, lg):
+        pred = ((torch.sigmoid(torch.from_numpy(l)) > 0.5).float() * 255).to(torch.uint8).numpy()
+        opr.paste_u8(want[im], opr.resize_u8(pred, w, h, "bicubic"), x, y)
+    cap, chunk = 12, 4
+    table = torch.zeros(cap, 6, dtype=torch.int32)
+    table[:len(jobs)] = torch.tensor(jobs, dtype=torch.int32)
+    table = table.cuda()
+    n_all = torch.tensor([len(jobs)], dtype=torch.int32, device="cuda")
+    canvas = ops.mask_scale_u8(torch.from_numpy(base).cuda(), 255)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for c in reversed(range(cap // chunk)):            # chunk order must not matter
+        n_c = torch.tensor([max(0, min(chunk, len(jobs) - c * chunk))], dtype=torch.int32, device="cuda")
+        logits = torch.zeros(chunk, g, g)
+        logits[:int(n_c)] = torch.from_numpy(lg[c * chunk:c * chunk + int(n_c)])
+        ops.paste_bicubic_dyn(logits.cuda(), table, c * chunk, n_c, n_all, canvas, 444, err=err)
+    assert int(err.item()) == 0
+    assert np.array_equal(canvas.cpu().numpy(), want)
+
+
+def test_crop_resize_dyn_equals_static_and_large_downscale():
+    """device-count crop/resize == the static call on the valid jobs; a > 19x down-scale (beyond the static tap table)
+    is PIL-exact on the dynamic path and raises on the static one."""
+    from ucod_dpl_b200.synth import synth_batch_u8
+    imgs = synth_batch_u8(1, 2, 600, 700).cuda()
+    jobs = torch.tensor([[0, 10, 20, 300, 200], [1, -30, 50, 400, 590], [1, 100, 100, 64, 64], [0, 0, 0, 700, 600]],
+                        dtype=torch.int32).cuda()
+    ref = ops.roi_crop_resize(imgs, jobs, (224, 224))
+    table = torch.zeros(6, 5, dtype=torch.int32, device="cuda")
+    table[:4] = jobs
+    for n in (4, 2, 0):
+        got = ops.roi_crop_resize_dyn(imgs, table, torch.tensor([n], dtype=torch.int32, device="cuda"), (224, 224))
+        assert torch.equal(got[:n], ref[:n])
+    big = synth_batch_u8(2, 1, 1300, 900).cuda()
+    job = torch.tensor([[0, 0, 0, 900, 1300]], dtype=torch.int32).cuda()
+    got = ops.roi_crop_resize_dyn(big, job, torch.tensor([1], dtype=torch.int32, device="cuda"), (40, 40))
+    want = np.stack([opr.resize_u8(big[0, c].cpu().numpy(), 40, 40, "bilinear") for c in range(3)])
+    assert np.array_equal(got[0].cpu().numpy(), want)
+    with pytest.raises(RuntimeError):
+        ops.roi_crop_resize(big, job, (40, 40))
+
+
+def test_device_pipeline_equals_host_lists():
+    """`look_twice_device` (no host synchronisation, chunks with device-side counts) produces bit-identical masks to
+    the host-list path (`process_preds` + `look_twice_batch`) on planted objects, ragged originals included."""
+    from ucod_dpl_b200.data.datasets.transforms import pack_padded
+    from ucod_dpl_b200.synth import planted_object_logits, synth_batch_u8, synth_image_u8
+    S = 224
+    ev = _tiny_evaluator(S, max_looks_per_image=3)
+    imgs = synth_batch_u8(0, 6, S, S).cuda()
+    planted = torch.stack([planted_object_logits(70 + i, 68, k) for i, k in enumerate((2, 0, 3, 1, 3, 2))]).cuda()
+    originals = [synth_image_u8(20 + i, 300 + 37 * i, 420 - 29 * i).permute(1, 2, 0).contiguous().numpy() for i in range(6)]
+    canvas, sizes = pack_padded(originals, "cuda")
+    res = ev.look_twice_device(imgs, canvas, layout="HWC", orig_sizes=sizes, first_logits=planted)
+    res.check()
+    up, boxes = ev.process_preds(planted)
+    assert torch.equal(up.to(torch.uint8), res.first) and boxes == res.bboxes
+    want = ev.look_twice_batch(canvas, boxes, up.to(torch.uint8), layout="HWC", orig_sizes=sizes)
+    assert torch.equal(res.final, want)
+    kept, status, wanted, _ = res.counts.cpu().tolist()
+    assert status == 0 and kept == wanted == sum(len(b) for b in boxes if b) and kept > 6  # > 1 chunk in use
+    # the number of chunks enqueued ahead of time is only a launch-count guess: with too few, check() completes the batch
+    assert ev._recent_chunks == [2]
+    ev._recent_chunks = [1]
+    res2 = ev.look_twice_device(imgs, canvas, layout="HWC", orig_sizes=sizes, first_logits=planted)
+    assert not torch.equal(res2.final, want)          # one chunk (6 of 12 second looks) so far
+    res2.check()
+    assert torch.equal(res2.final, want) and ev._recent_chunks == [1, 2]
+    # capacity overflow is reported, not silently dropped
+    ev1 = _tiny_evaluator(S, max_looks_per_image=1)
+    with pytest.raises(RuntimeError):
+        ev1.look_twice_device(imgs, canvas, layout="HWC", orig_sizes=sizes, first_logits=planted).check()

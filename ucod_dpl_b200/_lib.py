@@ -10,7 +10,7 @@ from pathlib import Path
 
 import torch
 
-_LIB_PATH = Path(__file__).resolve().parent / "csrc" / "libucod_b200.so"
+_LIB_PATH = Path(os.environ.get("UCOD_B200_LIB") or Path(__file__).resolve().parent / "csrc" / "libucod_b200.so")  # env: A/B builds
 _lib = None
 
 c_void_p = ctypes.c_void_p

@@ -74,6 +74,13 @@ int ucod_vit_keys(void* handle, const void* images, int image_dtype, int batch, 
                     keys_f32, keys_bf16, cls_attn, keep_cls, reinterpret_cast<cudaStream_t>(stream));
 }
 
+int ucod_vit_keys_dyn(void* handle, const void* images, int image_dtype, int batch, const int32_t* batch_dev, int img_h,
+                      int img_w, const float* pos_emb, void* workspace, uint64_t workspace_bytes, float* keys_f32,
+                      void* keys_bf16, float* cls_attn, int keep_cls, void* stream) {
+    return vit_keys(handle, images, image_dtype, batch, img_h, img_w, pos_emb, workspace, (size_t)workspace_bytes,
+                    keys_f32, keys_bf16, cls_attn, keep_cls, reinterpret_cast<cudaStream_t>(stream), batch_dev);
+}
+
 uint64_t ucod_decoder_workspace_bytes(int batch, int gin_h, int gin_w, int out_h, int out_w, int want_ortho) {
     return (uint64_t)decoder_workspace_bytes(batch, gin_h, gin_w, out_h, out_w, want_ortho);
 }
@@ -85,6 +92,15 @@ int ucod_decoder_fwd(const void* keys_bf16, int batch, int dim, int gin_h, int g
     DecoderWeights w{dim, w_dec, b_dec, emb, w_fg, b_fg, w_bg, b_bg};
     return decoder_forward(keys_bf16, batch, gin_h, gin_w, out_h, out_w, w, fg, bg, ortho, workspace,
                            (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_decoder_fwd_dyn(const void* keys_bf16, int batch, const int32_t* batch_dev, int dim, int gin_h, int gin_w,
+                         int out_h, int out_w, const void* w_dec, const float* b_dec, const float* emb,
+                         const float* w_fg, const float* b_fg, const float* w_bg, const float* b_bg, float* fg,
+                         float* bg, void* workspace, uint64_t workspace_bytes, void* stream) {
+    UCOD_REQUIRE(w_dec && b_dec && emb && w_fg && b_fg && w_bg && b_bg, "ucod_decoder_fwd_dyn: null weight pointer");
+    DecoderWeights w{dim, w_dec, b_dec, emb, w_fg, b_fg, w_bg, b_bg};
+    return decoder_forward(keys_bf16, batch, gin_h, gin_w, out_h, out_w, w, fg, bg, nullptr, workspace,
+                           (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream), batch_dev);
 }
 int ucod_features_to_tokens_bf16(const float* in, void* out, int batch, int channels, int pixels, int64_t sb,
                                  int64_t sc, int64_t sp, void* stream) {
@@ -137,6 +153,34 @@ int ucod_paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const i
                        uint64_t workspace_bytes, int32_t* err_flag, void* stream) {
     return paste_bicubic(logits, njobs, g_h, g_w, jobs, max_rank, mask, n_images, s_h, s_w, out_cap, workspace,
                          (size_t)workspace_bytes, err_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_lt_build_jobs(const int32_t* boxes, const int32_t* nbox, int batch, int s_h, int s_w, int src_h, int src_w,
+                       const int32_t* orig_sizes, int32_t* crop_jobs, int32_t* paste_jobs, int capacity,
+                       int32_t* counts, int chunk, int32_t* chunk_counts, void* stream) {
+    return lt_build_jobs(boxes, nbox, batch, s_h, s_w, src_h, src_w, orig_sizes, crop_jobs, paste_jobs, capacity, counts,
+                         chunk, chunk_counts, reinterpret_cast<cudaStream_t>(stream));
+}
+uint64_t ucod_roi_crop_resize_dyn_workspace_bytes(int capacity, int src_h, int src_w, int out_h, int out_w) {
+    return (uint64_t)roi_crop_resize_dyn_workspace_bytes(capacity, src_h, src_w, out_h, out_w);
+}
+int ucod_roi_crop_resize_dyn(const uint8_t* images, int n_images, int src_h, int src_w, int64_t image_stride,
+                             int64_t channel_stride, int64_t row_stride, int64_t pixel_stride, const int32_t* jobs,
+                             int capacity, const int32_t* njobs_dev, uint8_t* out, int out_h, int out_w,
+                             void* workspace, uint64_t workspace_bytes, int32_t* err_flag, void* stream) {
+    return roi_crop_resize_dyn(images, n_images, src_h, src_w, image_stride, channel_stride, row_stride, pixel_stride,
+                               jobs, capacity, njobs_dev, out, out_h, out_w, workspace, (size_t)workspace_bytes,
+                               err_flag, reinterpret_cast<cudaStream_t>(stream));
+}
+uint64_t ucod_paste_bicubic_dyn_workspace_bytes(int capacity, int g_h, int g_w, int out_cap) {
+    return (uint64_t)paste_bicubic_dyn_workspace_bytes(capacity, g_h, g_w, out_cap);
+}
+int ucod_paste_bicubic_dyn(const float* logits, int capacity, const int32_t* njobs_dev, int g_h, int g_w,
+                           const int32_t* all_jobs, int first_index, int n_all, const int32_t* n_all_dev,
+                           uint8_t* mask, int n_images, int s_h, int s_w, int out_cap, void* workspace,
+                           uint64_t workspace_bytes, int32_t* err_flag, void* stream) {
+    return paste_bicubic_dyn(logits, capacity, njobs_dev, g_h, g_w, all_jobs, first_index, n_all, n_all_dev, mask,
+                             n_images, s_h, s_w, out_cap, workspace, (size_t)workspace_bytes, err_flag,
+                             reinterpret_cast<cudaStream_t>(stream));
 }
 int ucod_mask_scale_u8(const uint8_t* in, uint8_t* out, uint64_t n, int mul, void* stream) {
     return mask_scale_u8(in, out, (size_t)n, mul, reinterpret_cast<cudaStream_t>(stream));

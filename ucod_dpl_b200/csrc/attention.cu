@@ -174,7 +174,8 @@ template <int D>
 __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     attention_fwd_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                          const __grid_constant__ CUtensorMap tm_v, __nv_bfloat16* __restrict__ ctx, int Tq, int Tk,
-                         int H, int ld_ctx, float scale_log2e, const int* __restrict__ kv_map) {
+                         int H, int ld_ctx, float scale_log2e, const int* __restrict__ kv_map,
+                         const int* __restrict__ batch_dev) {
     using C = AttCfg<D>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     // ones still in L2) and the out-projection GEMM starts with the first images' ctx rows
     const int bh = (int)gridDim.y - 1 - (int)blockIdx.y;
     const int b = bh / H, h = bh - b * H;
+    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;  // device-side batch count: whole CTA leaves
     const int col0 = h * D;
     const int n_tiles = (Tk + C::BN - 1) / C::BN;
 #ifdef UCOD_ATT_TIMELINE
@@ -544,7 +546,8 @@ template <int D>
 __global__ void __launch_bounds__(128)
     attention_rows_kernel(const __nv_bfloat16* __restrict__ q, int ld_q, const __nv_bfloat16* __restrict__ k,
                           const __nv_bfloat16* __restrict__ v, int ld_kv, __nv_bfloat16* __restrict__ ctx, int ld_ctx,
-                          int Tq, int Tk, int H, int row0, float scale, const int* __restrict__ kv_map) {
+                          int Tq, int Tk, int H, int row0, float scale, const int* __restrict__ kv_map,
+                          const int* __restrict__ batch_dev) {
     extern __shared__ float sm_rows[];
     float* sq = sm_rows;          // [D]
     float* part = sq + D;         // [128 / (D/2)][D] = 256 partial sums
@@ -553,6 +556,7 @@ __global__ void __launch_bounds__(128)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int row = row0 + blockIdx.x;
     const int b = blockIdx.y / H, h = blockIdx.y - b * H;
+    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     const int bkv = kv_map != nullptr ? __ldg(kv_map + b) : b;
     const __nv_bfloat16* qr = q + ((size_t)b * Tq + row) * (size_t)ld_q + h * D;
     const __nv_bfloat16* kb = k + (size_t)bkv * Tk * (size_t)ld_kv + h * D;
@@ -662,17 +666,18 @@ int launch_inst(const AttentionArgs& a, cudaStream_t stream) {
     const bool split_tail = a.tokens_q > C::BM && q_tail > 0 && q_tail <= kRowsMax && rows_smem <= 48 * 1024;
     dim3 grid((unsigned)(split_tail ? a.tokens_q / C::BM : ceil_div(a.tokens_q, C::BM)), (unsigned)(a.batch * a.heads));
     {
-        ProfScope ps(KC_ATTENTION, stream, 4.0 * a.batch * a.heads * (double)a.tokens_q * a.tokens_kv * a.head_dim_real);
+        ProfScope ps(KC_ATTENTION, stream,
+                     a.batch_dev ? 0.0 : 4.0 * a.batch * a.heads * (double)a.tokens_q * a.tokens_kv * a.head_dim_real);
         kern<<<grid, C::THREADS, C::SMEM, stream>>>(tq, tk, tv, reinterpret_cast<__nv_bfloat16*>(a.ctx), a.tokens_q,
                                                      a.tokens_kv, a.heads, a.ld_ctx, a.scale * 1.4426950408889634f,
-                                                     a.kv_batch_map);
+                                                     a.kv_batch_map, a.batch_dev);
     }
     if (split_tail) {
         ProfScope ps(KC_ATTENTION, stream, 0.0);  // its flops are counted with the tile kernel above
         attention_rows_kernel<D><<<dim3((unsigned)q_tail, grid.y), 128, rows_smem, stream>>>(
                 static_cast<const __nv_bfloat16*>(a.q), a.ld_q, static_cast<const __nv_bfloat16*>(a.k),
                 static_cast<const __nv_bfloat16*>(a.v), a.ld_kv, reinterpret_cast<__nv_bfloat16*>(a.ctx), a.ld_ctx,
-            a.tokens_q, a.tokens_kv, a.heads, a.tokens_q - q_tail, a.scale, a.kv_batch_map);
+            a.tokens_q, a.tokens_kv, a.heads, a.tokens_q - q_tail, a.scale, a.kv_batch_map, a.batch_dev);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;

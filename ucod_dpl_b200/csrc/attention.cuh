@@ -19,6 +19,7 @@ struct AttentionArgs {
     float scale = 0.125f;
     int kv_batch = 0;                   // number of K/V batches when kv_batch_map is used (0: same as batch)
     const int* kv_batch_map = nullptr;  // optional [batch]: K/V batch index of each q batch (cross-attention sharing)
+    const int* batch_dev = nullptr;     // optional device-side batch count (<= batch): CTAs of batches beyond it exit
 };
 int launch_attention(const AttentionArgs& args, cudaStream_t stream);
 

@@ -51,9 +51,10 @@ constexpr int DEC_PIX_PER_BLOCK = 64;  // 8 warps x 8 pixels
 // sumsq[b, c] += sum over this block's pixels of d_up[pix, c]^2
 __global__ void __launch_bounds__(256)
     decoder_sumsq_kernel(const float* __restrict__ d_in, float* __restrict__ sumsq, int gin_h, int gin_w, int out_h,
-                         int out_w) {
+                         int out_w, const int* __restrict__ batch_dev) {
     __shared__ float4 part[8][32];
     const int b = blockIdx.y;
+    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* d_img = d_in + (size_t)b * gin_h * gin_w * 128;
     const int npix = out_h * out_w;
@@ -90,8 +91,10 @@ __global__ void __launch_bounds__(256)
     decoder_head_kernel(const float* __restrict__ d_in, const float* __restrict__ sumsq, const float* __restrict__ emb,
                         const float* __restrict__ w_fg, const float* __restrict__ b_fg, const float* __restrict__ w_bg,
                         const float* __restrict__ b_bg, float* __restrict__ fg, float* __restrict__ bg,
-                        float* __restrict__ fhat_out, int gin_h, int gin_w, int out_h, int out_w) {
+                        float* __restrict__ fhat_out, int gin_h, int gin_w, int out_h, int out_w,
+                        const int* __restrict__ batch_dev) {
     const int b = blockIdx.y;
+    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* d_img = d_in + (size_t)b * gin_h * gin_w * 128;
     const int npix = out_h * out_w;
@@ -207,8 +210,10 @@ size_t decoder_workspace_bytes(int B, int gin_h, int gin_w, int out_h, int out_w
 }
 
 int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_h, int out_w, const DecoderWeights& w,
-                    float* fg, float* bg, float* ortho, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                    float* fg, float* bg, float* ortho, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                    const int* batch_dev) {
     UCOD_REQUIRE(keys_bf16 && fg && workspace, "decoder_forward: null argument");
+    UCOD_REQUIRE(batch_dev == nullptr || ortho == nullptr, "decoder_forward: device-side batch count is eval-only");
     UCOD_REQUIRE(B > 0 && gin_h > 0 && gin_w > 0 && out_h > 0 && out_w > 0, "decoder_forward: bad geometry");
     const size_t need = decoder_workspace_bytes(B, gin_h, gin_w, out_h, out_w, ortho != nullptr);
     UCOD_REQUIRE(ws_bytes >= need, "decoder_forward: workspace too small (%zu < %zu)", ws_bytes, need);
@@ -231,20 +236,21 @@ int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_
     ep.bias = w.b_dec;
     ep.out = d_in;
     ep.ld_out = 128;
+    ep.m_dev = batch_dev, ep.m_per = gin_h * gin_w;
     if (int rc = launch_gemm_bf16(keys_bf16, w.dim, w.w_dec, w.dim, B * gin_h * gin_w, 128, w.dim, ep, stream))
         return rc;
     UCOD_CHECK_CUDA(cudaMemsetAsync(sumsq, 0, (size_t)B * 128 * 4, stream));
     dim3 grid(ceil_div(npix, DEC_PIX_PER_BLOCK), B);
     const double d_bytes = (double)B * gin_h * gin_w * 128 * 4;
     {
-        ProfScope ps(KC_DECODER, stream, d_bytes);
-        decoder_sumsq_kernel<<<grid, 256, 0, stream>>>(d_in, sumsq, gin_h, gin_w, out_h, out_w);
+        ProfScope ps(KC_DECODER, stream, batch_dev ? 0.0 : d_bytes);
+        decoder_sumsq_kernel<<<grid, 256, 0, stream>>>(d_in, sumsq, gin_h, gin_w, out_h, out_w, batch_dev);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     {
-        ProfScope ps(KC_DECODER, stream, d_bytes + (double)B * npix * 8);
+        ProfScope ps(KC_DECODER, stream, batch_dev ? 0.0 : d_bytes + (double)B * npix * 8);
         decoder_head_kernel<<<grid, 256, 0, stream>>>(d_in, sumsq, w.emb, w.w_fg, w.b_fg, w.w_bg, w.b_bg, fg, bg, fhat,
-                                                      gin_h, gin_w, out_h, out_w);
+                                                      gin_h, gin_w, out_h, out_w, batch_dev);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     if (ortho) {

@@ -17,7 +17,8 @@ struct DecoderWeights {
 
 size_t decoder_workspace_bytes(int B, int gin_h, int gin_w, int out_h, int out_w, int want_ortho);
 int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_h, int out_w, const DecoderWeights& w,
-                    float* fg, float* bg, float* ortho, void* workspace, size_t ws_bytes, cudaStream_t stream);
+                    float* fg, float* bg, float* ortho, void* workspace, size_t ws_bytes, cudaStream_t stream,
+                    const int* batch_dev = nullptr);
 struct DecoderGrads {  // fp32 gradients, same shapes as the weights (w_dec as fp32 [128, dim])
     float* w_dec; float* b_dec; float* w_fg; float* b_fg; float* w_bg; float* b_bg;
 };

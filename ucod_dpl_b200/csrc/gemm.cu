@@ -189,6 +189,10 @@ __global__ void __launch_bounds__(192, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (ep.m_dev != nullptr) {  // device-side row count (capacity M)
+        const long long md = (long long)__ldg(ep.m_dev) * ep.m_per;
+        M = md < (long long)M ? (int)(md < 0 ? 0 : md) : M;
+    }
     const int m_tiles = (M + Cfg::BM - 1) / Cfg::BM;
     const int n_tiles = N / BN;
     const int total_tiles = m_tiles * n_tiles;
@@ -504,6 +508,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    if (ep.m_dev != nullptr) {  // device-side row count (capacity M)
+        const long long md = (long long)__ldg(ep.m_dev) * ep.m_per;
+        M = md < (long long)M ? (int)(md < 0 ? 0 : md) : M;
+    }
     const int m_pairs = (M + 2 * Cfg::BM - 1) / (2 * Cfg::BM);
     const int n_tiles = N / BN;
     const int total_tiles = m_pairs * n_tiles;
@@ -752,7 +760,7 @@ static int launch_inst(const CUtensorMap& ta, const CUtensorMap& tb, int M, int 
     const int tiles = ceil_div(M, Cfg::BM) * (N / BN);
     const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
     {
-        ProfScope ps(KC_GEMM, stream, 2.0 * M * N * K);
+        ProfScope ps(KC_GEMM, stream, ep.m_dev ? 0.0 : 2.0 * M * N * K);  // device-side row count: the caller books the work
         kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, M, N, K, ep);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
@@ -790,7 +798,7 @@ static int launch_pair_inst(const CUtensorMap& ta, const CUtensorMap& tb, int M,
     const int tiles = ceil_div(M, 2 * Cfg::BM) * (N / Cfg::BN);
     const int clusters = tiles < max_clusters ? tiles : max_clusters;
     {
-        ProfScope ps(KC_GEMM, stream, 2.0 * M * N * K);
+        ProfScope ps(KC_GEMM, stream, ep.m_dev ? 0.0 : 2.0 * M * N * K);  // device-side row count: the caller books the work
         kern<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(ta, tb, tout, M, N, K, ep);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());

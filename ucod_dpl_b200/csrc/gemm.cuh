@@ -24,6 +24,11 @@ struct GemmEpi {
     int ld_out = 0;      // row pitch of out/out2 in elements
     int tokens = 0;      // T (EPI_KEYS) or P (EPI_PATCH)
     int skip = 0;        // EPI_KEYS
+    // Device-side row count (second Look-Twice pass: the number of crops is only known on the device).  When
+    // m_dev != nullptr the kernel processes min(M, *m_dev * m_per) rows; M stays the capacity the tensor maps and
+    // buffers are sized for.  No host synchronisation is involved.
+    const int* m_dev = nullptr;
+    int m_per = 1;
 };
 
 // D[M,N] = A[M,K] * W[N,K]^T with fp32 accumulation in TMEM; A, W bf16 row-major (K contiguous).

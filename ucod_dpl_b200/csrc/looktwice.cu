@@ -241,7 +241,7 @@ __global__ void lt_boxes_kernel(const ImgSummary* __restrict__ summ, const int* 
 // ------------------------------------------------------------------------------------------------
 // Pillow ImagingResample (8 bpc): coefficient tables
 // ------------------------------------------------------------------------------------------------
-constexpr int RS_KMAX = 40;          // max taps per output sample (support scale up to ~19x for bilinear)
+constexpr int RS_KMAX = 40;          // default tap capacity per output sample (down-scale up to ~19x for bilinear)
 constexpr int RS_PRECISION_BITS = 22;
 
 __device__ __forceinline__ double filt_bilinear(double x) {
@@ -268,14 +268,18 @@ __device__ __forceinline__ double filt_bicubic(double x) {
 }
 
 // job geometry for one axis: in_size source samples -> out_size samples (box = whole source)
-// bounds[(job*2+axis)*out_cap + xx] = {xmin, count} ; coef[((job*2+axis)*RS_KMAX + k)*out_cap + xx]
+// bounds[(job*2+axis)*out_cap + xx] = {xmin, count} ; coef[((job*2+axis)*kmax + k)*out_cap + xx]
 // (tap-major, so that neighbouring output samples read neighbouring coefficients: coalesced in the horizontal passes)
+// kmax = tap capacity per output sample (host: from the largest possible down-scale); a job needing more sets err bit 0
+// and gets count 0 (its output is then the rounding constant only — the caller raises on the flag).
+// The filter is evaluated twice (sum, then normalised taps) instead of keeping the taps in a local array.
 __global__ void resample_coeffs_kernel(const int* __restrict__ in_sizes /*[njobs,2] (w,h)*/,
                                        const int* __restrict__ out_sizes /*[njobs,2] (w,h)*/, int njobs, int out_cap,
-                                       int bicubic, int2* __restrict__ bounds, int* __restrict__ coef,
-                                       int* __restrict__ err) {
+                                       int kmax, int bicubic, int2* __restrict__ bounds, int* __restrict__ coef,
+                                       int* __restrict__ err, const int* __restrict__ njobs_dev) {
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     const int axis = blockIdx.y, job = blockIdx.z;
+    if (njobs_dev != nullptr && job >= __ldg(njobs_dev)) return;
     const int in_size = in_sizes[job * 2 + axis], out_size = out_sizes[job * 2 + axis];
     if (xx >= out_size || xx >= out_cap || in_size <= 0) return;
     const double fsupport = bicubic ? 2.0 : 1.0;
@@ -283,8 +287,10 @@ __global__ void resample_coeffs_kernel(const int* __restrict__ in_sizes /*[njobs
     const double filterscale = scale < 1.0 ? 1.0 : scale;
     const double support = __dmul_rn(fsupport, filterscale);
     const int ksize = (int)ceil(support) * 2 + 1;
-    if (ksize > RS_KMAX) {
+    const size_t o = ((size_t)job * 2 + axis) * out_cap + xx;
+    if (ksize > kmax) {
         atomicOr(err, 1);
+        bounds[o] = make_int2(0, 0);
         return;
     }
     const double center = __dadd_rn(0.0, __dmul_rn((double)xx + 0.5, scale));
@@ -294,19 +300,16 @@ __global__ void resample_coeffs_kernel(const int* __restrict__ in_sizes /*[njobs
     int xmax = (int)__dadd_rn(__dadd_rn(center, support), 0.5);
     if (xmax > in_size) xmax = in_size;
     const int n = xmax - xmin;
-    double w[RS_KMAX];
     double ww = 0.0;
     for (int x = 0; x < n; ++x) {
         const double arg = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
-        const double v = bicubic ? filt_bicubic(arg) : filt_bilinear(arg);
-        w[x] = v;
-        ww = __dadd_rn(ww, v);
+        ww = __dadd_rn(ww, bicubic ? filt_bicubic(arg) : filt_bilinear(arg));
     }
-    const size_t o = ((size_t)job * 2 + axis) * out_cap + xx;
     bounds[o] = make_int2(xmin, n);
-    int* kk = coef + ((size_t)job * 2 + axis) * RS_KMAX * out_cap + xx;  // stride out_cap between taps
+    int* kk = coef + ((size_t)job * 2 + axis) * kmax * out_cap + xx;  // stride out_cap between taps
     for (int x = 0; x < n; ++x) {
-        double k = w[x];
+        const double arg = __dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss);
+        double k = bicubic ? filt_bicubic(arg) : filt_bilinear(arg);
         if (ww != 0.0) k = __ddiv_rn(k, ww);
         const double f = __dmul_rn(k, (double)(1 << RS_PRECISION_BITS));
         kk[(size_t)x * out_cap] = k < 0 ? (int)__dadd_rn(-0.5, f) : (int)__dadd_rn(0.5, f);
@@ -323,9 +326,10 @@ __global__ void crop_hpass_kernel(const uint8_t* __restrict__ images, int H0, in
                                   long long ch_stride, long long row_stride, long long px_stride,
                                   const int* __restrict__ jobs /*[n,5] img,x,y,w,h*/, const int2* __restrict__ bounds,
                                   const int* __restrict__ coef, uint8_t* __restrict__ tmp, int out_cap, int out_w,
-                                  int out_h, int tmp_rows) {
+                                  int out_h, int tmp_rows, int kmax, const int* __restrict__ njobs_dev) {
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     const int job = blockIdx.z;
+    if (njobs_dev != nullptr && job >= __ldg(njobs_dev)) return;
     const int c = blockIdx.y % 3, r = blockIdx.y / 3;
     const int* jb = jobs + job * 5;
     const int cw = jb[3], chh = jb[4];
@@ -333,19 +337,20 @@ __global__ void crop_hpass_kernel(const uint8_t* __restrict__ images, int H0, in
     const size_t vb = ((size_t)job * 2 + 1) * out_cap;
     const int y_first = bounds[vb].x;
     const int y_last = bounds[vb + out_h - 1].x + bounds[vb + out_h - 1].y;
-    if (r >= y_last - y_first || r >= tmp_rows) return;
-    const int sy = jb[2] + y_first + r;  // source row in the original image
+    // r walks the image rows the crop touches; rows of the crop outside the image are zero after the horizontal pass
+    // (PIL pads a crop with 0), so they are neither computed nor stored: the scratch is indexed by the image row.
+    const int sy0 = jb[2] + y_first;
+    const int sy = (sy0 > 0 ? sy0 : 0) + r;  // source row in the original image
+    if (sy >= jb[2] + y_last || sy >= H0 || r >= tmp_rows) return;
     const size_t hb = ((size_t)job * 2 + 0) * out_cap + xx;
     const int2 bd = bounds[hb];
-    const int* kk = coef + ((size_t)job * 2 + 0) * RS_KMAX * out_cap + xx;
+    const int* kk = coef + ((size_t)job * 2 + 0) * kmax * out_cap + xx;
     int acc = 1 << (RS_PRECISION_BITS - 1);
-    if (sy >= 0 && sy < H0) {
-        const uint8_t* row = images + (size_t)jb[0] * img_stride + (size_t)c * ch_stride + (size_t)sy * row_stride;
-        for (int k = 0; k < bd.y; ++k) {
-            const int sx = jb[1] + bd.x + k;
-            const int px = (sx >= 0 && sx < W0) ? row[(size_t)sx * px_stride] : 0;
-            acc += px * __ldg(kk + (size_t)k * out_cap);
-        }
+    const uint8_t* row = images + (size_t)jb[0] * img_stride + (size_t)c * ch_stride + (size_t)sy * row_stride;
+    for (int k = 0; k < bd.y; ++k) {
+        const int sx = jb[1] + bd.x + k;
+        const int px = (sx >= 0 && sx < W0) ? row[(size_t)sx * px_stride] : 0;
+        acc += px * __ldg(kk + (size_t)k * out_cap);
     }
     tmp[(((size_t)job * 3 + c) * tmp_rows + r) * out_w + xx] = clip8(acc);
 }
@@ -353,9 +358,11 @@ __global__ void crop_hpass_kernel(const uint8_t* __restrict__ images, int H0, in
 // ---- vertical pass: out[job][c][yy][xx] (planar u8) ----
 __global__ void crop_vpass_kernel(const uint8_t* __restrict__ tmp, const int* __restrict__ jobs,
                                   const int2* __restrict__ bounds, const int* __restrict__ coef,
-                                  uint8_t* __restrict__ out, int out_cap, int out_w, int out_h, int tmp_rows) {
+                                  uint8_t* __restrict__ out, int out_cap, int out_w, int out_h, int tmp_rows, int kmax,
+                                  int H0, const int* __restrict__ njobs_dev) {
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     const int job = blockIdx.z;
+    if (njobs_dev != nullptr && job >= __ldg(njobs_dev)) return;
     const int c = blockIdx.y % 3, yy = blockIdx.y / 3;
     const int* jb = jobs + job * 5;
     if (xx >= out_w) return;
@@ -367,11 +374,15 @@ __global__ void crop_vpass_kernel(const uint8_t* __restrict__ tmp, const int* __
     const size_t vb = ((size_t)job * 2 + 1) * out_cap;
     const int y_first = bounds[vb].x;
     const int2 bd = bounds[vb + yy];
-    const int* kk = coef + ((size_t)job * 2 + 1) * RS_KMAX * out_cap + yy;  // same address for the whole block
+    const int* kk = coef + ((size_t)job * 2 + 1) * kmax * out_cap + yy;  // same address for the whole block
     const uint8_t* src = tmp + ((size_t)job * 3 + c) * tmp_rows * out_w + xx;
+    const int sy0 = jb[2] + y_first;
+    const int base = sy0 > 0 ? sy0 : 0;  // image row stored at scratch row 0 (see crop_hpass_kernel)
     int acc = 1 << (RS_PRECISION_BITS - 1);
-    for (int k = 0; k < bd.y; ++k)
-        acc += (int)src[(size_t)(bd.x - y_first + k) * out_w] * __ldg(kk + (size_t)k * out_cap);
+    for (int k = 0; k < bd.y; ++k) {
+        const int sy = jb[2] + bd.x + k;
+        if (sy >= 0 && sy < H0) acc += (int)src[(size_t)(sy - base) * out_w] * __ldg(kk + (size_t)k * out_cap);
+    }
     *dst = clip8(acc);
 }
 
@@ -379,37 +390,56 @@ __global__ void crop_vpass_kernel(const uint8_t* __restrict__ tmp, const int* __
 __global__ void paste_hpass_kernel(const float* __restrict__ logits, int g_h, int g_w,
                                    const int* __restrict__ jobs /*[n,6] img,x,y,w,h,rank*/,
                                    const int2* __restrict__ bounds, const int* __restrict__ coef,
-                                   uint8_t* __restrict__ tmp, int out_cap) {
+                                   uint8_t* __restrict__ tmp, int out_cap, int kmax,
+                                   const int* __restrict__ njobs_dev) {
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y, job = blockIdx.z;
+    if (njobs_dev != nullptr && job >= __ldg(njobs_dev)) return;
     const int* jb = jobs + job * 6;
     const int w = jb[3], h = jb[4];
     if (w <= 0 || h <= 0 || xx >= w || xx >= out_cap) return;
     const size_t hb = ((size_t)job * 2 + 0) * out_cap + xx;
     const int2 bd = bounds[hb];
-    const int* kk = coef + ((size_t)job * 2 + 0) * RS_KMAX * out_cap + xx;
+    const int* kk = coef + ((size_t)job * 2 + 0) * kmax * out_cap + xx;
     const float* row = logits + ((size_t)job * g_h + r) * g_w;
     int acc = 1 << (RS_PRECISION_BITS - 1);
     for (int k = 0; k < bd.y; ++k) acc += (row[bd.x + k] > 0x1.8p-24f ? 255 : 0) * __ldg(kk + (size_t)k * out_cap);
     tmp[((size_t)job * g_h + r) * out_cap + xx] = clip8(acc);
 }
 
-// ---- paste: vertical pass, written straight into the full-size mask (only jobs of the given rank) ----
+// ---- paste: vertical pass, written straight into the full-size mask.
+// The reference pastes an image's boxes one after the other (loop_UCOD_DPL.py:332-351), each paste overwriting its
+// whole rectangle: the final value of a pixel comes from the LAST box that covers it.  Job tables are image-major with
+// ascending rank, so a job skips every pixel that a later job of the same image (entries job+1.. in `all_jobs`) covers;
+// all jobs can then run in one launch, in any order, across chunks.  rank >= 0 restores the round-1 behaviour (one
+// launch per rank, no look-ahead) for callers that pass unordered tables.
 __global__ void paste_vpass_kernel(const uint8_t* __restrict__ tmp, int g_h, const int* __restrict__ jobs,
                                    const int2* __restrict__ bounds, const int* __restrict__ coef,
-                                   uint8_t* __restrict__ mask, int S_h, int S_w, int out_cap, int rank) {
+                                   uint8_t* __restrict__ mask, int S_h, int S_w, int out_cap, int rank, int kmax,
+                                   const int* __restrict__ njobs_dev, const int* __restrict__ all_jobs,
+                                   int first_index, int n_all, const int* __restrict__ n_all_dev) {
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     const int yy = blockIdx.y, job = blockIdx.z;
+    if (njobs_dev != nullptr && job >= __ldg(njobs_dev)) return;
     const int* jb = jobs + job * 6;
-    if (jb[5] != rank) return;
+    if (rank >= 0 && jb[5] != rank) return;
     const int w = jb[3], h = jb[4];
     if (w <= 0 || h <= 0 || xx >= w || yy >= h || xx >= out_cap || yy >= out_cap) return;
     const int dx = jb[1] + xx, dy = jb[2] + yy;
     if (dx < 0 || dx >= S_w || dy < 0 || dy >= S_h) return;  // Image.paste clips
+    if (all_jobs != nullptr) {
+        const int total = n_all_dev != nullptr ? min(n_all, __ldg(n_all_dev)) : n_all;
+        for (int k = first_index + job + 1; k < total; ++k) {
+            const int* o = all_jobs + (size_t)k * 6;
+            if (o[0] != jb[0]) break;
+            if (o[3] > 0 && o[4] > 0 && o[3] <= out_cap && o[4] <= out_cap && dx >= o[1] && dx < o[1] + o[3] &&
+                dy >= o[2] && dy < o[2] + o[4])
+                return;  // a later paste of this image owns the pixel
+        }
+    }
     const size_t vb = ((size_t)job * 2 + 1) * out_cap + yy;
     const int2 bd = bounds[vb];
-    const int* kk = coef + ((size_t)job * 2 + 1) * RS_KMAX * out_cap + yy;
-    // the horizontal pass covered source rows y_first.. ; for an un-cropped source y_first is bounds[0].xmin
+    const int* kk = coef + ((size_t)job * 2 + 1) * kmax * out_cap + yy;
     const uint8_t* src = tmp + (size_t)job * g_h * out_cap + xx;
     int acc = 1 << (RS_PRECISION_BITS - 1);
     for (int k = 0; k < bd.y; ++k) acc += (int)src[(size_t)(bd.x + k) * out_cap] * __ldg(kk + (size_t)k * out_cap);
@@ -421,21 +451,28 @@ __global__ void mask_scale_kernel(const uint8_t* __restrict__ in, uint8_t* __res
     if (i < n) out[i] = in[i] ? (uint8_t)mul : 0;
 }
 
-__global__ void fill_crop_sizes_kernel(const int* jobs, int* sizes, int njobs, int out_w, int out_h) {
+__global__ void fill_crop_sizes_kernel(const int* jobs, int* sizes, int njobs, int out_w, int out_h,
+                                       const int* __restrict__ njobs_dev) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= njobs) return;
+    if (j >= njobs || (njobs_dev != nullptr && j >= __ldg(njobs_dev))) return;
     sizes[j * 2 + 0] = jobs[j * 5 + 3];
     sizes[j * 2 + 1] = jobs[j * 5 + 4];
     sizes[njobs * 2 + j * 2 + 0] = out_w;
     sizes[njobs * 2 + j * 2 + 1] = out_h;
 }
-__global__ void fill_paste_sizes_kernel(const int* jobs, int* sizes, int njobs, int g_w, int g_h) {
+__global__ void fill_paste_sizes_kernel(const int* jobs, int* sizes, int njobs, int g_w, int g_h, int out_cap,
+                                        int* __restrict__ err, const int* __restrict__ njobs_dev) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= njobs) return;
+    if (j >= njobs || (njobs_dev != nullptr && j >= __ldg(njobs_dev))) return;
     sizes[j * 2 + 0] = g_w;
     sizes[j * 2 + 1] = g_h;
-    sizes[njobs * 2 + j * 2 + 0] = jobs[j * 6 + 3];
-    sizes[njobs * 2 + j * 2 + 1] = jobs[j * 6 + 4];
+    int w = jobs[j * 6 + 3], h = jobs[j * 6 + 4];
+    if (w > out_cap || h > out_cap) {  // larger than the caller's bound: flagged, skipped
+        atomicOr(err, 2);
+        w = h = 0;
+    }
+    sizes[njobs * 2 + j * 2 + 0] = w;
+    sizes[njobs * 2 + j * 2 + 1] = h;
 }
 
 size_t align256(size_t v) { return (v + 255) / 256 * 256; }
@@ -475,29 +512,31 @@ int lt_boxes(const uint8_t* mask, int B, int H, int W, double look_twice_th, int
     const int T = 256;
     const unsigned lin = (unsigned)((total + T - 1) / T);
     dim3 g2(ceil_div(W, 128), H, B);
+    // algorithmic bytes credited to the whole CC + box stage: the u8 mask read once plus one int32
+    // label write and read per pixel = 9 B/pixel (2.4 MB per 518^2 mask); booked on the first kernel, the others add 0
     {
-        ProfScope ps(KC_CCL, stream, (double)total * 5);
+        ProfScope ps(KC_CCL, stream, (double)total * 9);
         ccl_init_kernel<<<lin, T, 0, stream>>>(mask, L, n_img, total);
     }
     {
-        ProfScope ps(KC_CCL, stream, (double)total * 8);
+        ProfScope ps(KC_CCL, stream, 0.0);
         ccl_merge_kernel<<<g2, 128, 0, stream>>>(L, H, W, B);
     }
     {
-        ProfScope ps(KC_CCL, stream, (double)total * 8);
+        ProfScope ps(KC_CCL, stream, 0.0);
         ccl_flatten_area_kernel<<<lin, T, 0, stream>>>(L, area, n_img, total);
     }
     lt_init_stats_kernel<<<ceil_div(B * LT_MAXBIG, T), T, 0, stream>>>(st, B * LT_MAXBIG, H, W);
     {
-        ProfScope ps(KC_CCL, stream, (double)total * 8);
+        ProfScope ps(KC_CCL, stream, 0.0);
         ccl_roots_kernel<<<lin, T, 0, stream>>>(L, area, summ, big_root, big_area, n_img, total, 0.01);
     }
     {
-        ProfScope ps(KC_CCL, stream, (double)total * 8);
+        ProfScope ps(KC_CCL, stream, 0.0);
         ccl_bbox_kernel<<<g2, 128, 0, stream>>>(L, area, st, H, W, B);
     }
     {
-        ProfScope ps(KC_CCL, stream, (double)B * LT_MAXBIG * 40);
+        ProfScope ps(KC_CCL, stream, 0.0);
         lt_boxes_kernel<<<ceil_div(B, 32), 32, 0, stream>>>(summ, big_area, st, boxes, nbox, status, B, H, W,
                                                            look_twice_th, dynamic, const_scale);
     }
@@ -507,10 +546,64 @@ int lt_boxes(const uint8_t* mask, int B, int H, int W, double look_twice_th, int
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t roi_crop_resize_workspace_bytes(int njobs, int max_crop_h, int out_h, int out_w) {
+// tap capacity for a down-scale of in_max source samples onto out samples (Pillow: support = max(scale, 1))
+static int taps_for(int in_max, int out) {
+    const double scale = (double)in_max / (double)(out > 0 ? out : 1);
+    const int k = (int)ceil(scale < 1.0 ? 1.0 : scale) * 2 + 1;
+    return k < 5 ? 5 : k;
+}
+
+static size_t crop_ws_bytes(int njobs, int max_crop_h, int out_h, int out_w, int kmax) {
     const int cap = out_h > out_w ? out_h : out_w;
-    return align256((size_t)njobs * 2 * cap * sizeof(int2)) + align256((size_t)njobs * 2 * cap * RS_KMAX * 4) +
+    return align256((size_t)njobs * 2 * cap * sizeof(int2)) + align256((size_t)njobs * 2 * cap * kmax * 4) +
            align256((size_t)njobs * 3 * max_crop_h * out_w) + align256((size_t)njobs * 4 * 4) + 1024;
+}
+size_t roi_crop_resize_workspace_bytes(int njobs, int max_crop_h, int out_h, int out_w) {
+    return crop_ws_bytes(njobs, max_crop_h, out_h, out_w, RS_KMAX);
+}
+// crops may stick out of the image (a Look-Twice box grows by up to sqrt(2) and is then mapped to the original): the
+// tap table covers crops of up to twice the source extent; larger ones set err bit 0
+size_t roi_crop_resize_dyn_workspace_bytes(int capacity, int H0, int W0, int out_h, int out_w) {
+    const int kh = taps_for(2 * H0, out_h), kw = taps_for(2 * W0, out_w);
+    return crop_ws_bytes(capacity, H0, out_h, out_w, kh > kw ? kh : kw);
+}
+
+static int crop_resize_core(const uint8_t* images, int H0, int W0, long long img_stride, long long ch_stride,
+                            long long row_stride, long long px_stride, const int* jobs, int njobs, const int* njobs_dev,
+                            int max_crop_h, int kmax, uint8_t* out, int out_h, int out_w, void* workspace,
+                            int* err_flag, cudaStream_t stream) {
+    const int cap = out_h > out_w ? out_h : out_w;
+    uint8_t* p = static_cast<uint8_t*>(workspace);
+    int2* bounds = reinterpret_cast<int2*>(p);
+    p += align256((size_t)njobs * 2 * cap * sizeof(int2));
+    int* coef = reinterpret_cast<int*>(p);
+    p += align256((size_t)njobs * 2 * cap * kmax * 4);
+    uint8_t* tmp = p;
+    p += align256((size_t)njobs * 3 * max_crop_h * out_w);
+    int* sizes = reinterpret_cast<int*>(p);  // [njobs,2] in (w,h) then [njobs,2] out (w,h)
+
+    // in/out size tables from the job list (device-side, no host round trip)
+    fill_crop_sizes_kernel<<<ceil_div(njobs, 128), 128, 0, stream>>>(jobs, sizes, njobs, out_w, out_h, njobs_dev);
+    {
+        ProfScope ps(KC_RESAMPLE, stream, 0.0);  // coefficient tables are scratch, not algorithmic traffic
+        dim3 g(ceil_div(cap, 128), 2, njobs);
+        resample_coeffs_kernel<<<g, 128, 0, stream>>>(sizes, sizes + njobs * 2, njobs, cap, kmax, 0, bounds, coef,
+                                                      err_flag, njobs_dev);
+    }
+    {
+        ProfScope ps(KC_RESAMPLE, stream, njobs_dev ? 0.0 : (double)njobs * 3 * max_crop_h * (out_w + W0));
+        dim3 g(ceil_div(out_w, 128), 3 * max_crop_h, njobs);
+        crop_hpass_kernel<<<g, 128, 0, stream>>>(images, H0, W0, img_stride, ch_stride, row_stride, px_stride, jobs,
+                                                 bounds, coef, tmp, cap, out_w, out_h, max_crop_h, kmax, njobs_dev);
+    }
+    {
+        ProfScope ps(KC_RESAMPLE, stream, njobs_dev ? 0.0 : (double)njobs * 3 * out_h * out_w * 3);
+        dim3 g(ceil_div(out_w, 128), 3 * out_h, njobs);
+        crop_vpass_kernel<<<g, 128, 0, stream>>>(tmp, jobs, bounds, coef, out, cap, out_w, out_h, max_crop_h, kmax, H0,
+                                                 njobs_dev);
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int roi_crop_resize(const uint8_t* images, int n_img, int H0, int W0, long long img_stride, long long ch_stride,
@@ -521,42 +614,79 @@ int roi_crop_resize(const uint8_t* images, int n_img, int H0, int W0, long long 
     UCOD_REQUIRE(njobs > 0 && out_h > 0 && out_w > 0 && max_crop_h > 0 && n_img > 0, "roi_crop_resize: bad geometry");
     UCOD_REQUIRE(ws_bytes >= roi_crop_resize_workspace_bytes(njobs, max_crop_h, out_h, out_w),
                  "roi_crop_resize: workspace too small");
-    const int cap = out_h > out_w ? out_h : out_w;
-    uint8_t* p = static_cast<uint8_t*>(workspace);
-    int2* bounds = reinterpret_cast<int2*>(p);
-    p += align256((size_t)njobs * 2 * cap * sizeof(int2));
-    int* coef = reinterpret_cast<int*>(p);
-    p += align256((size_t)njobs * 2 * cap * RS_KMAX * 4);
-    uint8_t* tmp = p;
-    p += align256((size_t)njobs * 3 * max_crop_h * out_w);
-    int* sizes = reinterpret_cast<int*>(p);  // [njobs,2] in (w,h) then [njobs,2] out (w,h)
+    return crop_resize_core(images, H0, W0, img_stride, ch_stride, row_stride, px_stride, jobs, njobs, nullptr,
+                            max_crop_h, RS_KMAX, out, out_h, out_w, workspace, err_flag, stream);
+}
 
-    // in/out size tables from the job list (device-side, no host round trip)
-    fill_crop_sizes_kernel<<<ceil_div(njobs, 128), 128, 0, stream>>>(jobs, sizes, njobs, out_w, out_h);
-    {
-        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * 2 * cap * RS_KMAX * 4);
-        dim3 g(ceil_div(cap, 128), 2, njobs);
-        resample_coeffs_kernel<<<g, 128, 0, stream>>>(sizes, sizes + njobs * 2, njobs, cap, 0, bounds, coef, err_flag);
-    }
-    {
-        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * 3 * max_crop_h * (out_w + W0));
-        dim3 g(ceil_div(out_w, 128), 3 * max_crop_h, njobs);
-        crop_hpass_kernel<<<g, 128, 0, stream>>>(images, H0, W0, img_stride, ch_stride, row_stride, px_stride, jobs,
-                                                 bounds, coef, tmp, cap, out_w, out_h, max_crop_h);
-    }
-    {
-        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * 3 * out_h * out_w * 3);
-        dim3 g(ceil_div(out_w, 128), 3 * out_h, njobs);
-        crop_vpass_kernel<<<g, 128, 0, stream>>>(tmp, jobs, bounds, coef, out, cap, out_w, out_h, max_crop_h);
-    }
-    UCOD_CHECK_CUDA(cudaGetLastError());
-    return 0;
+// Device-count variant: `jobs` holds up to `capacity` entries of which the first *njobs_dev are valid; any crop of
+// the H0 x W0 sources is supported (tap capacity and row scratch are sized for the whole source).
+int roi_crop_resize_dyn(const uint8_t* images, int n_img, int H0, int W0, long long img_stride, long long ch_stride,
+                        long long row_stride, long long px_stride, const int* jobs, int capacity, const int* njobs_dev,
+                        uint8_t* out, int out_h, int out_w, void* workspace, size_t ws_bytes, int* err_flag,
+                        cudaStream_t stream) {
+    UCOD_REQUIRE(images && jobs && out && workspace && err_flag && njobs_dev, "roi_crop_resize_dyn: null argument");
+    UCOD_REQUIRE(capacity > 0 && out_h > 0 && out_w > 0 && H0 > 0 && W0 > 0 && n_img > 0,
+                 "roi_crop_resize_dyn: bad geometry");
+    UCOD_REQUIRE(ws_bytes >= roi_crop_resize_dyn_workspace_bytes(capacity, H0, W0, out_h, out_w),
+                 "roi_crop_resize_dyn: workspace too small");
+    const int kh = taps_for(2 * H0, out_h), kw = taps_for(2 * W0, out_w);
+    return crop_resize_core(images, H0, W0, img_stride, ch_stride, row_stride, px_stride, jobs, capacity, njobs_dev, H0,
+                            kh > kw ? kh : kw, out, out_h, out_w, workspace, err_flag, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
-size_t paste_bicubic_workspace_bytes(int njobs, int g_h, int out_cap) {
-    return align256((size_t)njobs * 2 * out_cap * sizeof(int2)) + align256((size_t)njobs * 2 * out_cap * RS_KMAX * 4) +
+static size_t paste_ws_bytes(int njobs, int g_h, int out_cap, int kmax) {
+    return align256((size_t)njobs * 2 * out_cap * sizeof(int2)) + align256((size_t)njobs * 2 * out_cap * kmax * 4) +
            align256((size_t)njobs * g_h * out_cap) + align256((size_t)njobs * 4 * 4) + 1024;
+}
+size_t paste_bicubic_workspace_bytes(int njobs, int g_h, int out_cap) {
+    return paste_ws_bytes(njobs, g_h, out_cap, RS_KMAX);
+}
+// bicubic support is 2 * max(scale, 1): a g x g map pasted into >= 1 pixel
+static int paste_taps(int g_h, int g_w) { return 2 * taps_for(g_h > g_w ? g_h : g_w, 1); }
+size_t paste_bicubic_dyn_workspace_bytes(int capacity, int g_h, int g_w, int out_cap) {
+    return paste_ws_bytes(capacity, g_h, out_cap, paste_taps(g_h, g_w));
+}
+
+static int paste_core(const float* logits, int njobs, const int* njobs_dev, int g_h, int g_w, const int* jobs,
+                      int max_rank, const int* all_jobs, int first_index, int n_all, const int* n_all_dev,
+                      uint8_t* mask, int S_h, int S_w, int out_cap, int kmax, void* workspace, int* err_flag,
+                      cudaStream_t stream) {
+    uint8_t* p = static_cast<uint8_t*>(workspace);
+    int2* bounds = reinterpret_cast<int2*>(p);
+    p += align256((size_t)njobs * 2 * out_cap * sizeof(int2));
+    int* coef = reinterpret_cast<int*>(p);
+    p += align256((size_t)njobs * 2 * out_cap * kmax * 4);
+    uint8_t* tmp = p;
+    p += align256((size_t)njobs * g_h * out_cap);
+    int* sizes = reinterpret_cast<int*>(p);
+    fill_paste_sizes_kernel<<<ceil_div(njobs, 128), 128, 0, stream>>>(jobs, sizes, njobs, g_w, g_h, out_cap, err_flag,
+                                                                     njobs_dev);
+    {
+        ProfScope ps(KC_RESAMPLE, stream, 0.0);
+        dim3 g(ceil_div(out_cap, 128), 2, njobs);
+        resample_coeffs_kernel<<<g, 128, 0, stream>>>(sizes, sizes + njobs * 2, njobs, out_cap, kmax, 1, bounds, coef,
+                                                      err_flag, njobs_dev);
+    }
+    {
+        ProfScope ps(KC_RESAMPLE, stream, njobs_dev ? 0.0 : (double)njobs * g_h * (out_cap + g_w * 4));
+        dim3 g(ceil_div(out_cap, 128), g_h, njobs);
+        paste_hpass_kernel<<<g, 128, 0, stream>>>(logits, g_h, g_w, jobs, bounds, coef, tmp, out_cap, kmax, njobs_dev);
+    }
+    dim3 g(ceil_div(out_cap, 128), out_cap, njobs);
+    if (all_jobs != nullptr) {
+        ProfScope ps(KC_RESAMPLE, stream, 0.0);
+        paste_vpass_kernel<<<g, 128, 0, stream>>>(tmp, g_h, jobs, bounds, coef, mask, S_h, S_w, out_cap, -1, kmax,
+                                                  njobs_dev, all_jobs, first_index, n_all, n_all_dev);
+    } else {
+        for (int r = 0; r <= max_rank; ++r) {
+            ProfScope ps(KC_RESAMPLE, stream, (double)njobs * out_cap * out_cap / (max_rank + 1));
+            paste_vpass_kernel<<<g, 128, 0, stream>>>(tmp, g_h, jobs, bounds, coef, mask, S_h, S_w, out_cap, r, kmax,
+                                                      njobs_dev, nullptr, 0, 0, nullptr);
+        }
+    }
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
 }
 
 int paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const int* jobs, int max_rank, uint8_t* mask,
@@ -565,33 +695,105 @@ int paste_bicubic(const float* logits, int njobs, int g_h, int g_w, const int* j
     UCOD_REQUIRE(logits && jobs && mask && workspace && err_flag, "paste_bicubic: null argument");
     UCOD_REQUIRE(njobs > 0 && g_h > 0 && g_w > 0 && out_cap > 0 && max_rank >= 0, "paste_bicubic: bad geometry");
     UCOD_REQUIRE(ws_bytes >= paste_bicubic_workspace_bytes(njobs, g_h, out_cap), "paste_bicubic: workspace too small");
-    uint8_t* p = static_cast<uint8_t*>(workspace);
-    int2* bounds = reinterpret_cast<int2*>(p);
-    p += align256((size_t)njobs * 2 * out_cap * sizeof(int2));
-    int* coef = reinterpret_cast<int*>(p);
-    p += align256((size_t)njobs * 2 * out_cap * RS_KMAX * 4);
-    uint8_t* tmp = p;
-    p += align256((size_t)njobs * g_h * out_cap);
-    int* sizes = reinterpret_cast<int*>(p);
-    fill_paste_sizes_kernel<<<ceil_div(njobs, 128), 128, 0, stream>>>(jobs, sizes, njobs, g_w, g_h);
-    {
-        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * 2 * out_cap * RS_KMAX * 4);
-        dim3 g(ceil_div(out_cap, 128), 2, njobs);
-        resample_coeffs_kernel<<<g, 128, 0, stream>>>(sizes, sizes + njobs * 2, njobs, out_cap, 1, bounds, coef,
-                                                      err_flag);
-    }
-    {
-        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * g_h * (out_cap + g_w * 4));
-        dim3 g(ceil_div(out_cap, 128), g_h, njobs);
-        paste_hpass_kernel<<<g, 128, 0, stream>>>(logits, g_h, g_w, jobs, bounds, coef, tmp, out_cap);
-    }
-    for (int r = 0; r <= max_rank; ++r) {
-        ProfScope ps(KC_RESAMPLE, stream, (double)njobs * out_cap * out_cap / (max_rank + 1));
-        dim3 g(ceil_div(out_cap, 128), out_cap, njobs);
-        paste_vpass_kernel<<<g, 128, 0, stream>>>(tmp, g_h, jobs, bounds, coef, mask, S_h, S_w, out_cap, r);
-    }
-    UCOD_CHECK_CUDA(cudaGetLastError());
     (void)n_img;
+    return paste_core(logits, njobs, nullptr, g_h, g_w, jobs, max_rank, nullptr, 0, 0, nullptr, mask, S_h, S_w,
+                      out_cap, RS_KMAX, workspace, err_flag, stream);
+}
+
+// Device-count variant for one chunk of an image-major, rank-ascending job table: `jobs` = all_jobs + first_index*6,
+// *njobs_dev of its `capacity` entries are valid, the table holds min(n_all, *n_all_dev) entries in total.
+int paste_bicubic_dyn(const float* logits, int capacity, const int* njobs_dev, int g_h, int g_w, const int* all_jobs,
+                      int first_index, int n_all, const int* n_all_dev, uint8_t* mask, int n_img, int S_h, int S_w,
+                      int out_cap, void* workspace, size_t ws_bytes, int* err_flag, cudaStream_t stream) {
+    UCOD_REQUIRE(logits && all_jobs && mask && workspace && err_flag && njobs_dev && n_all_dev,
+                 "paste_bicubic_dyn: null argument");
+    UCOD_REQUIRE(capacity > 0 && g_h > 0 && g_w > 0 && out_cap > 0 && first_index >= 0 && n_all >= first_index,
+                 "paste_bicubic_dyn: bad geometry");
+    UCOD_REQUIRE(ws_bytes >= paste_bicubic_dyn_workspace_bytes(capacity, g_h, g_w, out_cap),
+                 "paste_bicubic_dyn: workspace too small");
+    (void)n_img;
+    return paste_core(logits, capacity, njobs_dev, g_h, g_w, all_jobs + (size_t)first_index * 6, 0, all_jobs,
+                      first_index, n_all, n_all_dev, mask, S_h, S_w, out_cap, paste_taps(g_h, g_w), workspace,
+                      err_flag, stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Look-Twice job tables on the device (replaces the host loop of loop_UCOD_DPL.py:331-342 and `resize_bbox`,
+// :387-397): image b contributes max(nbox[b], 0) jobs, image-major, rank = position in the sorted box list.
+// crop job = box mapped to the original image with CPython's float arithmetic (`int(v * (new / old))`, fp64,
+// truncation); paste job = the box itself in mask coordinates.
+// counts[0] = jobs written (<= capacity), counts[1] = status bits: 1 an image's box maths raised ValueError
+// (nbox == -2), 2 more jobs than `capacity` (extra ones dropped), 4 a box or mapped crop with w or h <= 0 (PIL raises
+// in the reference; the job is kept with its size zeroed so that crop / paste skip it), counts[2] = total requested.
+// chunk_counts[c] = number of valid jobs in [c*chunk, (c+1)*chunk).
+__global__ void lt_build_jobs_kernel(const int* __restrict__ boxes, const int* __restrict__ nbox, int B, int S_h,
+                                     int S_w, int src_h, int src_w, const int* __restrict__ orig_sizes,
+                                     int* __restrict__ crop_jobs, int* __restrict__ paste_jobs, int capacity,
+                                     int* __restrict__ counts, int chunk, int n_chunks, int* __restrict__ chunk_counts) {
+    extern __shared__ int offs[];  // [B + 1] exclusive prefix of the per-image job counts
+    __shared__ int status;
+    if (threadIdx.x == 0) status = 0;
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int n = nbox[b];
+        if (n == -2) atomicOr(&status, 1);
+        offs[b + 1] = n > 0 ? (n > LT_MAXBIG ? LT_MAXBIG : n) : 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        offs[0] = 0;
+        for (int b = 0; b < B; ++b) offs[b + 1] += offs[b];
+    }
+    __syncthreads();
+    const int total = offs[B];
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int n = offs[b + 1] - offs[b];
+        const int H0 = orig_sizes ? orig_sizes[2 * b] : src_h, W0 = orig_sizes ? orig_sizes[2 * b + 1] : src_w;
+        const double ws = __ddiv_rn((double)W0, (double)S_w), hs = __ddiv_rn((double)H0, (double)S_h);
+        for (int i = 0; i < n; ++i) {
+            const int slot = offs[b] + i;
+            if (slot >= capacity) break;
+            const int* bb = boxes + ((size_t)b * LT_MAXBIG + i) * 4;
+            int x = (int)__dmul_rn((double)bb[0], ws), y = (int)__dmul_rn((double)bb[1], hs);
+            int w = (int)__dmul_rn((double)bb[2], ws), h = (int)__dmul_rn((double)bb[3], hs);
+            int pw = bb[2], ph = bb[3];
+            if (w <= 0 || h <= 0 || pw <= 0 || ph <= 0) {
+                atomicOr(&status, 4);
+                w = h = pw = ph = 0;
+            }
+            int* cj = crop_jobs + (size_t)slot * 5;
+            cj[0] = b, cj[1] = x, cj[2] = y, cj[3] = w, cj[4] = h;
+            int* pj = paste_jobs + (size_t)slot * 6;
+            pj[0] = b, pj[1] = bb[0], pj[2] = bb[1], pj[3] = pw, pj[4] = ph, pj[5] = i;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int kept = total < capacity ? total : capacity;
+        counts[0] = kept;
+        counts[1] = status | (total > capacity ? 2 : 0);
+        counts[2] = total;
+        for (int c = 0; c < n_chunks; ++c) {
+            const int left = kept - c * chunk;
+            chunk_counts[c] = left < 0 ? 0 : (left > chunk ? chunk : left);
+        }
+    }
+}
+
+int lt_build_jobs(const int* boxes, const int* nbox, int B, int S_h, int S_w, int src_h, int src_w,
+                  const int* orig_sizes, int* crop_jobs, int* paste_jobs, int capacity, int* counts, int chunk,
+                  int* chunk_counts, cudaStream_t stream) {
+    UCOD_REQUIRE(boxes && nbox && crop_jobs && paste_jobs && counts && chunk_counts, "lt_build_jobs: null argument");
+    UCOD_REQUIRE(B > 0 && B <= 8192 && S_h > 0 && S_w > 0 && capacity > 0 && chunk > 0 &&
+                     (orig_sizes != nullptr || (src_h > 0 && src_w > 0)),
+                 "lt_build_jobs: bad geometry");
+    const int n_chunks = ceil_div(capacity, chunk);
+    ProfScope ps(KC_CCL, stream, 0.0);
+    lt_build_jobs_kernel<<<1, 256, (size_t)(B + 1) * sizeof(int), stream>>>(boxes, nbox, B, S_h, S_w, src_h, src_w,
+                                                                            orig_sizes, crop_jobs, paste_jobs,
+                                                                            capacity, counts, chunk, n_chunks,
+                                                                            chunk_counts);
+    UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 

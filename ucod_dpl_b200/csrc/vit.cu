@@ -23,9 +23,10 @@ namespace ucod {
 // ------------------------------------------------------------------------------------------------
 template <typename TIn>
 __global__ void im2col_patch_kernel(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int Hh, int Ww,
-                                    int p, int Kpad, float3 mean, float3 inv_std) {
+                                    int p, int Kpad, float3 mean, float3 inv_std, const int* __restrict__ batch_dev) {
     const int gw = Ww / p, gh = Hh / p;
     const int b = blockIdx.y, py = blockIdx.x;
+    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     const int kvalid = 3 * p * p;
     __nv_bfloat16* orow = out + ((size_t)b * gh * gw + (size_t)py * gw) * Kpad;
     const int wused = gw * p;
@@ -54,11 +55,13 @@ __global__ void im2col_patch_kernel(const TIn* __restrict__ img, __nv_bfloat16* 
 // (the direct version writes 2p-byte fragments: 0.36 ms per 64 images @518^2, 7 % of the HBM roofline).
 template <typename TIn>
 __global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int Hh,
-                                         int Ww, int p, int Kpad, float3 mean, float3 inv_std) {
+                                         int Ww, int p, int Kpad, float3 mean, float3 inv_std,
+                                         const int* __restrict__ batch_dev) {
     extern __shared__ __align__(16) uint8_t im2col_smem[];
     __nv_bfloat16* tile = reinterpret_cast<__nv_bfloat16*>(im2col_smem);
     const int gw = Ww / p, gh = Hh / p;
     const int b = blockIdx.y, py = blockIdx.x;
+    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     const int kvalid = 3 * p * p;
     const int wused = gw * p;
     for (int idx = threadIdx.x; idx < gw * (Kpad - kvalid); idx += blockDim.x) {
@@ -119,8 +122,9 @@ __global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloa
 
 // x[b*T + 0, :] = cls + pos[0, :]
 __global__ void cls_init_kernel(float* __restrict__ x, const float* __restrict__ cls, const float* __restrict__ pos,
-                                int T, int D) {
+                                int T, int D, const int* __restrict__ batch_dev) {
     const int b = blockIdx.x;
+    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     for (int d = threadIdx.x; d < D; d += blockDim.x) x[(size_t)b * T * D + d] = cls[d] + pos[d];
 }
 
@@ -130,8 +134,12 @@ __global__ void cls_init_kernel(float* __restrict__ x, const float* __restrict__
 template <int D>
 __global__ void layernorm_bf16_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                       const float* __restrict__ bsh, __nv_bfloat16* __restrict__ y, int rows,
-                                      float eps) {
+                                      float eps, const int* __restrict__ rows_dev, int rows_per) {
     constexpr int V = D / 128;  // float4 per lane
+    if (rows_dev != nullptr) {  // device-side row count (capacity `rows`)
+        const int rd = __ldg(rows_dev) * rows_per;
+        rows = rd < rows ? rd : rows;
+    }
     // rows are walked from the end: the GEMM that produced x finished with its last rows (still in the 126 MB L2),
     // and the GEMM that consumes y starts with the first rows, which are then the ones written last
     const int row = rows - 1 - (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5));
@@ -172,12 +180,14 @@ __global__ void layernorm_bf16_kernel(const float* __restrict__ x, const float* 
 // ------------------------------------------------------------------------------------------------
 __global__ void cls_row_attention_kernel(const __nv_bfloat16* __restrict__ xn, const __nv_bfloat16* __restrict__ wq,
                                          const float* __restrict__ bq, const float* __restrict__ keys_all,
-                                         float* __restrict__ attn, int T, int D, int H, float scale) {
+                                         float* __restrict__ attn, int T, int D, int H, float scale,
+                                         const int* __restrict__ batch_dev) {
     extern __shared__ float sm[];
     float* q = sm;            // 64
     float* logits = sm + 64;  // T
     __shared__ float red[32];
     const int b = blockIdx.x / H, h = blockIdx.x % H;
+    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     const __nv_bfloat16* xr = xn + (size_t)b * T * D;
     for (int d = warp; d < 64; d += nw) {
@@ -300,17 +310,17 @@ int vit_workspace_bytes(void* handle, int B, int img_h, int img_w, size_t* out) 
 }
 
 static int layernorm(const float* x, const float* w, const float* b, __nv_bfloat16* y, int rows, float eps,
-                     cudaStream_t s) {
+                     cudaStream_t s, const int* rows_dev = nullptr, int rows_per = 1) {
     const int wpb = 8;
-    ProfScope ps(KC_LAYERNORM, s, (double)rows * 768 * 6);
-    layernorm_bf16_kernel<768><<<ceil_div(rows, wpb), wpb * 32, 0, s>>>(x, w, b, y, rows, eps);
+    ProfScope ps(KC_LAYERNORM, s, rows_dev ? 0.0 : (double)rows * 768 * 6);
+    layernorm_bf16_kernel<768><<<ceil_div(rows, wpb), wpb * 32, 0, s>>>(x, w, b, y, rows, eps, rows_dev, rows_per);
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
 
 int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h, int img_w, const float* pos_emb,
              void* workspace, size_t ws_bytes, float* keys_f32, void* keys_bf16, float* cls_attn, int keep_cls,
-             cudaStream_t stream) {
+             cudaStream_t stream, const int* batch_dev) {
     UCOD_REQUIRE(handle && images && pos_emb && workspace, "ucod_vit_keys: null argument");
     VitModel* m = static_cast<VitModel*>(handle);
     const ucod_vit_cfg& c = m->cfg;
@@ -328,7 +338,7 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
     const float3 mean = make_float3(0.485f, 0.456f, 0.406f);
     const float3 istd = make_float3(1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f);
     dim3 g_im(gh, B);
-    prof_pre(KC_EMBED, stream, (double)B * 3 * img_h * img_w * (image_dtype ? 1 : 4) + (double)B * P * c.patch_kpad * 2);
+    prof_pre(KC_EMBED, stream, batch_dev ? 0.0 : (double)B * 3 * img_h * img_w * (image_dtype ? 1 : 4) + (double)B * P * c.patch_kpad * 2);
     const size_t im_smem = (size_t)gw * c.patch_kpad * sizeof(__nv_bfloat16);
     if (im_smem <= 200 * 1024 && c.patch_kpad % 8 == 0) {
         static bool im_configured = false;
@@ -341,21 +351,22 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
         }
         if (image_dtype == 0)
             im2col_patch_smem_kernel<float><<<g_im, 512, im_smem, stream>>>(static_cast<const float*>(images), w.patches,
-                                                                           B, img_h, img_w, p, c.patch_kpad, mean, istd);
+                                                                           B, img_h, img_w, p, c.patch_kpad, mean, istd, batch_dev);
         else
             im2col_patch_smem_kernel<uint8_t><<<g_im, 512, im_smem, stream>>>(
-                static_cast<const uint8_t*>(images), w.patches, B, img_h, img_w, p, c.patch_kpad, mean, istd);
+                static_cast<const uint8_t*>(images), w.patches, B, img_h, img_w, p, c.patch_kpad, mean, istd, batch_dev);
     } else if (image_dtype == 0)
         im2col_patch_kernel<float><<<g_im, 256, 0, stream>>>(static_cast<const float*>(images), w.patches, B, img_h,
-                                                             img_w, p, c.patch_kpad, mean, istd);
+                                                             img_w, p, c.patch_kpad, mean, istd, batch_dev);
     else
         im2col_patch_kernel<uint8_t><<<g_im, 256, 0, stream>>>(static_cast<const uint8_t*>(images), w.patches, B,
-                                                               img_h, img_w, p, c.patch_kpad, mean, istd);
+                                                               img_h, img_w, p, c.patch_kpad, mean, istd, batch_dev);
     prof_post(KC_EMBED, stream);
     UCOD_CHECK_CUDA(cudaGetLastError());
     {
         GemmEpi ep;
         ep.mode = EPI_PATCH;
+        ep.m_dev = batch_dev, ep.m_per = P;
         ep.bias = m->patch_b;
         ep.pos = pos_emb;
         ep.out = w.x;
@@ -366,8 +377,8 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
             return rc;
     }
     {
-        ProfScope ps(KC_EMBED, stream, (double)B * D * 4);
-        cls_init_kernel<<<B, 256, 0, stream>>>(w.x, m->cls, pos_emb, T, D);
+        ProfScope ps(KC_EMBED, stream, batch_dev ? 0.0 : (double)B * D * 4);
+        cls_init_kernel<<<B, 256, 0, stream>>>(w.x, m->cls, pos_emb, T, D, batch_dev);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
 
@@ -375,10 +386,11 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
     const float scale = 0.125f;  // 1/sqrt(64)
     for (int l = 0; l + 1 < c.layers; ++l) {
         const ucod_vit_layer& L = m->layers[l];
-        if (int rc = layernorm(w.x, L.ln1_w, L.ln1_b, w.xn, M, c.ln_eps, stream)) return rc;
+        if (int rc = layernorm(w.x, L.ln1_w, L.ln1_b, w.xn, M, c.ln_eps, stream, batch_dev, T)) return rc;
         {
             GemmEpi ep;
             ep.mode = EPI_BIAS_BF16;
+            ep.m_dev = batch_dev, ep.m_per = T;
             ep.bias = L.b_qkv;
             ep.out = w.qkv;
             ep.ld_out = 3 * D;
@@ -390,20 +402,23 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
             a.batch = B, a.heads = H, a.tokens_q = T, a.tokens_kv = T;
             a.ld_q = 3 * D, a.ld_kv = 3 * D, a.ld_ctx = D;
             a.scale = scale;
+            a.batch_dev = batch_dev;
             if (int rc = launch_attention(a, stream)) return rc;
         }
         {
             GemmEpi ep;
             ep.mode = EPI_RESID_F32;
+            ep.m_dev = batch_dev, ep.m_per = T;
             ep.bias = L.b_o;
             ep.out = w.x;
             ep.ld_out = D;
             if (int rc = launch_gemm_bf16(w.ctx, D, L.w_o, D, M, D, D, ep, stream)) return rc;
         }
-        if (int rc = layernorm(w.x, L.ln2_w, L.ln2_b, w.xn, M, c.ln_eps, stream)) return rc;
+        if (int rc = layernorm(w.x, L.ln2_w, L.ln2_b, w.xn, M, c.ln_eps, stream, batch_dev, T)) return rc;
         {
             GemmEpi ep;
             ep.mode = EPI_BIAS_GELU_BF16;
+            ep.m_dev = batch_dev, ep.m_per = T;
             ep.bias = L.b_fc1;
             ep.out = w.h;
             ep.ld_out = c.mlp_dim;
@@ -412,6 +427,7 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
         {
             GemmEpi ep;
             ep.mode = EPI_RESID_F32;
+            ep.m_dev = batch_dev, ep.m_per = T;
             ep.bias = L.b_fc2;
             ep.out = w.x;
             ep.ld_out = D;
@@ -421,12 +437,13 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
 
     // ---- last layer: LN1 + key projection only ----
     const ucod_vit_layer& L = m->layers[c.layers - 1];
-    if (int rc = layernorm(w.x, L.ln1_w, L.ln1_b, w.xn, M, c.ln_eps, stream)) return rc;
+    if (int rc = layernorm(w.x, L.ln1_w, L.ln1_b, w.xn, M, c.ln_eps, stream, batch_dev, T)) return rc;
     const __nv_bfloat16* wk = static_cast<const __nv_bfloat16*>(L.w_qkv) + (size_t)D * D;
     const float* bk = L.b_qkv + D;
     if (keys_f32 || keys_bf16) {
         GemmEpi ep;
         ep.mode = EPI_KEYS;
+        ep.m_dev = batch_dev, ep.m_per = T;
         ep.bias = bk;
         ep.out = keys_f32;
         ep.out2 = keys_bf16;
@@ -439,6 +456,7 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
         // all-token fp32 keys (CLS included) for the CLS-row softmax
         GemmEpi ep;
         ep.mode = EPI_BIAS_F32;
+        ep.m_dev = batch_dev, ep.m_per = T;
         ep.bias = bk;
         ep.out = w.keys_all;
         ep.ld_out = D;
@@ -448,7 +466,7 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
         {
             ProfScope ps(KC_EMBED, stream, (double)B * T * D * 4);
             cls_row_attention_kernel<<<B * H, 256, smem, stream>>>(w.xn, static_cast<const __nv_bfloat16*>(L.w_qkv),
-                                                                   L.b_qkv, w.keys_all, cls_attn, T, D, H, scale);
+                                                                   L.b_qkv, w.keys_all, cls_attn, T, D, H, scale, batch_dev);
         }
         UCOD_CHECK_CUDA(cudaGetLastError());
     }

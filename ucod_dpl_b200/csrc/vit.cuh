@@ -11,6 +11,6 @@ int vit_destroy(void* handle);
 int vit_workspace_bytes(void* handle, int B, int img_h, int img_w, size_t* out);
 int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h, int img_w, const float* pos_emb,
              void* workspace, size_t ws_bytes, float* keys_f32, void* keys_bf16, float* cls_attn, int keep_cls,
-             cudaStream_t stream);
+             cudaStream_t stream, const int* batch_dev = nullptr);
 
 }  // namespace ucod

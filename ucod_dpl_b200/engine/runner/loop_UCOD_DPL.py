@@ -26,11 +26,59 @@ def resize_bbox(bbox, original_width, original_height, new_width, new_height):
     return [int(x * ws), int(y * hs), int(w * ws), int(h * hs)]
 
 
+class LookTwiceResult:
+    """What one Look-Twice pass leaves on the device: nothing here has synchronised with the host.
+
+    final     float [N,S,S] in [0,1] — the reference's `preds_up` after the second look (loop_UCOD_DPL.py:352)
+    first     uint8 [N,S,S] {0,1} — the first-look mask (`preds_up` of process_preds)
+    boxes / nbox   int32 [N,128,4] / [N] as written by `ucod_lt_boxes` (nbox -1 = None, -2 = ValueError)
+    counts    int32 [4] (second looks kept, status bits, second looks requested, 0) or None when Look-Twice is off
+    `check()` is the one place that reads anything back (a few dozen bytes): it raises what the reference would have
+    raised for this batch, and — if the batch needed more second-look chunks than were enqueued ahead of time — runs
+    the missing chunks and refreshes `final` (see `LookTwiceEvaluator.look_twice_device`).
+    `bboxes` converts the box table to the reference's per-image lists (also a host read)."""
+
+    def __init__(self, final, first, boxes, nbox, counts, err, canvas=None, resume=None):
+        self.final, self.first, self.boxes, self.nbox, self.counts, self.err = final, first, boxes, nbox, counts, err
+        self.canvas, self._resume = canvas, resume
+        self._lists = None
+
+    def check(self) -> None:
+        nb = self.nbox.cpu()
+        if bool((nb == -2).any()):
+            raise ValueError("math domain error")  # expand_bbox: sqrt of a negative scale (reference raises too)
+        if self.counts is not None:
+            kept, status, wanted, _ = self.counts.cpu().tolist()
+            if status & 4:
+                raise ValueError("height and width must be > 0")  # PIL raises in the reference
+            if status & 2:
+                raise ops.UcodError(f"Look-Twice: {wanted} second looks requested, capacity {kept}; raise "
+                                    "`max_looks_per_image`")
+            if self._resume is not None:
+                self._resume(self, kept)
+                self._resume = None
+        if self.err is not None and int(self.err.item()):
+            raise ops.UcodError("Look-Twice resampling: a crop or box is outside the supported scale range")
+
+    @property
+    def bboxes(self):
+        if self._lists is None:
+            nb = self.nbox.cpu().tolist()
+            bx = self.boxes.cpu()
+            self._lists = [None if n < 0 else bx[b, :n].tolist() for b, n in enumerate(nb)]
+        return self._lists
+
+
 class LookTwiceEvaluator:
-    """First look (ViT keys -> decoder@fs -> mask@S) -> boxes -> second look on the crops -> pasted mask."""
+    """First look (ViT keys -> decoder@fs -> mask@S) -> boxes -> second look on the crops -> pasted mask.
+
+    The whole flow stays on the device: box lists become crop / paste job tables in a kernel (`ucod_lt_build_jobs`),
+    the second ViT + decoder pass runs on fixed-size chunks of that table whose valid length is read by the kernels
+    themselves (`*_dyn` entry points), and pastes resolve their order per pixel.  The host only enqueues."""
 
     def __init__(self, extractor: VitKeyExtractor, model, image_size, feature_size: int = 68,
-                 look_twice_th: float = 0.15, expand_type: str = "dynamic", look_twice: bool = True):
+                 look_twice_th: float = 0.15, expand_type: str = "dynamic", look_twice: bool = True,
+                 max_looks_per_image: int = 4):
         self.extractor = extractor
         self.model = model
         self.img_size = tuple(image_size)
@@ -38,27 +86,26 @@ class LookTwiceEvaluator:
         self.look_twice_th = float(look_twice_th)
         self.expand_type = expand_type
         self.enabled = look_twice
+        self.max_looks_per_image = int(max_looks_per_image)
         self.patch = extractor.spec.patch
+        # second-look chunks enqueued ahead of time (see look_twice_device); adapts to what recent batches needed
+        self._recent_chunks: list = []
 
     # ---- reference-compatible pieces ----
     @torch.no_grad()
     def process_preds(self, preds: torch.Tensor, label_tensor=None):
         """preds [B,1,fs,fs] logits (CUDA).  B = 1: returns (preds_up [1,S,S] float, bboxes | None) exactly like the
-        reference; B > 1: returns (preds_up [B,S,S] float, list of per-image bboxes | None)."""
+        reference; B > 1: returns (preds_up [B,S,S] float, list of per-image bboxes | None).  Host lists mean a
+        device->host read; the batched pipeline (`look_twice_device`) never calls this."""
         h, w = self.img_size
         mask = ops.upsample_bilinear(preds[:, 0], (h, w), binarize=True)
         boxes, nbox, status, _ = ops.lt_boxes(mask, self.look_twice_th, self.expand_type)
-        nb = nbox.cpu().tolist()
-        bx = boxes.cpu()
-        out: List[Optional[list]] = []
-        for b, n in enumerate(nb):
-            if n == -2:
-                raise ValueError("math domain error")  # expand_bbox: sqrt of a negative scale (reference raises too)
-            out.append(None if n < 0 else bx[b, :n].tolist())
+        res = LookTwiceResult(None, mask, boxes, nbox, None, None)
+        res.check()
         up = mask.float()
         if preds.shape[0] == 1:
-            return up, out[0]
-        return up, out
+            return up, res.bboxes[0]
+        return up, res.bboxes
 
     def expand_bbox(self, mask, bbox, img_width, img_height, expand_type="const", scale=1.3):
         """Host-side statement of loop_UCOD_DPL.py:399-417 for API parity (the device path computes the same in
@@ -90,11 +137,12 @@ class LookTwiceEvaluator:
     @torch.no_grad()
     def look_twice_batch(self, originals: torch.Tensor, bboxes_per_image, masks_u8: torch.Tensor,
                          layout: str = "CHW", orig_sizes=None) -> torch.Tensor:
-        """originals: uint8 RGB originals of the batch ([N,3,H0,W0] or [N,H0,W0,3]); bboxes_per_image: list (len N)
-        of box lists or None; masks_u8 [N,S,S] {0,1}.  Returns new masks float [N,S,S] in [0,1]
-        (loop_UCOD_DPL.py:326-352 for every image that has boxes; others keep their mask).
-        orig_sizes (optional, [N,2] (h, w)): `originals` is a zero-padded canvas of differently sized images
-        (`pack_padded`); boxes are mapped with each image's own size and crops past an image read 0 like PIL's."""
+        """Second look for HOST box lists (the reference's `look_twice` signature, batched): originals uint8 RGB
+        ([N,3,H0,W0] or [N,H0,W0,3]); bboxes_per_image: list (len N) of box lists or None; masks_u8 [N,S,S] {0,1}.
+        Returns new masks float [N,S,S] in [0,1] (loop_UCOD_DPL.py:326-352 for every image that has boxes; others keep
+        their mask).  orig_sizes (optional, [N,2] (h, w)): `originals` is a zero-padded canvas of differently sized
+        images (`pack_padded`); boxes are mapped with each image's own size and crops past an image read 0 like PIL's.
+        The device-resident pipeline is `look_twice_device`; this entry point exists for callers that hold lists."""
         ih, iw = self.img_size
         dev = masks_u8.device
         if layout == "CHW":
@@ -123,26 +171,76 @@ class LookTwiceEvaluator:
             g = (ih // self.patch, iw // self.patch)
             fg, _, _ = self.model.decoder.forward_tokens(k16, g, g, want_bg=False)  # raw 37^2 grid (:343-345)
             ops.paste_bicubic(fg[:, 0], pj, canvas)
-        return canvas.float() / 255.0
+        return ops.to_tensor_normalize(canvas[:, None])[:, 0]
 
     @torch.no_grad()
-    def __call__(self, images: torch.Tensor, originals: torch.Tensor | None = None, layout: str = "CHW",
-                 orig_sizes=None):
-        """images: network-size inputs [N,3,S,S] (uint8 raw or fp32 normalised); originals: the original-resolution
-        uint8 images the crops are taken from (defaults to `images` when they are uint8; with `orig_sizes` a
-        zero-padded canvas of ragged images).  Returns (final masks float [N,S,S] in [0,1], per-image bboxes)."""
+    def look_twice_device(self, images: torch.Tensor, originals: torch.Tensor | None = None, layout: str = "CHW",
+                          orig_sizes=None, first_logits: torch.Tensor | None = None) -> LookTwiceResult:
+        """The whole of loop_UCOD_DPL.py:297-313 for a batch, enqueued without a single host synchronisation.
+        images: network-size inputs [N,3,S,S] (uint8 raw or fp32 normalised); originals: the original-resolution
+        uint8 images the crops are taken from (defaults to `images` when they are uint8; with `orig_sizes` [N,2] a
+        zero-padded canvas of ragged images); first_logits: optional [N,1,fs,fs] logits that replace the first-look
+        prediction as `process_preds`' input (the first look still runs; used to plant objects in benchmarks).
+
+        The second look runs on chunks of N crops whose valid length the kernels read on the device.  How many chunks
+        are enqueued ahead of time follows what the last batches needed (an empty chunk still costs ~60 early-exit
+        launches); a batch that needs more is completed by `LookTwiceResult.check()`, which every consumer calls when
+        it reads the masks back — results never depend on the guess, only the launch count does."""
         fg = self.first_look(images)
-        up, bboxes = self.process_preds(fg)
-        if images.shape[0] == 1:
-            bboxes = [bboxes]
-        if not self.enabled or all(b is None for b in bboxes):
-            return up, bboxes
+        if first_logits is not None:
+            fg = first_logits
+        ih, iw = self.img_size
+        mask = ops.upsample_bilinear(fg[:, 0], (ih, iw), binarize=True)
+        boxes, nbox, _, _ = ops.lt_boxes(mask, self.look_twice_th, self.expand_type)
+        canvas = ops.mask_scale_u8(mask, 255)
+        if not self.enabled:
+            return LookTwiceResult(ops.to_tensor_normalize(canvas[:, None])[:, 0], mask, boxes, nbox, None, None)
         if originals is None:
             if images.dtype != torch.uint8:
                 raise ValueError("originals (uint8) are required when `images` are already normalised")
             originals = images
-        mask_u8 = up.to(torch.uint8)
-        return self.look_twice_batch(originals, bboxes, mask_u8, layout=layout, orig_sizes=orig_sizes), bboxes
+        N = images.shape[0]
+        H0, W0 = originals.shape[-2:] if layout == "CHW" else originals.shape[1:3]
+        chunk = N
+        capacity = chunk * self.max_looks_per_image
+        sizes = None if orig_sizes is None else torch.as_tensor(orig_sizes)
+        crop, paste, counts, chunks = ops.lt_build_jobs(boxes, nbox, (ih, iw), (H0, W0), sizes, capacity=capacity,
+                                                        chunk=chunk)
+        err = torch.zeros(1, device=mask.device, dtype=torch.int32)
+        g = (ih // self.patch, iw // self.patch)
+        out_cap = int(math.ceil(1.5 * max(ih, iw)))  # expand_bbox grows a box by at most sqrt(2)
+
+        def run_chunk(c):
+            n_c = chunks[c:c + 1]
+            crops = ops.roi_crop_resize_dyn(originals, crop[c * chunk:(c + 1) * chunk], n_c, (ih, iw), layout=layout,
+                                            err=err)
+            _, k16, _ = self.extractor.keys(crops, want_f32=False, want_bf16=True, count_dev=n_c)
+            fg2, _, _ = self.model.decoder.forward_tokens(k16, g, g, want_bg=False, count_dev=n_c)  # :343-345
+            ops.paste_bicubic_dyn(fg2[:, 0], paste, c * chunk, n_c, counts[0:1], canvas, out_cap, err=err)
+
+        ahead = min(self.max_looks_per_image, max(self._recent_chunks)) if self._recent_chunks else self.max_looks_per_image
+        for c in range(ahead):
+            run_chunk(c)
+        final = ops.to_tensor_normalize(canvas[:, None])[:, 0]  # / 255 (:352)
+
+        def resume(res, kept):  # called from check(): host knows the count now
+            need = (kept + chunk - 1) // chunk
+            self._recent_chunks = (self._recent_chunks + [need])[-8:]
+            if need > ahead:
+                for c in range(ahead, need):
+                    run_chunk(c)
+                res.final.copy_(ops.to_tensor_normalize(canvas[:, None])[:, 0])
+
+        return LookTwiceResult(final, mask, boxes, nbox, counts, err, canvas=canvas, resume=resume)
+
+    @torch.no_grad()
+    def __call__(self, images: torch.Tensor, originals: torch.Tensor | None = None, layout: str = "CHW",
+                 orig_sizes=None):
+        """Returns (final masks float [N,S,S] in [0,1], per-image bboxes) like the reference's loop body; the box
+        lists and the error checks are read back once, after everything has been enqueued."""
+        res = self.look_twice_device(images, originals, layout, orig_sizes)
+        res.check()
+        return res.final, res.bboxes
 
 
 class TrainLoop:

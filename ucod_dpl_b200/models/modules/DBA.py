@@ -37,14 +37,15 @@ class RevDecoder(nn.Module):
             self._packed = (tag, w.detach().reshape(w.shape[0], w.shape[1]).to(torch.bfloat16).contiguous())
         return self._packed[1]
 
-    def forward_tokens(self, keys_bf16: torch.Tensor, grid_in, grid_out, want_bg=True, want_ortho=False):
+    def forward_tokens(self, keys_bf16: torch.Tensor, grid_in, grid_out, want_bg=True, want_ortho=False,
+                       count_dev=None):
         """Fused path: token-major bf16 keys on `grid_in`, logits on `grid_out` (the bilinear feature upsample of
         loop_UCOD_DPL.py:153,305 is folded into the decoder)."""
         return ops.decoder_forward(
             keys_bf16, grid_in, grid_out, self._w_dec_bf16(), self.decoupling.bias.detach().float(),
             self.learnable_embedding.detach().float().contiguous(), self.conv_out_fg.weight.detach().reshape(-1),
             self.conv_out_fg.bias.detach(), self.conv_out_bg.weight.detach().reshape(-1),
-            self.conv_out_bg.bias.detach(), want_bg=want_bg, want_ortho=want_ortho)
+            self.conv_out_bg.bias.detach(), want_bg=want_bg, want_ortho=want_ortho, count_dev=count_dev)
 
     def calc_orthogonal_loss(self, feature_1, feature_2, weight=1.0):
         raise NotImplementedError("the orthogonality loss is fused into forward() (Gram identity, csrc/decoder.cu)")

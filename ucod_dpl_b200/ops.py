@@ -42,8 +42,9 @@ def features_to_tokens_bf16(features: torch.Tensor) -> torch.Tensor:
 
 
 def decoder_forward(keys_bf16: torch.Tensor, grid_in, grid_out, w_dec_bf16, b_dec, emb, w_fg, b_fg, w_bg, b_bg, *,
-                    want_bg: bool = True, want_ortho: bool = False):
-    """keys_bf16 [B, gin_h*gin_w, dim] -> (fg [B,1,oh,ow], bg | None, ortho scalar tensor | None)."""
+                    want_bg: bool = True, want_ortho: bool = False, count_dev: torch.Tensor | None = None):
+    """keys_bf16 [B, gin_h*gin_w, dim] -> (fg [B,1,oh,ow], bg | None, ortho scalar tensor | None).
+    count_dev: optional int32 device scalar, number of leading images to process (eval only, read on the device)."""
     _lib.require_cuda(keys_bf16)
     if keys_bf16.dtype != torch.bfloat16 or not keys_bf16.is_contiguous():
         raise UcodError("decoder_forward expects contiguous bf16 token-major keys")
@@ -62,8 +63,16 @@ def decoder_forward(keys_bf16: torch.Tensor, grid_in, grid_out, w_dec_bf16, b_de
     ws = _ws(need, dev)
     wp, wn = _aligned(ws)
     with torch.cuda.device(dev):
-        _lib.call("ucod_decoder_fwd", ptr(keys_bf16), B, dim, gh, gw, oh, ow, ptr(w_dec_bf16), ptr(b_dec), ptr(emb),
-                  ptr(w_fg), ptr(b_fg), ptr(w_bg), ptr(b_bg), ptr(fg), ptr(bg), ptr(ortho), wp, wn, stream_ptr(dev))
+        if count_dev is None:
+            _lib.call("ucod_decoder_fwd", ptr(keys_bf16), B, dim, gh, gw, oh, ow, ptr(w_dec_bf16), ptr(b_dec),
+                      ptr(emb), ptr(w_fg), ptr(b_fg), ptr(w_bg), ptr(b_bg), ptr(fg), ptr(bg), ptr(ortho), wp, wn,
+                      stream_ptr(dev))
+        else:
+            if want_ortho:
+                raise UcodError("decoder_forward: count_dev is an eval-only option (no orthogonality loss)")
+            _lib.call("ucod_decoder_fwd_dyn", ptr(keys_bf16), B, ptr(count_dev), dim, gh, gw, oh, ow, ptr(w_dec_bf16),
+                      ptr(b_dec), ptr(emb), ptr(w_fg), ptr(b_fg), ptr(w_bg), ptr(b_bg), ptr(fg), ptr(bg), wp, wn,
+                      stream_ptr(dev))
     return fg, bg, ortho
 
 
@@ -171,7 +180,86 @@ def roi_crop_resize(images_u8: torch.Tensor, jobs: torch.Tensor, out_size, layou
     with torch.cuda.device(dev):
         _lib.call("ucod_roi_crop_resize", ptr(images_u8), N, H0, W0, _i64(s_img), _i64(s_ch), _i64(s_row), _i64(s_px),
                   ptr(jobs), n, max_h, ptr(out), oh, ow, wp, wn, ptr(err), stream_ptr(dev))
+    if int(err.item()) & 1:  # (this wrapper already synchronised for max_h; the *_dyn path defers the check)
+        raise UcodError("roi_crop_resize: a crop is down-scaled by more than ~19x, beyond this call's tap table; "
+                        "use roi_crop_resize_dyn (no limit)")
     return out
+
+
+def lt_build_jobs(boxes: torch.Tensor, nbox: torch.Tensor, mask_size, src_size=None, orig_sizes=None, *, capacity: int,
+                  chunk: int):
+    """Device-side Look-Twice job tables (no host synchronisation): boxes int32 [B,128,4], nbox int32 [B] from
+    `lt_boxes` -> (crop_jobs int32 [capacity,5], paste_jobs int32 [capacity,6], counts int32 [4] =
+    (jobs kept, status bits, jobs requested, 0), chunk_counts int32 [ceil(capacity / chunk)])."""
+    _lib.require_cuda(boxes, nbox)
+    B = nbox.shape[0]
+    dev = boxes.device
+    sh, sw = mask_size
+    if orig_sizes is not None:
+        orig_sizes = orig_sizes.to(device=dev, dtype=torch.int32).contiguous()
+        h0 = w0 = 0
+    else:
+        h0, w0 = src_size
+    crop = torch.zeros(capacity, 5, device=dev, dtype=torch.int32)
+    paste = torch.zeros(capacity, 6, device=dev, dtype=torch.int32)
+    counts = torch.zeros(4, device=dev, dtype=torch.int32)
+    chunks = torch.zeros((capacity + chunk - 1) // chunk, device=dev, dtype=torch.int32)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_lt_build_jobs", ptr(boxes), ptr(nbox), B, sh, sw, int(h0), int(w0), ptr(orig_sizes), ptr(crop),
+                  ptr(paste), capacity, ptr(counts), chunk, ptr(chunks), stream_ptr(dev))
+    return crop, paste, counts, chunks
+
+
+def roi_crop_resize_dyn(images_u8: torch.Tensor, jobs: torch.Tensor, njobs_dev: torch.Tensor, out_size,
+                        layout: str = "CHW", err: torch.Tensor | None = None) -> torch.Tensor:
+    """`roi_crop_resize` for a job slice whose length is a device scalar (`njobs_dev`, int32, <= jobs.shape[0]).
+    No host synchronisation; `err` (int32 [1], accumulated, bit 0 = tap table overflow) is the caller's to check."""
+    _lib.require_cuda(images_u8, jobs, njobs_dev)
+    if images_u8.dtype != torch.uint8 or jobs.dtype != torch.int32 or not jobs.is_contiguous():
+        raise UcodError("roi_crop_resize_dyn expects uint8 images and a contiguous int32 job table")
+    if layout == "CHW":
+        N, _, H0, W0 = images_u8.shape
+        s_img, s_ch, s_row, s_px = images_u8.stride()
+    else:
+        N, H0, W0, _ = images_u8.shape
+        s_img, s_row, s_px, s_ch = images_u8.stride()
+    cap = jobs.shape[0]
+    oh, ow = out_size
+    dev = images_u8.device
+    out = torch.empty(cap, 3, oh, ow, device=dev, dtype=torch.uint8)
+    if err is None:
+        err = torch.zeros(1, device=dev, dtype=torch.int32)
+    lib = _lib.load()
+    lib.ucod_roi_crop_resize_dyn_workspace_bytes.restype = _u64
+    ws = _ws(lib.ucod_roi_crop_resize_dyn_workspace_bytes(cap, H0, W0, oh, ow), dev)
+    wp, wn = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_roi_crop_resize_dyn", ptr(images_u8), N, H0, W0, _i64(s_img), _i64(s_ch), _i64(s_row),
+                  _i64(s_px), ptr(jobs), cap, ptr(njobs_dev), ptr(out), oh, ow, wp, wn, ptr(err), stream_ptr(dev))
+    return out
+
+
+def paste_bicubic_dyn(logits: torch.Tensor, all_jobs: torch.Tensor, first_index: int, njobs_dev: torch.Tensor,
+                      n_all_dev: torch.Tensor, mask_u8: torch.Tensor, out_cap: int,
+                      err: torch.Tensor | None = None) -> None:
+    """Paste the slice [first_index, first_index + njobs_dev) of an image-major, rank-ascending paste table
+    (`lt_build_jobs`) into mask uint8 [N,S,S]; logits fp32 [capacity,g,g] are the slice's second-look predictions.
+    A pixel takes the value of the last job of its image that covers it, as the reference's sequential pastes do."""
+    _lib.require_cuda(logits, all_jobs, njobs_dev, n_all_dev, mask_u8)
+    logits = logits.float().contiguous()
+    cap, gh, gw = logits.shape
+    N, Sh, Sw = mask_u8.shape
+    dev = logits.device
+    if err is None:
+        err = torch.zeros(1, device=dev, dtype=torch.int32)
+    lib = _lib.load()
+    lib.ucod_paste_bicubic_dyn_workspace_bytes.restype = _u64
+    ws = _ws(lib.ucod_paste_bicubic_dyn_workspace_bytes(cap, gh, gw, out_cap), dev)
+    wp, wn = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_paste_bicubic_dyn", ptr(logits), cap, ptr(njobs_dev), gh, gw, ptr(all_jobs), int(first_index),
+                  all_jobs.shape[0], ptr(n_all_dev), ptr(mask_u8), N, Sh, Sw, int(out_cap), wp, wn, ptr(err),
+                  stream_ptr(dev))
 
 
 def paste_bicubic(logits: torch.Tensor, jobs: torch.Tensor, mask_u8: torch.Tensor) -> None:
@@ -195,6 +283,8 @@ def paste_bicubic(logits: torch.Tensor, jobs: torch.Tensor, mask_u8: torch.Tenso
     with torch.cuda.device(dev):
         _lib.call("ucod_paste_bicubic", ptr(logits), n, gh, gw, ptr(jobs), max_rank, ptr(mask_u8), N, Sh, Sw, cap, wp,
                   wn, ptr(err), stream_ptr(dev))
+    if int(err.item()) & 1:
+        raise UcodError("paste_bicubic: a box is smaller than ~4 px, beyond this call's tap table; use paste_bicubic_dyn")
 
 
 def mask_scale_u8(mask_u8: torch.Tensor, mul: int = 255) -> torch.Tensor:

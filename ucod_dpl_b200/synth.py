@@ -129,3 +129,31 @@ def synth_coral_inputs(seed: int, batch: int = 1, grid: int = 56, dim: int = 768
         y0, y1, x0, x1 = edges[r] + 1, edges[r + 1] - 1, edges[c] + 1, edges[c + 1] - 1
         preds[:, :, y0:y1, x0:x1] = 1.5 * torch.randn(batch, 1, y1 - y0, x1 - x0, generator=g).clamp(-1, 1)
     return l, h, preds
+
+
+def planted_object_logits(index: int, feature_size: int = 68, objects: int = 2) -> torch.Tensor:
+    """[1,fs,fs] fp32 first-look logits with `objects` well-separated small blobs (SURVEY.md 8(d) "LT" row: a random-init
+    backbone almost never segments small objects, so the Look-Twice benchmark plants them at `process_preds`' input).
+    Each blob covers 1.5-5 % of the frame after `sigmoid > 0.5` — above the 1 % box gate, far below look_twice_th —
+    so `process_preds` returns exactly `objects` boxes for every image."""
+    g = torch.Generator().manual_seed(4321 + int(index))
+    fs = feature_size
+    yy = torch.arange(fs, dtype=torch.float32).view(-1, 1)
+    xx = torch.arange(fs, dtype=torch.float32).view(1, -1)
+    out = torch.full((fs, fs), -4.0)
+    placed = []
+    while len(placed) < objects:
+        r = torch.rand(3, generator=g)
+        rad = (0.10 + 0.07 * float(r[2])) * fs            # logit > 0 inside rad / sqrt(2): area pi rad^2 / 2
+        cy = rad + float(r[0]) * (fs - 2 * rad)
+        cx = rad + float(r[1]) * (fs - 2 * rad)
+        if any((cy - py) ** 2 + (cx - px) ** 2 < (rad + pr + 3.0) ** 2 for py, px, pr in placed):
+            continue
+        placed.append((cy, cx, rad))
+        out = torch.maximum(out, 4.0 * (1.0 - 2.0 * (((yy - cy) / rad) ** 2 + ((xx - cx) / rad) ** 2)))
+    return out[None]
+
+
+def planted_object_batch(start: int, count: int, feature_size: int = 68, objects: int = 2) -> torch.Tensor:
+    """[count,1,fs,fs] fp32 (CPU)."""
+    return torch.stack([planted_object_logits(start + i, feature_size, objects) for i in range(count)], dim=0)

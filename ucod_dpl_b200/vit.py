@@ -162,10 +162,12 @@ class VitKeyExtractor:
         return self._ws
 
     def keys(self, images: torch.Tensor, *, want_f32: bool = True, want_bf16: bool = False,
-             want_cls_attn: bool = False, keep_cls: bool = False):
+             want_cls_attn: bool = False, keep_cls: bool = False, count_dev: torch.Tensor | None = None):
         """images: [B,3,H,W] fp32 (normalised) or uint8 (raw RGB) CUDA tensor.
 
-        Returns (keys_f32 | None, keys_bf16 | None, cls_attn | None); keys are token-major [B, P(+1), 768]."""
+        Returns (keys_f32 | None, keys_bf16 | None, cls_attn | None); keys are token-major [B, P(+1), 768].
+        count_dev (optional, int32 device scalar): only the first `count_dev` images are processed — the count is read
+        by the kernels on the device (`ucod_vit_keys_dyn`), B is the capacity; rows of later images are undefined."""
         _lib.require_cuda(images)
         if images.dim() != 4 or images.shape[1] != 3:
             raise _lib.UcodError(f"expected images [B,3,H,W], got {tuple(images.shape)}")
@@ -189,7 +191,16 @@ class VitKeyExtractor:
         k16 = torch.empty(B, rows, D, device=self.device, dtype=torch.bfloat16) if want_bf16 else None
         att = torch.empty(B, self.spec.heads, P, device=self.device, dtype=torch.float32) if want_cls_attn else None
         with torch.cuda.device(self.device):
-            _lib.call("ucod_vit_keys", self._handle, _lib.ptr(images), dt, B, H, W, _lib.ptr(pos),
-                      ctypes.c_void_p(ws.data_ptr() + off), ctypes.c_uint64(ws.numel() - off), _lib.ptr(k32),
-                      _lib.ptr(k16), _lib.ptr(att), 1 if keep_cls else 0, _lib.stream_ptr(self.device))
+            if count_dev is None:
+                _lib.call("ucod_vit_keys", self._handle, _lib.ptr(images), dt, B, H, W, _lib.ptr(pos),
+                          ctypes.c_void_p(ws.data_ptr() + off), ctypes.c_uint64(ws.numel() - off), _lib.ptr(k32),
+                          _lib.ptr(k16), _lib.ptr(att), 1 if keep_cls else 0, _lib.stream_ptr(self.device))
+            else:
+                _lib.require_cuda(count_dev)
+                if count_dev.dtype != torch.int32:
+                    raise _lib.UcodError("count_dev must be an int32 device tensor")
+                _lib.call("ucod_vit_keys_dyn", self._handle, _lib.ptr(images), dt, B, _lib.ptr(count_dev), H, W,
+                          _lib.ptr(pos), ctypes.c_void_p(ws.data_ptr() + off), ctypes.c_uint64(ws.numel() - off),
+                          _lib.ptr(k32), _lib.ptr(k16), _lib.ptr(att), 1 if keep_cls else 0,
+                          _lib.stream_ptr(self.device))
         return k32, k16, att
