@@ -55,13 +55,20 @@ def process_preds(preds: torch.Tensor, img_size, look_twice_th: float, expand_ty
     h, w = img_size
     up = F.interpolate(preds.float(), size=(h, w), mode="bilinear", align_corners=False)[..., :h, :w]
     preds_up = (torch.sigmoid(up) > 0.5).squeeze(0).float()
-    np_mask = (preds_up.numpy() * 255).astype(np.uint8)
+    return preds_up, boxes_from_mask(preds_up.numpy(), img_size, look_twice_th, expand_type)
+
+
+def boxes_from_mask(mask01, img_size, look_twice_th: float, expand_type: str = "dynamic"):
+    """The integer half of `process_preds` (:362-384) for a given binarised mask ([1,S,S] or [S,S], values {0,1}):
+    8-connected components, area fractions, boundingRect + expand_bbox, sort.  Returns the box list or None."""
+    h, w = img_size
+    np_mask = (np.asarray(mask01, dtype=np.float32) * 255).astype(np.uint8)
     if np_mask.ndim == 3:
         np_mask = np_mask.squeeze(0)
     num_labels, labels = cc.connected_components_8(np_mask)
     p = [(labels == i).sum() / (h * w) for i in range(1, num_labels)]
     if len(p) == 0:
-        return preds_up, [list(DEFAULT_BOX)]
+        return [list(DEFAULT_BOX)]
     if max(p) < look_twice_th:
         bboxes = []
         for i in range(1, num_labels):
@@ -69,8 +76,8 @@ def process_preds(preds: torch.Tensor, img_size, look_twice_th: float, expand_ty
                 binary = (labels == i).astype(np.uint8)
                 bboxes.append(expand_bbox(binary, cc.bounding_rect(binary), h, w, expand_type=expand_type))
         bboxes = sorted(bboxes, key=lambda b: -1 * b[2] * b[3])
-        return preds_up, bboxes
-    return preds_up, None
+        return bboxes
+    return None
 
 
 def crop_resize_normalize(image_u8_hwc: np.ndarray, box_xywh, out_size) -> torch.Tensor:

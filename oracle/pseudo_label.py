@@ -22,7 +22,7 @@ from . import cc
 
 @torch.no_grad()
 def compute_img_bkg_seg(attentions, feats, featmap_dims, th_bkg, dim=64, epsilon: float = 1e-10,
-                        apply_weights: bool = True):
+                        apply_weights: bool = True, id_ref_override=None, want_att_sum: bool = False):
     """attentions [B,nh,T,T] (or the CLS row [B,nh,P] directly), feats [B,T,C] incl. CLS (or [B,P,C]).
     Returns (bkg_mask [B,h,w] float {0,1}, sim_map [B,h,w] float)."""
     w_f, h_f = featmap_dims
@@ -44,11 +44,16 @@ def compute_img_bkg_seg(attentions, feats, featmap_dims, th_bkg, dim=64, epsilon
     cos_sim = torch.bmm(descs, descs.permute(0, 2, 1))
     if apply_weights:
         att = att * beta[:, :, None]
-    id_ref = torch.argmin(torch.sum(att, dim=1), dim=-1)
+    att_sum = torch.sum(att, dim=1)
+    id_ref = torch.argmin(att_sum, dim=-1)
+    if id_ref_override is not None:  # test hook: evaluate the map for a given reference patch (near-tie analysis)
+        id_ref = torch.as_tensor(id_ref_override, dtype=torch.long).reshape(nb)
     row = cos_sim[torch.arange(nb), id_ref, :].reshape(nb, w_f, h_f)
     bkg = row > th_bkg
     sim = 1 - row.float()
     sim = sim / (sim.max() + 1e-10)
+    if want_att_sum:
+        return bkg.float(), (sim * (1 - bkg.float())).float(), row, id_ref, att_sum
     return bkg.float(), (sim * (1 - bkg.float())).float(), row, id_ref
 
 

@@ -11,8 +11,6 @@ import pytest
 import torch
 from safetensors.torch import load_file
 
-from oracle import pipeline as opipe
-from oracle import vit as ovit
 from ucod_dpl_b200.models.uscod import baseline
 from ucod_dpl_b200.pipeline import FirstStageEval
 from ucod_dpl_b200.synth import random_vit_state_dict, synth_batch_u8
@@ -30,23 +28,53 @@ def _pipe(kind: str, S: int):
     return FirstStageEval(vit_sd, spec_for(kind), model, (S, S), 68, device="cuda"), vit_sd, dec_sd
 
 
+GOLD = ROOT / "tests" / "golden" / "configs_eval.npz"   # fp32 CPU oracle outputs, tools/make_golden_configs.py
+
+
+def _compare_with_golden(tag: str, kind: str, S: int, sig_max: float, sig_mean: float, delta: float):
+    """CUDA first-stage eval vs the committed oracle vectors.  Tolerances (bf16 tensor-core backbone vs fp32 reference):
+    max / mean |sigmoid diff| on the 68x68 logits, and the margin rule for the integer output: a mask pixel may differ
+    from the oracle only where the ORACLE's own upsampled logit is within `delta` of the threshold (|logit| < delta,
+    i.e. sigmoid in 0.5 +- delta/4) — every mismatch is then a tie broken by rounding, never a different decision."""
+    import numpy as np
+    import torch.nn.functional as F
+    g = np.load(GOLD)
+    idx = g[tag + "_images"].tolist()
+    pipe, _, _ = _pipe(kind, S)
+    imgs = torch.stack([synth_batch_u8(i, 1, S, S)[0] for i in idx]).cuda()
+    fg = pipe.logits(imgs).cpu()
+    masks = pipe(imgs).cpu()
+    ref = torch.from_numpy(g[tag + "_logits"])
+    ref_mask = torch.from_numpy(np.unpackbits(g[tag + "_mask"], axis=-1)[..., :S])
+    d = (torch.sigmoid(fg) - torch.sigmoid(ref)).abs()
+    up_ref = F.interpolate(ref, size=(S, S), mode="bilinear", align_corners=False)[:, 0]
+    bad = masks != ref_mask
+    agree = 1.0 - bad.float().mean().item()
+    worst = up_ref[bad].abs().max().item() if bad.any() else 0.0
+    print(f"{tag}: sigmoid diff max {d.max().item():.4f} mean {d.mean().item():.5f}; mask agreement {agree:.5f}; "
+          f"{int(bad.sum())} mismatching pixels, largest |oracle logit| among them {worst:.4f}")
+    assert d.max().item() <= sig_max and d.mean().item() <= sig_mean
+    assert worst < delta, worst
+    return agree
+
+
 def test_config0_dinov1_first_stage_eval_matches_oracle():
-    S = 296
-    pipe, vit_sd, dec_sd = _pipe("dinov1", S)
-    imgs = synth_batch_u8(0, 8, S, S)
-    fg = pipe.logits(imgs.cuda()).cpu()
-    masks = pipe(imgs.cuda()).cpu()
-    ref = opipe.first_stage_eval(vit_sd, ovit.spec_for("dinov1"), dec_sd, imgs, (S, S), 68)
-    # bf16 backbone vs fp32 reference.  The random-init ViT-B/8 (no LayerScale) gives low-contrast keys (token std
-    # 0.28 vs 0.39 for the DINOv2 config, same absolute bf16 error ~6e-3 rms), so its decoder logits sit closer to
-    # the sigmoid = 0.5 boundary than a trained model's: measured max 2.3e-2 / mean 3.7e-3 on the sigmoid outputs and
-    # 99.55 % identical mask pixels; the DINOv2 config (smoke(), test_vit_gpu) meets 1e-2 / 99.9 %.
-    d = (torch.sigmoid(fg) - torch.sigmoid(ref["logits"])).abs()
-    agree = (masks == ref["mask"]).float().mean().item()
-    print(f"config0: sigmoid diff max {d.max().item():.4f} mean {d.mean().item():.5f} p99.9 "
-          f"{d.flatten().kthvalue(int(d.numel() * 0.999)).values.item():.4f}; mask agreement {agree:.5f}")
-    assert d.mean().item() < 5e-3 and d.max().item() < 3e-2
+    """configs[0]: DINO ViT-B/8, 8 images @296^2, shipped UCOD_DPL_dinov1 weights.
+    The random-init ViT-B/8 (no LayerScale) gives low-contrast keys, so many decoder logits sit near the threshold:
+    measured max 2.3e-2 / mean 3.7e-3 on the sigmoid outputs, 99.55 % identical pixels, every mismatch at
+    |oracle logit| < 0.072.  tools/diag_parity.py shows that the gap is the bf16 backbone itself: pushing the CUDA
+    backbone's fp32 keys through an fp32 decoder gives the same numbers (1.9e-2 / 99.51 %), so a higher-precision
+    last projection / decoder GEMM would not change it."""
+    agree = _compare_with_golden("c0", "dinov1", 296, sig_max=3e-2, sig_mean=5e-3, delta=0.1)
     assert agree >= 0.995
+
+
+def test_config1_dinov2_full_size_matches_oracle():
+    """configs[1] at its real size: images 0, 21, 42, 63 of the 64-image batch @518^2, DINOv2 ViT-B/14 + shipped
+    UCOD_DPL_dinov2 weights, against the fp32 oracle: north_star's tolerances (<= 1e-2 on sigmoid outputs, >= 99.9 %
+    identical mask pixels) plus the margin rule."""
+    agree = _compare_with_golden("c1", "dinov2", 518, sig_max=1e-2, sig_mean=2e-3, delta=0.05)
+    assert agree >= 0.999
 
 
 def test_config1_full_size_determinism_and_batch_independence():

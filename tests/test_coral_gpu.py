@@ -100,7 +100,9 @@ def test_resize_tokens_matches_interpolate():
 
 def test_coral_evaluator_end_to_end():
     """Whole second-stage eval of one image vs the CPU oracle pipeline (random-init ViT-B/14 + shipped decoder +
-    seeded refiner).  bf16 backbone vs fp32 oracle: coarse logits within tolerance, final masks >= 98 % equal."""
+    seeded refiner), nothing injected.  bf16 backbone + bf16 CSF block vs the fp32 oracle: refined logits within 10 %
+    of their range, and the margin rule for the integer output — a final mask pixel may differ from the oracle's only
+    where the oracle's own interpolated probability is a near-tie (|p - 0.5| < delta)."""
     from safetensors.torch import load_file
     from oracle import pipeline as opipe
     from oracle import vit as ovit
@@ -128,7 +130,14 @@ def test_coral_evaluator_end_to_end():
     assert got.shape == ref["refined"].shape
     scale = ref["refined"].abs().max().item()
     assert (got - ref["refined"]).abs().max().item() < 0.1 * max(scale, 1.0)
-    agree = (masks[0].cpu().float() == ref["mask"][0]).float().mean().item()
+    import torch.nn.functional as F
+    p_ref = F.interpolate(torch.sigmoid(ref["refined"]), size=(300, 340), mode="bilinear")[0, 0]
+    bad = masks[0].cpu().float() != ref["mask"][0]
+    agree = 1.0 - bad.float().mean().item()
+    worst = (p_ref[bad] - 0.5).abs().max().item() if bad.any() else 0.0
+    print(f"coral e2e: refined max |diff| {(got - ref['refined']).abs().max().item():.4f} (range {scale:.2f}), mask "
+          f"agreement {agree:.5f}, {int(bad.sum())} mismatching pixels, largest |p - 0.5| among them {worst:.4f}")
+    assert worst < 0.06, worst
     assert agree >= 0.98, agree
 
 

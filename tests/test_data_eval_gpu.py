@@ -19,6 +19,7 @@ from safetensors.torch import load_file
 from oracle import decoder as odec
 from oracle import looktwice as olt
 from oracle import metrics as omet
+from oracle import pil_resample as opr
 from oracle import vit as ovit
 from ucod_dpl_b200.data.datasets import ImageTransforms, USCODDataset, pack_padded
 from ucod_dpl_b200.engine.runner.loop_UCOD_DPL import LookTwiceEvaluator
@@ -96,8 +97,8 @@ def test_feature_cache_is_reference_layout(tmp_path):
     assert (key[0].cpu() - item["features"]).abs().mean().item() < 2e-3
 
 
-def _oracle_flow(vit_sd, dec_sd, img_u8, label_hw, S, fs):
-    """loop_UCOD_DPL.py:297-311 in fp32 on the CPU for one image -> bool mask at the label size."""
+def _oracle_stages(vit_sd, dec_sd, S, fs):
+    """fp32 CPU pieces of loop_UCOD_DPL.py:297-317 (one image at a time), exposed stage by stage."""
     from torchvision import transforms as T
     spec = ovit.spec_for("dinov2")
     tf = T.Compose([T.Resize((S, S)), T.ToTensor(), T.Normalize([0.485, 0.456, 0.406], [0.229, 0.224, 0.225])])
@@ -105,19 +106,37 @@ def _oracle_flow(vit_sd, dec_sd, img_u8, label_hw, S, fs):
     def seg_keys(x):
         return ovit.keys_to_map(ovit.vit_forward(vit_sd, spec, x)["key_tokens"])
 
-    keys = seg_keys(tf(Image.fromarray(img_u8))[None])
-    feats = F.interpolate(keys, size=(fs, fs), mode="bilinear")
-    preds = odec.baseline_forward(dec_sd, feats, want_ortho=False)[0]
-    up, bboxes = olt.process_preds(preds, (S, S), 0.15, "dynamic")
-    first = up.clone()
-    if bboxes is not None:
-        up = olt.look_twice(img_u8, bboxes, up, (S, S),
-                            lambda x: odec.baseline_forward(dec_sd, seg_keys(x), want_ortho=False)[0])
-    final = F.interpolate(up.reshape(1, 1, S, S).float(), size=label_hw, mode="bilinear")[0, 0] > 0.5
-    return final.numpy(), bboxes, first
+    def first_logits(img_u8):
+        feats = F.interpolate(seg_keys(tf(Image.fromarray(img_u8))[None]), size=(fs, fs), mode="bilinear")
+        return odec.baseline_forward(dec_sd, feats, want_ortho=False)[0]
+
+    def second_logits(x):  # normalised crop [1,3,S,S] -> logits on the raw grid
+        return odec.baseline_forward(dec_sd, seg_keys(x), want_ortho=False)[0]
+
+    return first_logits, second_logits
+
+
+def _margin_ok(got_mask, want_mask, ref_logit_up, delta):
+    """mask pixels may differ from the oracle only where the oracle's own (interpolated) logit is a near-tie"""
+    bad = got_mask != want_mask
+    return (not bad.any()) or float(np.abs(ref_logit_up[bad]).max()) < delta, float(1.0 - bad.mean())
 
 
 def test_eval_launcher_end_to_end(tmp_path, monkeypatch):
+    """`scripts.eval` on ragged synthetic image folders (both test sets of the sweep), checked as a CHAIN against the
+    fp32 CPU oracle, every link with identical inputs on both sides:
+      (1) the PNG the launcher wrote == the evaluator called directly on the same decoded image (>= 99.95 %: the
+          launcher batches four images, which changes the GEMM tile order and so the last bits of the logits), and the
+          result table == the oracle metric suite over the PNGs (1e-9);
+      (2) first look, float: |sigmoid diff| <= 1e-2 on the 68x68 logits, mask pixels differ only at oracle near-ties;
+      (3) boxes, integer: the CUDA box list == the oracle's component / box logic run on the CUDA first-look mask;
+      (4) second look, float: per box, logits on the raw grid within 1e-2 (sigmoid) of the oracle's on the PIL-made
+          crop, cells differ only at oracle near-ties; paste, integer: Pillow-exact bicubic pastes of the CUDA-binarised
+          second looks reproduce the evaluator's canvas bit for bit; the final bilinear resize + threshold agrees to
+          >= 99.99 % (fp32 ties at exactly 0.5).
+    No link injects oracle results into the CUDA path; floats are compared with north_star's tolerances and every
+    integer stage bit for bit."""
+    from ucod_dpl_b200 import ops
     from ucod_dpl_b200.scripts import eval as ev
     S, fs = 224, 68
     data = tmp_path / "data"
@@ -139,42 +158,67 @@ def test_eval_launcher_end_to_end(tmp_path, monkeypatch):
     model = baseline(SimpleNamespace(dim=768)).cuda().eval()
     model.load_state_dict(dec_sd)
     looker = LookTwiceEvaluator(VitKeyExtractor(vit_sd, spec_for("dinov2")), model, (S, S), fs, 0.15, "dynamic")
-    any_boxed = False
+    tf = ImageTransforms.get_image_transform((S, S))
+    first_logits, second_logits = _oracle_stages(vit_sd, dec_sd, S, fs)
+    n_boxed = n_second = 0
     for name, n in (("SETA", 5), ("SETB", 3)):
         files = sorted(os.listdir(run / "preds" / name))
         assert files == [f"img_{i:02d}.png" for i in range(n)]
-        items, agree, boxed = [], [], []
+        items = []
         for f in files:
             pred = np.asarray(Image.open(run / "preds" / name / f))
             gt = np.asarray(Image.open(data / name / "gt" / f))
             assert pred.shape == gt.shape and set(np.unique(pred)) <= {0, 255}
             items.append(omet.per_image(gt.astype(np.float64) / 255.0, pred > 0))
             img = np.asarray(Image.open(data / name / "im" / f).convert("RGB"))
-            want, obox, ofirst = _oracle_flow(vit_sd, dec_sd, img, gt.shape, S, fs)
-            agree.append(float(((pred > 0) == want).mean()))
-            boxed.append(bool(obox) and obox != [[129, 129, 259, 259]])
-            if boxed[-1]:
-                # Stage isolation: a component box list is control flow computed from a noisy (random-init ViT)
-                # first-look mask, so bf16-vs-fp32 pixel flips move boxes by a pixel and reorder the pastes.  Drive
-                # the CUDA second look with the ORACLE's first mask and boxes: the ragged crop / ViT / paste path
-                # itself must agree.
-                canvas, sizes = pack_padded([img], "cuda")
-                new = looker.look_twice_batch(canvas, [obox], ofirst.to(torch.uint8).cuda(), layout="HWC",
-                                              orig_sizes=sizes)
-                final = F.interpolate(new[None], size=gt.shape, mode="bilinear")[0, 0] > 0.5
-                iso = float((final.cpu().numpy() == want).mean())
-                print(name, f, "second look on the oracle's boxes: agreement", round(iso, 4))
-                assert iso >= 0.995, iso
+            # (1) launcher == evaluator on the same image, exactly
+            canvas, sizes = pack_padded([img], "cuda")
+            r = looker.look_twice_device(tf.batch([img]), canvas, layout="HWC", orig_sizes=sizes)
+            r.check()
+            direct = ops.upsample_bilinear(r.final[0], gt.shape, binarize=3).cpu().numpy()
+            assert float(((direct > 0) == (pred > 0)).mean()) >= 0.9995, (name, f)
+            # (2) first look (float)
+            lg_ref = first_logits(img)
+            lg = looker.first_look(tf.batch([img])).cpu()
+            assert (torch.sigmoid(lg) - torch.sigmoid(lg_ref)).abs().max().item() <= 1e-2
+            up_ref = F.interpolate(lg_ref, size=(S, S), mode="bilinear", align_corners=False)[0, 0].numpy()
+            ok, agree1 = _margin_ok(r.first[0].cpu().numpy(), (up_ref > 0).astype(np.uint8), up_ref, 0.05)
+            assert ok, (name, f, agree1)   # (an image whose logits hover around 0 has many such ties: 98.4 % on img_03)
+            # (3) boxes (integer) from the CUDA mask
+            boxes = olt.boxes_from_mask(r.first[0].cpu().numpy(), (S, S), 0.15, "dynamic")
+            assert boxes == r.bboxes[0], (name, f, boxes, r.bboxes[0])
+            # (4a) second look, float: per box, the CUDA logits on the raw grid vs the oracle's on the PIL-made crop
+            first01 = r.first[0].cpu().numpy()
+            canvas_u8 = (first01 * 255).astype(np.uint8)
+            if boxes:
+                n_boxed += boxes != [olt.DEFAULT_BOX]
+                n_second += len(boxes)
+                H0, W0 = img.shape[:2]
+                cj = torch.tensor([[0] + olt.resize_bbox(bb, S, S, W0, H0) for bb in boxes], dtype=torch.int32).cuda()
+                crops = ops.roi_crop_resize(canvas, cj, (S, S), layout="HWC")
+                _, k16, _ = looker.extractor.keys(crops, want_f32=False, want_bf16=True)
+                g = S // 14
+                fg2 = model.decoder.forward_tokens(k16, (g, g), (g, g), want_bg=False)[0].cpu()
+                for i, bb in enumerate(boxes):
+                    x, _ = olt.crop_resize_normalize(img, cj[i, 1:].tolist(), (S, S))
+                    ref2 = second_logits(x[None])
+                    assert (torch.sigmoid(fg2[i]) - torch.sigmoid(ref2[0])).abs().max().item() <= 1e-2
+                    bad = (fg2[i] > 0) != (ref2[0] > 0)
+                    assert (not bad.any()) or ref2[0][bad].abs().max().item() < 0.05
+                    # (4b) paste, integer: Pillow-exact bicubic of the CUDA-binarised second look
+                    pred_u8 = ((fg2[i, 0] > 0).to(torch.uint8) * 255).numpy()
+                    opr.paste_u8(canvas_u8, opr.resize_u8(pred_u8, bb[2], bb[3], "bicubic"), bb[0], bb[1])
+            assert np.array_equal(canvas_u8, np.rint(r.final[0].cpu().numpy() * 255).astype(np.uint8)), (name, f)
+            up = torch.from_numpy(canvas_u8).float().div(255.0)
+            want = (F.interpolate(up.reshape(1, 1, S, S), size=gt.shape, mode="bilinear")[0, 0] > 0.5).numpy()
+            agree = float(((direct > 0) == want).mean())
+            print(name, f, "boxes", boxes, "first-look agreement", round(agree1, 5), "final agreement", round(agree, 5))
+            assert agree >= 0.9999, (name, f, agree)
         # the launcher's table is the oracle metric suite over the PNGs it wrote
         want_tab = omet.aggregate(items)
         for k, v in want_tab.items():
             assert abs(res[name][k] - v) < 1e-9, (name, k, res[name][k], v)
-        # bf16 CUDA pipeline vs fp32 CPU oracle of the whole flow (both looks)
-        # (both looks; images with a real box list only loosely, see above — measured 0.90 there, >= 0.993 elsewhere)
-        any_boxed = any_boxed or any(boxed)
-        print(name, "mask agreement per image:", [round(a, 4) for a in agree], "boxed:", boxed)
-        assert all(a >= (0.85 if b else 0.99) for a, b in zip(agree, boxed)), agree
-    assert any_boxed, "the synthetic sets should exercise a real box list at least once"
+    assert n_boxed >= 1 and n_second >= 3, "the synthetic sets should exercise real box lists"
 
 
 def test_second_stage_launcher(tmp_path, monkeypatch):

@@ -95,22 +95,43 @@ def test_refine_other_sizes_and_thresholds():
 
 
 def test_generator_end_to_end_small():
-    """ViT@224 -> scoring -> cleanup vs oracle ViT (fp32) -> oracle scoring: masks agree except near-threshold."""
+    """Pseudo-label generation from raw images (ViT @224 -> scoring -> cleanup) against the fp32 CPU oracle, nothing
+    injected, checked as a chain:
+      float   the cosine map to the least-attended patch is within 2e-2 of the oracle's;
+      integer the reference patch index is the oracle's (or the two candidates are a near-tie in the oracle);
+      margin  a pre-cleanup label may differ only where the oracle's cosine is within 0.03 of th_bkg;
+      integer the final mask equals the oracle's small-component cleanup applied to the CUDA pre-cleanup mask, bit for
+              bit — and therefore equals the oracle's final mask wherever no near-tie pixel was involved."""
     from oracle import vit as ovit
     from ucod_dpl_b200.generate_pseudo_label import PseudoLabelGenerator
     from ucod_dpl_b200.synth import random_vit_state_dict, synth_batch_u8
     spec = ovit.spec_for("dinov2")
     sd = random_vit_state_dict(spec, seed=0)
-    imgs = synth_batch_u8(0, 3, 224, 224)
+    imgs = synth_batch_u8(0, 6, 224, 224)
     gen = PseudoLabelGenerator(sd, "dinov2")
     masks = gen(imgs.cuda()).cpu().numpy()
+    k32, _, att = gen.extractor.keys(imgs.cuda(), want_f32=True, want_cls_attn=True)
+    cos, bkg, ref_idx, _ = ops.pseudo_label_score(att, k32, 0.6)
+    cos, bkg, ref_idx = cos.cpu().reshape(-1, 16, 16), bkg.cpu().reshape(-1, 16, 16), ref_idx.cpu().tolist()
     ref = ovit.vit_forward(sd, spec, ovit.normalize_u8(imgs), want_attn=True)
-    agree = 0
-    for b in range(3):
-        bkg, _, row, _ = opl.compute_img_bkg_seg(ref["cls_attn"][b:b + 1], ref["key_tokens"][b:b + 1], (16, 16), 0.6)
-        want = opl.refine_post_process((1 - bkg[0]).numpy())
-        agree += (want == masks[b]).mean()
-    assert agree / 3 >= 0.99
+    same_final = 0
+    for b in range(6):
+        args = (ref["cls_attn"][b:b + 1], ref["key_tokens"][b:b + 1], (16, 16), 0.6)
+        obkg_pure, _, _, oid, asum = opl.compute_img_bkg_seg(*args, want_att_sum=True)
+        if ref_idx[b] != int(oid[0]):
+            # the least-attended patch is an argmin over floats: a different winner is only acceptable when the
+            # oracle's own two candidates are a near-tie (< 1 % apart); the map is then checked for the CUDA winner
+            a, o = asum[0, ref_idx[b]].item(), asum[0, int(oid[0])].item()
+            print(f"image {b}: reference patch {ref_idx[b]} vs oracle {int(oid[0])}; oracle attention sums {a:.6f} / {o:.6f}")
+            assert (a - o) / abs(o) < 1e-2, (b, ref_idx[b], int(oid[0]), a, o)
+        obkg, _, row, _ = opl.compute_img_bkg_seg(*args, id_ref_override=[ref_idx[b]])
+        assert (cos[b] - row[0]).abs().max().item() < 2e-2
+        bad = bkg[b].float() != obkg[0]
+        assert (not bad.any()) or (row[0][bad] - 0.6).abs().max().item() < 0.03
+        pre = (1 - bkg[b]).numpy()
+        assert np.array_equal(masks[b], opl.refine_post_process(pre))
+        same_final += int(np.array_equal(masks[b], opl.refine_post_process((1 - obkg_pure[0]).numpy())))
+    print("final pseudo-label masks identical to the pure-oracle ones:", same_final, "of 6")
 
 
 def test_pseudo_label_cache_written_in_reference_format(tmp_path):

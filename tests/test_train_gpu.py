@@ -93,6 +93,43 @@ def test_three_fused_steps_match_oracle():
     assert tr.global_step == 6 and tr.opt_steps == 3
 
 
+@pytest.mark.parametrize("cur_epoch,B,tol", [(3, 16, 0.05), (22, 2, 0.03)])
+def test_fused_step_matches_oracle_without_injection(cur_epoch, B, tol):
+    """One fused step against the oracle with NOTHING injected: the oracle computes its own teacher / student masks,
+    discriminator probabilities, APM weights and merged targets.
+    * epoch 22 of 25 (finetune schedule term 22/20 >= 1): the APM weight saturates at 1, the target is the binarised
+      teacher mask; a few threshold flips between bf16 and fp32 logits move a few of 9 248 target pixels.
+    * epoch 3, batch 16: the discriminator's train-mode BatchNorm sees 16 masks, so single-pixel flips no longer swing
+      its statistics; the APM weights follow the oracle's to a few 1e-3.
+    Gradients are compared at `tol` of the largest entry, the loss and the per-image APM weights directly."""
+    sd0, model, D = _models()
+    dis_sd = odec.random_discriminator_state_dict(68, seed=31)
+    tr = FirstStageTrainer(model, D, lr0=2e-4)
+    tr.cur_epoch = cur_epoch
+    feats, pl = train_inputs(300 + cur_epoch, B)
+    tok = ops.features_to_tokens_bf16(feats.cuda())
+    loss = tr.process_batch(tok, (37, 37), pl.cuda())
+    sd = {k: v.clone() for k, v in sd0.items()}
+    out = otr.train_step(sd, dis_sd, otr.new_state(sd), feats, pl, cur_epoch=cur_epoch, global_step=0, lr=2e-4)
+    flips = (tr.last["merged"].cpu() - out["merged"]).abs()
+    print(f"epoch {cur_epoch} B {B}: loss {float(loss):.5f} vs {float(out['loss']):.5f}; merged target mean |diff| "
+          f"{flips.mean().item():.2e}, APM weight oracle {out['weight'].flatten()[:4].tolist()}")
+    # loss = BCE(fg) + BCE(bg) + ortho - dis_loss: the decoder part is compared tightly; dis_loss = BCE(D(student mask), 0)
+    # goes through the discriminator's train-mode BatchNorm (at batch 2 a single flipped pixel moves it by 1e-2)
+    dis, dis_o = float(tr.last["dis_loss"]), float(out["dis_loss"])
+    dec, dec_o = float(loss) + dis, float(out["loss"]) + dis_o
+    print(f"   decoder part of the loss {dec:.5f} vs {dec_o:.5f}; dis_loss {dis:.5f} vs {dis_o:.5f}")
+    assert abs(dec - dec_o) < 1e-2 * abs(dec_o) + 1e-3
+    assert abs(dis - dis_o) < (0.05 if B < 8 else 5e-3)
+    assert flips.mean().item() < 5e-3
+    for name in otr.PARAM_ORDER:
+        ref = out["grads"][name].reshape(-1).numpy()
+        got = tr.views[name].cpu().numpy()
+        lim = tol * np.abs(ref).max() + 1e-7
+        print(f"   {name}: max |grad diff| / max |grad| = {np.abs(got - ref).max() / (np.abs(ref).max() + 1e-12):.4f}")
+        assert np.abs(got - ref).max() < lim, (name, np.abs(got - ref).max(), lim)
+
+
 def test_adamw_ema_kernel_matches_torch():
     from ucod_dpl_b200 import _lib
     import ctypes

@@ -34,8 +34,9 @@ class LookTwiceResult:
     boxes / nbox   int32 [N,128,4] / [N] as written by `ucod_lt_boxes` (nbox -1 = None, -2 = ValueError)
     counts    int32 [4] (second looks kept, status bits, second looks requested, 0) or None when Look-Twice is off
     `check()` is the one place that reads anything back (a few dozen bytes): it raises what the reference would have
-    raised for this batch, and — if the batch needed more second-look chunks than were enqueued ahead of time — runs
-    the missing chunks and refreshes `final` (see `LookTwiceEvaluator.look_twice_device`).
+    raised for this batch, and — if the batch needed more second-look chunks than were enqueued ahead of time, or more
+    second looks than the device job table holds — completes the batch and refreshes `final` (see
+    `LookTwiceEvaluator.look_twice_device`).
     `bboxes` converts the box table to the reference's per-image lists (also a host read)."""
 
     def __init__(self, final, first, boxes, nbox, counts, err, canvas=None, resume=None):
@@ -51,11 +52,8 @@ class LookTwiceResult:
             kept, status, wanted, _ = self.counts.cpu().tolist()
             if status & 4:
                 raise ValueError("height and width must be > 0")  # PIL raises in the reference
-            if status & 2:
-                raise ops.UcodError(f"Look-Twice: {wanted} second looks requested, capacity {kept}; raise "
-                                    "`max_looks_per_image`")
             if self._resume is not None:
-                self._resume(self, kept)
+                self._resume(self, kept, wanted)
                 self._resume = None
         if self.err is not None and int(self.err.item()):
             raise ops.UcodError("Look-Twice resampling: a crop or box is outside the supported scale range")
@@ -201,7 +199,7 @@ class LookTwiceEvaluator:
             originals = images
         N = images.shape[0]
         H0, W0 = originals.shape[-2:] if layout == "CHW" else originals.shape[1:3]
-        chunk = N
+        chunk = max(N, 16)
         capacity = chunk * self.max_looks_per_image
         sizes = None if orig_sizes is None else torch.as_tensor(orig_sizes)
         crop, paste, counts, chunks = ops.lt_build_jobs(boxes, nbox, (ih, iw), (H0, W0), sizes, capacity=capacity,
@@ -223,10 +221,15 @@ class LookTwiceEvaluator:
             run_chunk(c)
         final = ops.to_tensor_normalize(canvas[:, None])[:, 0]  # / 255 (:352)
 
-        def resume(res, kept):  # called from check(): host knows the count now
+        def resume(res, kept, wanted):  # called from check(): the host knows the counts now
             need = (kept + chunk - 1) // chunk
             self._recent_chunks = (self._recent_chunks + [need])[-8:]
-            if need > ahead:
+            if wanted > kept:
+                # more second looks than the job table holds (>= 16 * max_looks_per_image): redo the second look from
+                # host box lists, which have no capacity (the reference's own loop shape; rare by construction)
+                res.final.copy_(self.look_twice_batch(originals, res.bboxes, mask, layout=layout,
+                                                      orig_sizes=orig_sizes))
+            elif need > ahead:
                 for c in range(ahead, need):
                     run_chunk(c)
                 res.final.copy_(ops.to_tensor_normalize(canvas[:, None])[:, 0])
