@@ -166,13 +166,24 @@ int ucod_refine_small_components(const uint8_t* mask_in, uint8_t* mask_out, int 
  * expansion in exact fp64, stable sort by -w*h.
  * boxes: int32 [batch, UCOD_LT_MAX_BOXES, 4] (x,y,w,h); nbox: int32 [batch] — >= 0 number of boxes,
  * -1 = "None" (largest component fraction >= look_twice_th, no second look), -2 = the reference would raise
- * ValueError (sqrt of a negative scale); status: int32 [batch] bit0 = sqrt domain, bit1 = box table overflow.
+ * ValueError (sqrt of a negative scale), -3 = labeller capacity exceeded (see ucod_lt_boxes_ex);
+ * status: int32 [batch] bit0 = sqrt domain, bit1 = box table overflow, bit2 = labeller capacity.
  * labels (optional, int32 [batch,h,w]): per-pixel component root (min raster index of the component, -1 = bg). */
 #define UCOD_LT_MAX_BOXES 128
 uint64_t ucod_lt_boxes_workspace_bytes(int batch, int h, int w);
 int ucod_lt_boxes(const uint8_t* mask, int batch, int h, int w, double look_twice_th, int expand_dynamic,
                   double const_scale, int32_t* boxes, int32_t* nbox, int32_t* status, int32_t* labels,
                   void* workspace, uint64_t workspace_bytes, void* stream);
+
+/* Same with the labelling algorithm chosen by the caller.  algorithm 0 = automatic (what ucod_lt_boxes does): masks of
+ * up to 1024 rows are labelled by ONE CTA each in shared memory — bit image, runs of foreground pixels, union-find over
+ * runs; no label image ever reaches HBM, the only sizeable traffic is the mask itself.  A mask with more runs or
+ * components than shared memory holds (~23 000 runs at 518^2; masks up-sampled from a 68 x 68 logit map have at most
+ * 18 130) gets nbox = -3 and status bit 2 (value 4); re-run such a batch with algorithm 1 = union-find over pixels in
+ * global memory (any size).  algorithm 2 = shared-memory labeller or an error when the geometry does not fit. */
+int ucod_lt_boxes_ex(const uint8_t* mask, int batch, int h, int w, double look_twice_th, int expand_dynamic,
+                     double const_scale, int32_t* boxes, int32_t* nbox, int32_t* status, int32_t* labels,
+                     void* workspace, uint64_t workspace_bytes, int algorithm, void* stream);
 
 /* PIL `crop` + torchvision `Resize((out_h,out_w))` (Pillow antialiased BILINEAR, bit-exact fixed-point two-pass
  * resample) of ROIs of uint8 RGB images (loop_UCOD_DPL.py:335-342).  images: uint8, element strides given

@@ -216,3 +216,38 @@ print('REF_OK')
     assert "REF_OK" in out.stdout, out.stderr[-2000:]
     ours_rd = MetaListPickleIO(base_path=tmp_path / "theirs")
     assert ours_rd.mode == "r" and ours_rd.len() == 5 and torch.equal(ours_rd.read_file(1), items[1])
+
+
+def test_backbone_checkpoint_discovery_and_random_opt_in(tmp_path, monkeypatch):
+    """`load_vit_state_dict`: picks the checkpoint that matches the requested architecture (DINO ViT-B/8 vs DINOv2-B/14
+    both live under ./weights for the dinov1 configs), and refuses to fall back to random weights silently."""
+    from types import SimpleNamespace
+
+    import pytest
+    from safetensors.torch import save_file
+
+    from ucod_dpl_b200.data.utils import feature_extractor as fe
+    from ucod_dpl_b200.synth import random_vit_state_dict
+    from ucod_dpl_b200.vit import spec_for
+
+    def tiny(kind):  # only the tensors the matcher looks at
+        sd = random_vit_state_dict(spec_for(kind), seed=1)
+        keep = ("embeddings.patch_embeddings.projection.weight", "embeddings.cls_token",
+                "encoder.layer.0.attention.attention.key.weight", "encoder.layer.0.layer_scale1.lambda1")
+        return {k: v.contiguous() for k, v in sd.items() if k in keep}
+
+    (tmp_path / "a_dinov2").mkdir(), (tmp_path / "b_dino").mkdir()
+    save_file(tiny("dinov2"), str(tmp_path / "a_dinov2" / "model.safetensors"))
+    save_file(tiny("dinov1"), str(tmp_path / "b_dino" / "model.safetensors"))
+    for kind, name, patch in (("dinov2", "facebook/dinov2-base", 14), ("dinov1", "facebook/dino-vitb8", 8)):
+        cfg = SimpleNamespace(type=kind, backbone=name, backbone_weights=None, backbone_weight_base=str(tmp_path))
+        sd = fe.load_vit_state_dict(cfg)
+        assert sd["embeddings.patch_embeddings.projection.weight"].shape[-1] == patch
+    empty = SimpleNamespace(type="dinov2", backbone="facebook/dinov2-base", backbone_weights=None,
+                            backbone_weight_base=str(tmp_path / "nothing"))
+    monkeypatch.delenv(fe.ALLOW_RANDOM_ENV, raising=False)
+    with pytest.raises(FileNotFoundError):
+        fe.load_vit_state_dict(empty)
+    assert "embeddings.cls_token" in fe.load_vit_state_dict(empty, allow_random_init=True)
+    monkeypatch.setenv(fe.ALLOW_RANDOM_ENV, "1")
+    assert "embeddings.cls_token" in fe.load_vit_state_dict(empty)

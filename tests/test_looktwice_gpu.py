@@ -335,3 +335,35 @@ def test_device_pipeline_equals_host_lists():
     assert status1 & 2 and wanted1 > kept1 == 20
     r1.check()
     assert torch.equal(r1.final[:6], want)
+
+
+def test_shared_memory_labeller_equals_global():
+    """The run-based shared-memory labeller (one CTA per mask) and the global-memory union-find produce identical box
+    tables, summaries and label images — on blob masks at both pipeline sizes, noise masks (thousands of components),
+    stripes / checkerboards (the run-capacity corner) and degenerate masks."""
+    rng = np.random.default_rng(21)
+    for S in (518, 296, 97):
+        masks = []
+        for t in range(6):
+            lg = blob_logits(int(rng.integers(0, 7)), seed=300 + t, size=(0.02, 0.15))
+            masks.append(ops.upsample_bilinear(lg[:, 0].cuda(), (S, S), binarize=True)[0].cpu().numpy())
+        masks.append((rng.random((S, S)) < 0.5).astype(np.uint8))             # noise: very many components
+        masks.append((rng.random((S, S)) < 0.08).astype(np.uint8))
+        m = np.zeros((S, S), np.uint8); m[::2] = 1; masks.append(m)          # horizontal stripes
+        m = np.zeros((S, S), np.uint8); m[:, ::2] = 1; masks.append(m)       # vertical stripes: W/2 runs per row
+        masks.append(np.zeros((S, S), np.uint8))
+        masks.append(np.ones((S, S), np.uint8))
+        m = np.zeros((S, S), np.uint8); m[0, 0] = m[-1, -1] = m[0, -1] = 1; masks.append(m)
+        mk = torch.from_numpy(np.stack(masks)).cuda()
+        a = ops.lt_boxes(mk, 0.15, "dynamic", want_labels=True, algorithm="global")
+        b = ops.lt_boxes(mk, 0.15, "dynamic", want_labels=True, algorithm="shared")
+        nb_a, nb_b = a[1].cpu().tolist(), b[1].cpu().tolist()
+        for i in range(len(masks)):
+            if nb_b[i] == -3:                      # capacity: only the dense-noise / stripe masks may hit it
+                assert i in (6, 7, 9), (S, i)   # more components than bit-image words, or more runs than slots
+                continue
+            assert nb_a[i] == nb_b[i], (S, i, nb_a[i], nb_b[i])
+            n = max(nb_a[i], 0)
+            assert torch.equal(a[0][i, :n], b[0][i, :n]), (S, i)
+            assert torch.equal(a[3][i], b[3][i]), (S, i)
+        assert sum(1 for v in nb_b if v != -3) >= len(masks) - 3

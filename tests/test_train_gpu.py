@@ -93,6 +93,29 @@ def test_three_fused_steps_match_oracle():
     assert tr.global_step == 6 and tr.opt_steps == 3
 
 
+def test_teacher_follows_the_ema_weights():
+    """The teacher forward must see the EMA weights of the CURRENT step (they are updated in place by the fused
+    AdamW / EMA kernel): after a few steps its logits equal a fresh EMA decoder loaded from the state_dict."""
+    _, model, D = _models()
+    tr = FirstStageTrainer(model, D, lr0=2e-2)          # large lr: the EMA weights move visibly
+    tr.cur_epoch = 3
+    feats, pl = train_inputs(900, B=2)
+    tok = ops.features_to_tokens_bf16(feats.cuda())
+    for _ in range(4):
+        tr.process_batch(tok, (37, 37), pl.cuda())
+    fresh = baseline(SimpleNamespace(dim=768))
+    fresh.load_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, strict=True)
+    fresh = fresh.cuda().eval()
+    want, _, _ = fresh.decoder_ema.forward_tokens(tok, (37, 37), (68, 68), want_bg=False)
+    model.decoder_ema._packed = None
+    now, _, _ = model.decoder_ema.forward_tokens(tok, (37, 37), (68, 68), want_bg=False)
+    assert torch.allclose(now, want, atol=1e-5)
+    # what the trainer's own next teacher pass computes (cache rebuilt inside the step)
+    tr._forward_backward(tok, (37, 37), pl.cuda())
+    cached = model.decoder_ema._w_dec_bf16()
+    assert torch.equal(cached, model.decoder_ema.decoupling.weight.detach().reshape(128, 768).to(torch.bfloat16))
+
+
 @pytest.mark.parametrize("cur_epoch,B,tol", [(3, 16, 0.05), (22, 2, 0.03)])
 def test_fused_step_matches_oracle_without_injection(cur_epoch, B, tol):
     """One fused step against the oracle with NOTHING injected: the oracle computes its own teacher / student masks,
@@ -185,3 +208,66 @@ def test_discriminator_epoch_steps_match_reference_golden():
             assert int(v) == int(gold["dis_final_" + k])
             continue
         np.testing.assert_allclose(v.cpu().numpy(), gold["dis_final_" + k], atol=3e-5, rtol=2e-3, err_msg=k)
+
+
+def test_graph_replay_matches_eager_steps():
+    """CUDA-graph replay of the forward / APM / backward sequence: same losses and parameters as the eager path over
+    six steps with changing inputs (float atomics make both paths order-dependent in the last bits)."""
+    outs = []
+    for use_graph in (False, True):
+        _, model, D = _models()
+        tr = FirstStageTrainer(model, D, lr0=2e-4, use_graph=use_graph)
+        tr.cur_epoch = 3
+        losses = []
+        for step in range(6):
+            feats, pl = train_inputs(500 + step, B=4)
+            tok = ops.features_to_tokens_bf16(feats.cuda())
+            losses.append(float(tr.process_batch(tok, (37, 37), pl.cuda())))
+        assert tr.global_step == 12 and tr.opt_steps == 6
+        assert (tr._graph is not None) == use_graph
+        outs.append((losses, {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}))
+    (l0, p0), (l1, p1) = outs
+    assert np.allclose(l0, l1, rtol=2e-4, atol=2e-5), (l0, l1)
+    for k in p0:
+        # AdamW's first steps move every weight by ~lr whatever the gradient's size, so last-bit gradient differences
+        # (float atomics in the scatter kernels) show up as a small fraction of 6 * lr = 1.2e-3
+        assert torch.allclose(p0[k], p1[k], rtol=1e-4, atol=5e-5), k
+
+
+def _ddp_worker(rank, world, port, out):
+    import os
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.cuda.set_device(rank)
+    torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        _, model, D = _models()
+        tr = FirstStageTrainer(model, D, lr0=2e-4)
+        tr.cur_epoch = 3
+        for step in range(3):
+            feats, pl = train_inputs(700 + 10 * step + rank, B=4)      # every rank its own shard of the global batch
+            tok = ops.features_to_tokens_bf16(feats.cuda())
+            _, _ = tr._forward_backward(tok, (37, 37), pl.cuda())
+            local = tr.flat_g.clone()
+            gathered = [torch.empty_like(local) for _ in range(world)]
+            torch.distributed.all_gather(gathered, local)
+            tr._optimizer_step()                                        # NCCL all-reduce + AdamW(1/world) + EMA
+            mean = torch.stack(gathered).mean(0)
+            assert torch.allclose(tr.flat_g / world, mean, rtol=1e-5, atol=1e-8), step
+        params = [torch.empty_like(tr.flat_p) for _ in range(world)]
+        torch.distributed.all_gather(params, tr.flat_p)
+        assert all(torch.equal(params[0], p) for p in params[1:])      # replicas stay bit-identical
+        if rank == 0:
+            out.put("ok")
+    finally:
+        torch.distributed.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_two_rank_nccl_gradient_allreduce():
+    """The path's only data-path collective on real hardware: two ranks, different shards, one flat NCCL all-reduce of
+    the decoder gradients per step; the applied gradient is the mean over ranks and the replicas stay identical."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    mp.spawn(_ddp_worker, args=(2, 29591, out), nprocs=2, join=True)
+    assert out.get(timeout=10) == "ok"

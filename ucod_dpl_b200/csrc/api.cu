@@ -134,6 +134,12 @@ int ucod_lt_boxes(const uint8_t* mask, int batch, int h, int w, double look_twic
     return lt_boxes(mask, batch, h, w, look_twice_th, expand_dynamic, const_scale, boxes, nbox, status, labels,
                     workspace, (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
+int ucod_lt_boxes_ex(const uint8_t* mask, int batch, int h, int w, double look_twice_th, int expand_dynamic,
+                     double const_scale, int32_t* boxes, int32_t* nbox, int32_t* status, int32_t* labels,
+                     void* workspace, uint64_t workspace_bytes, int algorithm, void* stream) {
+    return lt_boxes(mask, batch, h, w, look_twice_th, expand_dynamic, const_scale, boxes, nbox, status, labels,
+                    workspace, (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream), algorithm);
+}
 uint64_t ucod_roi_crop_resize_workspace_bytes(int njobs, int max_crop_h, int out_h, int out_w) {
     return (uint64_t)roi_crop_resize_workspace_bytes(njobs, max_crop_h, out_h, out_w);
 }

@@ -13,6 +13,7 @@
 
 #include "gemm.cuh"
 #include "prof.cuh"
+#include "wgrad.cuh"
 
 namespace ucod {
 
@@ -136,59 +137,105 @@ __global__ void __launch_bounds__(256)
 }
 
 // Orthogonality loss pieces from the normalised features fhat [B, npix, 128] (first 64 = branch 1):
-//   gram[b, 0|1, 64, 64] += F_k^T F_k over a pixel chunk ; diag[b] += sum_i (f1_i . f2_i)^2
+//   gram[b, 0|1, 64, 64] = F_k^T F_k ; diag[b] = sum_i (f1_i . f2_i)^2
+// Stage 1: one CTA per (pixel chunk, image) computes both 64x64 Grams of its chunk with 4x4 register tiles (256 threads
+// = 16 x 16 tiles; per pixel a thread reads two float4 per branch from shared memory for 32 FMAs) and writes them to
+// its own slot of `part` — no atomics.  Stage 2 sums the slots in a fixed order (bit-reproducible), stage 3 reduces
+// <G1, G2>_F - diag in fp64.  (Round 1: 8-pixel tiles, 34 shared loads per 32 FMAs and 8 192 float atomics per CTA:
+// 240 us for 16 images; this version: see DESIGN.md.)
+constexpr int GRAM_CHUNK = 128;  // pixels per CTA
+constexpr int GRAM_TILE = 32;    // pixels staged per synchronisation
+
 __global__ void __launch_bounds__(256)
-    decoder_gram_kernel(const float* __restrict__ fhat, float* __restrict__ gram, float* __restrict__ diag, int npix,
-                        int chunk) {
-    __shared__ float sf[8][128];
-    const int b = blockIdx.y;
-    const int p0 = blockIdx.x * chunk;
-    const int p1 = min(npix, p0 + chunk);
-    // thread t owns entries (r, c0..c0+15) of both Grams: r = t / 4, c0 = (t % 4) * 16
-    const int r = threadIdx.x >> 2, c0 = (threadIdx.x & 3) * 16;
-    float g1[16], g2[16];
+    decoder_gram_kernel(const float* __restrict__ fhat, float* __restrict__ part, float* __restrict__ dpart, int npix) {
+    __shared__ __align__(16) float sf[GRAM_TILE][128];
+    __shared__ float sdiag[8];
+    const int b = blockIdx.y, nchunks = gridDim.x;
+    const int p0 = blockIdx.x * GRAM_CHUNK;
+    const int p1 = min(npix, p0 + GRAM_CHUNK);
+    const int tr = (threadIdx.x >> 4) * 4, tc = (threadIdx.x & 15) * 4;  // this thread's 4x4 tile: rows tr.., cols tc..
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float g1[4][4], g2[4][4];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) g1[i] = 0.f, g2[i] = 0.f;
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g1[i][j] = 0.f, g2[i][j] = 0.f;
     float dacc = 0.f;
-    for (int p = p0; p < p1; p += 8) {
-        const int n = min(8, p1 - p);
+    for (int p = p0; p < p1; p += GRAM_TILE) {
+        const int n = min(GRAM_TILE, p1 - p);
         __syncthreads();
-        for (int i = threadIdx.x; i < n * 128; i += 256) sf[i >> 7][i & 127] = fhat[((size_t)b * npix + p) * 128 + i];
+        const float4* src = reinterpret_cast<const float4*>(fhat + ((size_t)b * npix + p) * 128);
+        for (int i = threadIdx.x; i < n * 32; i += 256) reinterpret_cast<float4*>(&sf[0][0])[i] = src[i];
         __syncthreads();
         for (int k = 0; k < n; ++k) {
-            const float a1 = sf[k][r], a2 = sf[k][64 + r];
+            const float4 a1 = *reinterpret_cast<const float4*>(&sf[k][tr]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&sf[k][tc]);
+            const float4 a2 = *reinterpret_cast<const float4*>(&sf[k][64 + tr]);
+            const float4 b2 = *reinterpret_cast<const float4*>(&sf[k][64 + tc]);
+            const float av1[4] = {a1.x, a1.y, a1.z, a1.w}, bv1[4] = {b1.x, b1.y, b1.z, b1.w};
+            const float av2[4] = {a2.x, a2.y, a2.z, a2.w}, bv2[4] = {b2.x, b2.y, b2.z, b2.w};
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                g1[i] += a1 * sf[k][c0 + i];
-                g2[i] += a2 * sf[k][64 + c0 + i];
-            }
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g1[i][j] = fmaf(av1[i], bv1[j], g1[i][j]);
+                    g2[i][j] = fmaf(av2[i], bv2[j], g2[i][j]);
+                }
         }
-        if (threadIdx.x < n * 32) {  // warp k handles pixel k's dot product f1.f2
-            const int k = threadIdx.x >> 5, l = threadIdx.x & 31;
-            float d = sf[k][l] * sf[k][64 + l] + sf[k][l + 32] * sf[k][96 + l];
+        for (int k = warp; k < n; k += 8) {  // per-pixel dot product f1 . f2
+            float d = sf[k][lane] * sf[k][64 + lane] + sf[k][lane + 32] * sf[k][96 + lane];
             d = warp_sum(d);
-            if (l == 0) dacc += d * d;
+            dacc += d * d;  // identical in every lane
         }
     }
-    float* gb = gram + (size_t)b * 2 * 4096;
+    float* gp = part + ((size_t)b * nchunks + blockIdx.x) * 8192;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        atomicAdd(gb + r * 64 + c0 + i, g1[i]);
-        atomicAdd(gb + 4096 + r * 64 + c0 + i, g2[i]);
+    for (int i = 0; i < 4; ++i) {
+        *reinterpret_cast<float4*>(gp + (tr + i) * 64 + tc) = make_float4(g1[i][0], g1[i][1], g1[i][2], g1[i][3]);
+        *reinterpret_cast<float4*>(gp + 4096 + (tr + i) * 64 + tc) = make_float4(g2[i][0], g2[i][1], g2[i][2], g2[i][3]);
     }
-    if ((threadIdx.x & 31) == 0 && dacc != 0.f) atomicAdd(diag + b, dacc);
+    if (lane == 0) sdiag[warp] = dacc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sdiag[w];
+        dpart[(size_t)b * nchunks + blockIdx.x] = t;
+    }
+}
+
+// gram[b, e] = sum over chunks (fixed order) ; prod[b, blk] = partial <G1, G2>_F of this block's elements (fp64)
+__global__ void __launch_bounds__(256)
+    decoder_gram_reduce_kernel(const float* __restrict__ part, float* __restrict__ gram, double* __restrict__ prod,
+                               int nchunks) {
+    __shared__ double red[8];
+    const int b = blockIdx.y;
+    const int e = blockIdx.x * 256 + threadIdx.x;  // element of one 64x64 matrix (gridDim.x = 16)
+    const float* pp = part + (size_t)b * nchunks * 8192;
+    float s1 = 0.f, s2 = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+        s1 += pp[(size_t)c * 8192 + e];
+        s2 += pp[(size_t)c * 8192 + 4096 + e];
+    }
+    gram[(size_t)b * 8192 + e] = s1;
+    gram[(size_t)b * 8192 + 4096 + e] = s2;
+    double acc = (double)s1 * (double)s2;
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        prod[(size_t)b * gridDim.x + blockIdx.x] = t;
+    }
 }
 
 // ortho = (sum_b <G1_b, G2_b>_F - sum_b diag_b) / (B * npix^2)
-__global__ void decoder_ortho_finish_kernel(const float* __restrict__ gram, const float* __restrict__ diag,
-                                            float* __restrict__ out, int B, int npix) {
+__global__ void decoder_ortho_finish_kernel(const double* __restrict__ prod, int nprod, const float* __restrict__ dpart,
+                                            int ndiag, float* __restrict__ out, int B, int npix) {
     __shared__ double red[32];
     double acc = 0.0;
-    for (int i = threadIdx.x; i < B * 4096; i += blockDim.x) {
-        const int b = i >> 12, e = i & 4095;
-        acc += (double)gram[(size_t)b * 8192 + e] * (double)gram[(size_t)b * 8192 + 4096 + e];
-    }
-    for (int b = threadIdx.x; b < B; b += blockDim.x) acc -= (double)diag[b];
+    for (int i = threadIdx.x; i < nprod; i += blockDim.x) acc += prod[i];
+    for (int i = threadIdx.x; i < ndiag; i += blockDim.x) acc -= (double)dpart[i];
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
     __syncthreads();
@@ -199,12 +246,18 @@ __global__ void decoder_ortho_finish_kernel(const float* __restrict__ gram, cons
     }
 }
 
+static size_t gram_scratch_bytes(int B, int npix) {
+    const size_t nchunks = (size_t)ceil_div(npix, GRAM_CHUNK);
+    return (size_t)B * nchunks * 8192 * 4 + (size_t)B * nchunks * 4 + (size_t)B * 16 * 8 + 1024;
+}
+
 size_t decoder_workspace_bytes(int B, int gin_h, int gin_w, int out_h, int out_w, int want_ortho) {
     size_t n = (size_t)B * gin_h * gin_w * 128 * 4;  // d_in
     n += (size_t)B * 128 * 4;                        // sumsq
     if (want_ortho) {
         n += (size_t)B * out_h * out_w * 128 * 4;    // fhat
-        n += (size_t)B * 8192 * 4 + (size_t)B * 4;   // gram + diag
+        n += (size_t)B * 8192 * 4 + (size_t)B * 4;   // gram + diag (layout shared with the backward)
+        n += gram_scratch_bytes(B, out_h * out_w);   // per-chunk partial Grams / diag sums / fp64 products
     }
     return n + 4096;
 }
@@ -254,16 +307,22 @@ int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     if (ortho) {
-        UCOD_CHECK_CUDA(cudaMemsetAsync(gram, 0, (size_t)B * 8192 * 4 + (size_t)B * 4, stream));
-        const int chunk = 256;
-        dim3 g2(ceil_div(npix, chunk), B);
+        const int nchunks = ceil_div(npix, GRAM_CHUNK);
+        float* part = diag + (((size_t)B + 63) / 64) * 64;  // 256-byte aligned past the per-image diag slots
+        float* dpart = part + (size_t)B * nchunks * 8192;
+        double* prod = reinterpret_cast<double*>(dpart + (((size_t)B * nchunks + 1) / 2) * 2);
+        dim3 g2(nchunks, B);
         {
             ProfScope ps(KC_DECODER, stream, (double)B * npix * 128 * 4);
-            decoder_gram_kernel<<<g2, 256, 0, stream>>>(fhat, gram, diag, npix, chunk);
+            decoder_gram_kernel<<<g2, 256, 0, stream>>>(fhat, part, dpart, npix);
         }
         UCOD_CHECK_CUDA(cudaGetLastError());
-        ProfScope ps(KC_DECODER, stream, (double)B * 8192 * 4);
-        decoder_ortho_finish_kernel<<<1, 256, 0, stream>>>(gram, diag, ortho, B, npix);
+        {
+            ProfScope ps(KC_DECODER, stream, (double)B * nchunks * 8192 * 4);
+            decoder_gram_reduce_kernel<<<dim3(16, B), 256, 0, stream>>>(part, gram, prod, nchunks);
+        }
+        ProfScope ps(KC_DECODER, stream, (double)B * 16 * 8);
+        decoder_ortho_finish_kernel<<<1, 256, 0, stream>>>(prod, B * 16, dpart, B * nchunks, ortho, B, npix);
         UCOD_CHECK_CUDA(cudaGetLastError());
     }
     return 0;
@@ -423,81 +482,26 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// dD = A - (r_c^2 t_c) E ; db_dec[c] += sum over rows
-__global__ void __launch_bounds__(256)
-    decoder_bwd_finish_kernel(const float* __restrict__ a_buf, const float* __restrict__ e_buf,
-                              const float* __restrict__ tsum, const float* __restrict__ sumsq,
-                              const float* __restrict__ emb, float* __restrict__ dD, float* __restrict__ g_bdec,
-                              int rows_per_img, int total_rows) {
-    const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int r0 = blockIdx.x * 64;
-    const float e = __ldg(emb + c);
-    float acc = 0.f;
-    for (int i = half; i < 64; i += 2) {
-        const int row = r0 + i;
-        if (row >= total_rows) break;
-        const int b = row / rows_per_img;
-        const float g = e / fmaxf(fabsf(e) * sqrtf(sumsq[b * 128 + c]), 1e-12f);
-        const float v = a_buf[(size_t)row * 128 + c] - g * g * tsum[b * 128 + c] * e_buf[(size_t)row * 128 + c];
-        dD[(size_t)row * 128 + c] = v;
-        acc += v;
-    }
-    atomicAdd(g_bdec + c, acc);
+// five small accumulators of the backward (head-weight / bias gradients, the two BCE sums) zeroed by one launch
+__global__ void decoder_bwd_zero_kernel(float* w_fg, float* w_bg, float* b_fg, float* b_bg, float* loss2) {
+    const int t = threadIdx.x;
+    if (t < 64) w_fg[t] = 0.f, w_bg[t] = 0.f;
+    if (t == 0) b_fg[0] = 0.f, b_bg[0] = 0.f, loss2[0] = 0.f, loss2[1] = 0.f;
 }
 
-// dW[c][k] += sum_t dD[t][c] * X[t][k]   (c < 128, k < dim; X bf16 token-major; split over token ranges)
-__global__ void __launch_bounds__(256)
-    decoder_wgrad_kernel(const float* __restrict__ dD, const __nv_bfloat16* __restrict__ X, float* __restrict__ dW,
-                         int T, int dim, int tokens_per_split) {
-    __shared__ __align__(16) float sD[16][128];
-    __shared__ __align__(16) float sX[16][64];
-    const int k0 = blockIdx.x * 64;
-    const int t_begin = blockIdx.y * tokens_per_split;
-    const int t_end = min(T, t_begin + tokens_per_split);
-    const int cg = threadIdx.x >> 4, kg = threadIdx.x & 15;  // 16 x 16 thread grid: 8 channels x 4 features each
-    float acc[8][4];
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int t0 = t_begin; t0 < t_end; t0 += 16) {
-        const int n = min(16, t_end - t0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < 16 * 32; i += 256) {  // dD: 16 rows x 128 floats as float4
-            const int rr = i >> 5, cc = (i & 31) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rr < n) v = *reinterpret_cast<const float4*>(dD + (size_t)(t0 + rr) * 128 + cc);
-            *reinterpret_cast<float4*>(&sD[rr][cc]) = v;
-        }
-        for (int i = threadIdx.x; i < 16 * 32; i += 256) {  // X: 16 rows x 64 bf16 as bf16x2
-            const int rr = i >> 5, cc = (i & 31) * 2;
-            float2 v = make_float2(0.f, 0.f);
-            if (rr < n) v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(X + (size_t)(t0 + rr) * dim + k0 + cc));
-            sX[rr][cc] = v.x, sX[rr][cc + 1] = v.y;
-        }
-        __syncthreads();
-#pragma unroll
-        for (int tt = 0; tt < 16; ++tt) {
-            const float4 a0 = *reinterpret_cast<const float4*>(&sD[tt][cg * 8]);
-            const float4 a1 = *reinterpret_cast<const float4*>(&sD[tt][cg * 8 + 4]);
-            const float4 bx = *reinterpret_cast<const float4*>(&sX[tt][kg * 4]);
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bv[4] = {bx.x, bx.y, bx.z, bx.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] += av[i] * bv[j];
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) atomicAdd(dW + (size_t)(cg * 8 + i) * dim + k0 + kg * 4 + j, acc[i][j]);
+static size_t bwd_scatter_bytes(size_t rows, int B) {  // A, E scatter buffers + per-image channel sums, 256-aligned
+    return ((rows * 128 * 4 * 2 + (size_t)B * 128 * 4) + 255) / 256 * 256;
 }
 
 size_t decoder_backward_workspace_bytes(int B, int gin_h, int gin_w) {
     const size_t rows = (size_t)B * gin_h * gin_w;
-    return rows * 128 * 4 * 3 + (size_t)B * 128 * 4 + 4096;  // A, E, dD, tsum
+    // A, E, tsum | dDt (bf16, transposed), split-K partial tiles, column-sum partials (wgrad.cu); dim <= 1024
+    size_t wg = 0;
+    for (int dim = 256; dim <= 1024; dim += 256) {
+        const size_t n = wgrad_workspace_bytes((int)rows, dim);
+        wg = n > wg ? n : wg;
+    }
+    return bwd_scatter_bytes(rows, B) + wg + 4096;
 }
 
 int decoder_backward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_h, int out_w, const DecoderWeights& w,
@@ -523,19 +527,17 @@ int decoder_backward(const void* keys_bf16, int B, int gin_h, int gin_w, int out
     const float* fhat = reinterpret_cast<const float*>(fb + off);
     off += (size_t)B * npix * 128 * 4;
     const float* gram = reinterpret_cast<const float*>(fb + off);
+    UCOD_REQUIRE(w.dim <= 1024 && w.dim % 256 == 0, "decoder_backward: dim must be a multiple of 256 (<= 1024)");
+    UCOD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "decoder_backward: workspace must be 256-byte aligned");
     float* a_buf = static_cast<float*>(workspace);
     float* e_buf = a_buf + rows * 128;
-    float* dD = e_buf + rows * 128;
-    float* tsum = dD + rows * 128;
-    UCOD_CHECK_CUDA(cudaMemsetAsync(a_buf, 0, rows * 128 * 4 * 2, stream));
-    UCOD_CHECK_CUDA(cudaMemsetAsync(tsum, 0, (size_t)B * 128 * 4, stream));
-    UCOD_CHECK_CUDA(cudaMemsetAsync(g.w_dec, 0, (size_t)128 * w.dim * 4, stream));
-    UCOD_CHECK_CUDA(cudaMemsetAsync(g.b_dec, 0, 128 * 4, stream));
-    UCOD_CHECK_CUDA(cudaMemsetAsync(g.w_fg, 0, 64 * 4, stream));
-    UCOD_CHECK_CUDA(cudaMemsetAsync(g.w_bg, 0, 64 * 4, stream));
-    UCOD_CHECK_CUDA(cudaMemsetAsync(g.b_fg, 0, 4, stream));
-    UCOD_CHECK_CUDA(cudaMemsetAsync(g.b_bg, 0, 4, stream));
-    UCOD_CHECK_CUDA(cudaMemsetAsync(loss2, 0, 8, stream));
+    float* tsum = e_buf + rows * 128;
+    uint8_t* wg_ws = static_cast<uint8_t*>(workspace) + bwd_scatter_bytes(rows, B);
+    const size_t wg_bytes = ws_bytes - bwd_scatter_bytes(rows, B);
+    // one memset for the scatter targets (A, E, tsum are contiguous), one launch for the five small accumulators; the
+    // weight / bias gradient of the 1x1 conv is written (not accumulated) by the split-K reduction
+    UCOD_CHECK_CUDA(cudaMemsetAsync(a_buf, 0, rows * 128 * 4 * 2 + (size_t)B * 128 * 4, stream));
+    decoder_bwd_zero_kernel<<<1, 64, 0, stream>>>(g.w_fg, g.w_bg, g.b_fg, g.b_bg, loss2);
     {
         dim3 grid(ceil_div(npix, DEC_PIX_PER_BLOCK), B);
         ProfScope ps(KC_DECODER, stream, (double)B * npix * 128 * 4 * 2 + (double)rows * 128 * 4 * 3);
@@ -544,24 +546,8 @@ int decoder_backward(const void* keys_bf16, int B, int gin_h, int gin_w, int out
                                                             g.b_fg, g.w_bg, g.b_bg, loss2, B, gin_h, gin_w, out_h, out_w);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
-    {
-        ProfScope ps(KC_DECODER, stream, (double)rows * 128 * 4 * 3);
-        decoder_bwd_finish_kernel<<<ceil_div((int)rows, 64), 256, 0, stream>>>(a_buf, e_buf, tsum, sumsq, w.emb, dD,
-                                                                               g.b_dec, gin_h * gin_w, (int)rows);
-    }
-    UCOD_CHECK_CUDA(cudaGetLastError());
-    {
-        int splits = ceil_div(2 * device_sm_count(), w.dim / 64);
-        int tps = ceil_div((int)rows, splits);
-        tps = ceil_div(tps, 16) * 16;
-        splits = ceil_div((int)rows, tps);
-        dim3 grid(w.dim / 64, splits);
-        ProfScope ps(KC_DECODER, stream, (double)rows * (128 * 4 + w.dim * 2));
-        decoder_wgrad_kernel<<<grid, 256, 0, stream>>>(dD, static_cast<const __nv_bfloat16*>(keys_bf16), g.w_dec,
-                                                       (int)rows, w.dim, tps);
-    }
-    UCOD_CHECK_CUDA(cudaGetLastError());
-    return 0;
+    return wgrad_tensor_core(a_buf, e_buf, tsum, sumsq, w.emb, keys_bf16, gin_h * gin_w, (int)rows, w.dim, g.w_dec,
+                             g.b_dec, wg_ws, wg_bytes, stream);
 }
 
 // Fused AdamW (torch semantics, decoupled weight decay) + EMA of the updated parameters

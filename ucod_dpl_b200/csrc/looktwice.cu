@@ -122,9 +122,308 @@ __global__ void ccl_roots_kernel(const int* __restrict__ L, int* __restrict__ ar
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Run-based connected components in shared memory: ONE CTA labels one whole mask without ever materialising a label
+// image.  The u8 mask (the only HBM-sized read: H*W bytes) is packed to one bit per pixel with warp ballots; rows are
+// cut into runs of foreground pixels; runs of adjacent rows that touch (8-connectivity: overlap after growing by one
+// pixel) are united with a union-find over RUN indices (atomicMin linking in shared memory); component areas are
+// accumulated per root, the big components (area fraction > 0.01) get bounding box and OpenCV first-block key from
+// their runs.  Outputs are the per-image summary / big-component tables the box kernel (`lt_boxes_kernel`) consumes.
+// Shared memory: bit image (4*H*ceil(W/32) B, later reused for the per-root accumulators) + 8 B per run.
+// Capacity: `rmax` runs and as many components as the bit image has words; a mask beyond that sets flag 4 in the
+// summary (nbox = -3) and the host re-runs that batch through the global-memory labeller.  Masks that come from a
+// bilinearly up-sampled fs x fs logit map have at most fs/2+1 runs per row and (fs/2)^2 components — 18 130 runs and
+// 1 156 components for 68 -> 518 — so the Look-Twice pipeline never overflows.
+// ------------------------------------------------------------------------------------------------
 struct BigStats {
     int x0, x1, y0, y1, key;
 };
+
+__device__ __forceinline__ int rl_find(const int* parent, int i) {
+    const volatile int* V = parent;
+    while (true) {
+        const int p = V[i];
+        if (p == i) return i;
+        i = p;
+    }
+}
+__device__ __forceinline__ void rl_union(int* parent, int a, int b) {
+    while (true) {
+        a = rl_find(parent, a);
+        b = rl_find(parent, b);
+        if (a == b) return;
+        if (a < b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+    ccl_runs_kernel(const uint8_t* __restrict__ mask, int H, int W, int rmax, ImgSummary* __restrict__ summ,
+                    int* __restrict__ big_area, BigStats* __restrict__ st, int* __restrict__ labels_out,
+                    double big_gate) {
+    extern __shared__ __align__(16) uint8_t ccl_smem[];
+    const int WW = (W + 31) >> 5;
+    uint32_t* bits = reinterpret_cast<uint32_t*>(ccl_smem);              // [H * WW]; later: acc[] per root slot
+    int* acc = reinterpret_cast<int*>(ccl_smem);
+    int* row_off = reinterpret_cast<int*>(bits + (size_t)H * WW);       // [H + 1]
+    int* parent = row_off + (H + 1);                                     // [rmax]
+    uint16_t* rs = reinterpret_cast<uint16_t*>(parent + rmax);           // [rmax] run start x
+    uint16_t* re = rs + rmax;                                            // [rmax] run end x (inclusive)
+    __shared__ int s_scan[33];
+    __shared__ int s_total, s_roots, s_max_area, s_nbig, s_flags;
+    __shared__ BigStats s_big[LT_MAXBIG];
+    __shared__ int s_big_area[LT_MAXBIG];
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int stage_bytes = ((W + 15 + 16) >> 4) << 4;  // one staged row per warp (16-byte vectors incl. head / tail)
+    if (tid == 0) s_max_area = 0, s_nbig = 0, s_flags = 0, s_roots = 0;
+    for (int i = tid; i < LT_MAXBIG; i += blockDim.x) {
+        s_big[i].x0 = W, s_big[i].x1 = -1, s_big[i].y0 = H, s_big[i].y1 = -1, s_big[i].key = 0x7fffffff;
+        s_big_area[i] = 0;
+    }
+
+    // ---- 1. bit image: one warp per row.  The row is staged in shared memory with 16-byte loads from the
+    //         aligned-down address (all of a row's loads are in flight together: one memory round trip per row instead
+    //         of one per 32 pixels), then one ballot per 32 pixels turns it into words ----
+    {
+        uint8_t* stage = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(re + rmax) + 15) & ~uintptr_t(15)) +
+                         (size_t)warp * stage_bytes;
+        const size_t total_bytes = (size_t)gridDim.x * H * W;
+        for (int y = warp; y < H; y += nwarps) {
+            const size_t off = ((size_t)b * H + y) * W;       // byte offset of the row in the batch tensor
+            const uint8_t* row = mask + off;
+            const int head = (int)(reinterpret_cast<uintptr_t>(row) & 15);
+            const int nvec = (head + W + 15) >> 4;
+            for (int v = lane; v < nvec; v += 32) {
+                // bytes [16 v - head, 16 v - head + 16) of the row; stay inside the tensor at both ends
+                const long long lo = (long long)off + 16ll * v - head;
+                if (lo >= 0 && (size_t)lo + 16 <= total_bytes) {
+                    reinterpret_cast<uint4*>(stage)[v] = __ldg(reinterpret_cast<const uint4*>(mask + lo));
+                } else {
+                    for (int k = 0; k < 16; ++k) {
+                        const long long a = lo + k;
+                        stage[16 * v + k] = (a >= 0 && (size_t)a < total_bytes) ? mask[a] : 0;
+                    }
+                }
+            }
+            __syncwarp();
+            for (int w0 = 0; w0 < WW; ++w0) {
+                const int x = w0 * 32 + lane;
+                const uint32_t word = __ballot_sync(0xffffffffu, x < W && stage[head + x] != 0);
+                if (lane == 0) bits[y * WW + w0] = word;
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- 2. runs per row (count, exclusive scan over rows, extraction) ----
+    int my_cnt = 0;
+    if (tid < H) {
+        uint32_t carry = 0;
+        for (int w0 = 0; w0 < WW; ++w0) {
+            const uint32_t v = bits[tid * WW + w0];
+            my_cnt += __popc(v & ~((v << 1) | carry));
+            carry = v >> 31;
+        }
+    }
+    {   // block-wide exclusive scan of my_cnt over tid (H <= blockDim.x)
+        int incl = my_cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = lane < nwarps ? s_scan[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            s_scan[lane] = v;  // inclusive totals per warp
+            if (lane == 31) s_total = v;
+        }
+        __syncthreads();
+        const int base = (warp > 0 ? s_scan[warp - 1] : 0) + incl - my_cnt;
+        if (tid < H) row_off[tid] = base;
+        if (tid == 0) row_off[H] = s_total;
+    }
+    __syncthreads();
+    const int n_runs = s_total;
+    if (n_runs > rmax) {  // out of run slots: flagged, nothing else is written for this image
+        if (tid == 0) {
+            summ[b].n_comp = 0, summ[b].max_area = 0, summ[b].n_big = 0, summ[b].pad = 4;
+        }
+        return;
+    }
+    if (tid < H) {
+        int o = row_off[tid];
+        bool in_run = false;
+        for (int w0 = 0; w0 < WW; ++w0) {
+            uint32_t v = bits[tid * WW + w0];
+            int pos = 0;  // bits below `pos` are consumed
+            while (pos < 32) {
+                const uint32_t rest = pos ? (v >> pos) : v;
+                if (!in_run) {
+                    if (rest == 0) break;
+                    const int s = __ffs(rest) - 1;
+                    pos += s;
+                    rs[o] = (uint16_t)(w0 * 32 + pos);
+                    in_run = true;
+                } else {
+                    const uint32_t inv = ~rest & (pos ? (0xffffffffu >> pos) : 0xffffffffu);
+                    if (inv == 0) {  // run continues to the end of the word
+                        pos = 32;
+                        break;
+                    }
+                    const int e = __ffs(inv) - 1;
+                    pos += e;
+                    re[o++] = (uint16_t)(w0 * 32 + pos - 1);
+                    in_run = false;
+                }
+            }
+        }
+        if (in_run) re[o++] = (uint16_t)(W - 1);  // bits past W are zero, so this only happens at the row end
+    }
+    for (int i = tid; i < n_runs; i += blockDim.x) parent[i] = i;
+    __syncthreads();
+
+    // ---- 3. unite touching runs of adjacent rows (two-pointer walk per row pair) ----
+    if (tid >= 1 && tid < H) {
+        int i = row_off[tid - 1], j = row_off[tid];
+        const int ie = row_off[tid], je = row_off[tid + 1];
+        while (i < ie && j < je) {
+            const int as = rs[i], ae = re[i], bs = rs[j], be = re[j];
+            if (as <= be + 1 && bs <= ae + 1) rl_union(parent, i, j);
+            if (ae < be) ++i; else ++j;
+        }
+    }
+    __syncthreads();
+    // ---- 4. flatten, count roots, give every root an accumulator slot ----
+    for (int i = tid; i < n_runs; i += blockDim.x) parent[i] = rl_find(parent, i);
+    __syncthreads();
+    const int acc_cap = H * WW;
+    for (int i0 = 0; i0 < n_runs; i0 += blockDim.x) {  // roots get slots in run order (chunked block scan)
+        const int i = i0 + tid;
+        const int is_root = (i < n_runs && parent[i] == i) ? 1 : 0;
+        int incl = is_root;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_scan[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int v = lane < nwarps ? s_scan[lane] : 0;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            s_scan[lane] = v;
+        }
+        __syncthreads();
+        const int slot = s_roots + (warp > 0 ? s_scan[warp - 1] : 0) + incl - is_root;
+        if (is_root && slot < acc_cap) parent[i] = -1 - slot;
+        __syncthreads();
+        if (tid == 0) s_roots += s_scan[31];
+        __syncthreads();
+    }
+    const int n_roots = s_roots;
+    if (n_roots > acc_cap) {
+        if (tid == 0) summ[b].n_comp = 0, summ[b].max_area = 0, summ[b].n_big = 0, summ[b].pad = 4;
+        return;
+    }
+    for (int i = tid; i < n_roots; i += blockDim.x) acc[i] = 0;  // (the bit image is no longer needed)
+    __syncthreads();
+    auto slot_of = [&](int i) {
+        const int p = parent[i];
+        return p < 0 ? -1 - p : -1 - parent[p];
+    };
+    // ---- 5. areas ----
+    for (int i = tid; i < n_runs; i += blockDim.x) atomicAdd(&acc[slot_of(i)], (int)re[i] - (int)rs[i] + 1);
+    __syncthreads();
+    // ---- 6. largest component, big components ----
+    const double hw = (double)((long long)H * W);
+    for (int k = tid; k < n_roots; k += blockDim.x) {
+        const int a = acc[k];
+        atomicMax(&s_max_area, a);
+        if (__ddiv_rn((double)a, hw) > big_gate) {
+            const int bslot = atomicAdd(&s_nbig, 1);
+            if (bslot < LT_MAXBIG) {
+                s_big_area[bslot] = a;
+                acc[k] = -(bslot + 1);
+            }
+        }
+    }
+    __syncthreads();
+    // ---- 7. bounding box / OpenCV first-block key of the big components, from their runs (thread per row) ----
+    if (tid < H && s_nbig > 0) {
+        const int half_w = (W + 1) >> 1;
+        for (int i = row_off[tid]; i < row_off[tid + 1]; ++i) {
+            const int a = acc[slot_of(i)];
+            if (a >= 0) continue;
+            BigStats* g = &s_big[-a - 1];
+            atomicMin(&g->x0, (int)rs[i]);
+            atomicMax(&g->x1, (int)re[i]);
+            atomicMin(&g->y0, tid);
+            atomicMax(&g->y1, tid);
+            atomicMin(&g->key, (tid >> 1) * half_w + ((int)rs[i] >> 1));
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        summ[b].n_comp = n_roots, summ[b].max_area = s_max_area, summ[b].n_big = s_nbig, summ[b].pad = 0;
+    }
+    for (int i = tid; i < LT_MAXBIG; i += blockDim.x) {
+        st[b * LT_MAXBIG + i] = s_big[i];
+        big_area[b * LT_MAXBIG + i] = s_big_area[i];
+    }
+    // ---- 8. optional label image: every pixel gets the smallest raster index of its component, background -1 ----
+    if (labels_out != nullptr) {
+        int* L = labels_out + (size_t)b * H * W;
+        for (int i = tid; i < H * W; i += blockDim.x) L[i] = -1;
+        __syncthreads();
+        if (tid < H) {
+            for (int i = row_off[tid]; i < row_off[tid + 1]; ++i) {
+                const int p = parent[i];
+                const int root = p < 0 ? i : p;
+                int lo = 0, hi = H;  // row of the root run: last y with row_off[y] <= root
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (row_off[mid] <= root) lo = mid; else hi = mid;
+                }
+                const int lab = lo * W + (int)rs[root];
+                for (int x = rs[i]; x <= re[i]; ++x) L[tid * W + x] = lab;
+            }
+        }
+    }
+}
+
+static size_t ccl_runs_smem_bytes(int H, int W, int rmax) {
+    const size_t ww = (size_t)((W + 31) >> 5);
+    const size_t stage = (size_t)(((W + 15 + 16) >> 4) << 4) * 32;  // per-warp row staging
+    return (size_t)H * ww * 4 + (size_t)(H + 1) * 4 + (size_t)rmax * 8 + stage + 16;
+}
+// run capacity that fits the 227 KB of one CTA (0: this geometry cannot use the shared-memory labeller)
+static int ccl_runs_capacity(int H, int W) {
+    if (H > 1024 || W > 65535) return 0;
+    const size_t fixed = ccl_runs_smem_bytes(H, W, 0) + 6 * 1024;  // + the kernel's static shared arrays
+    const size_t budget = 227 * 1024;
+    if (fixed + 8 * 1024 > budget) return 0;
+    return (int)((budget - fixed) / 8) & ~7;
+}
 
 __global__ void ccl_bbox_kernel(const int* __restrict__ L, const int* __restrict__ area, BigStats* __restrict__ st,
                                 int H, int W, int B) {
@@ -169,8 +468,12 @@ __global__ void lt_boxes_kernel(const ImgSummary* __restrict__ summ, const int* 
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     int* out = boxes + (size_t)b * LT_MAXBIG * 4;
-    status[b] = 0;
     const ImgSummary s = summ[b];
+    status[b] = s.pad & 4;
+    if (s.pad & 4) {  // the shared-memory labeller ran out of run / component slots for this mask
+        nbox[b] = -3;
+        return;
+    }
     if (s.n_comp == 0) {  // loop_UCOD_DPL.py:369-370
         out[0] = 129, out[1] = 129, out[2] = 259, out[3] = 259;
         nbox[b] = 1;
@@ -488,10 +791,11 @@ size_t lt_boxes_workspace_bytes(int B, int H, int W) {
 
 int lt_boxes(const uint8_t* mask, int B, int H, int W, double look_twice_th, int dynamic, double const_scale,
              int* boxes, int* nbox, int* status, int* labels_out, void* workspace, size_t ws_bytes,
-             cudaStream_t stream) {
+             cudaStream_t stream, int algorithm) {
     UCOD_REQUIRE(mask && boxes && nbox && status && workspace, "lt_boxes: null argument");
     UCOD_REQUIRE(B > 0 && H > 0 && W > 0 && (long long)H * W < (1ll << 30), "lt_boxes: bad geometry");
     UCOD_REQUIRE(ws_bytes >= lt_boxes_workspace_bytes(B, H, W), "lt_boxes: workspace too small");
+    UCOD_REQUIRE(algorithm >= 0 && algorithm <= 2, "lt_boxes: algorithm must be 0 (auto), 1 (global) or 2 (shared)");
     const int n_img = H * W;
     const size_t total = (size_t)B * n_img;
     uint8_t* p = static_cast<uint8_t*>(workspace);
@@ -506,6 +810,29 @@ int lt_boxes(const uint8_t* mask, int B, int H, int W, double look_twice_th, int
     int* big_area = reinterpret_cast<int*>(p);
     p += align256((size_t)B * LT_MAXBIG * 4);
     BigStats* st = reinterpret_cast<BigStats*>(p);
+
+    const int rmax = ccl_runs_capacity(H, W);
+    UCOD_REQUIRE(algorithm != 2 || rmax > 0, "lt_boxes: %d x %d masks do not fit the shared-memory labeller", H, W);
+    if (algorithm != 1 && rmax > 0) {
+        // run-based labelling in shared memory, one CTA per mask (no label image, no global atomics)
+        const size_t smem = ccl_runs_smem_bytes(H, W, rmax);
+        static size_t configured = 0;
+        if (smem > configured) {
+            UCOD_CHECK_CUDA(cudaFuncSetAttribute(ccl_runs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        {
+            ProfScope ps(KC_CCL, stream, (double)total * 9);  // credited like the global path
+            ccl_runs_kernel<<<B, 1024, smem, stream>>>(mask, H, W, rmax, summ, big_area, st, labels_out, 0.01);
+        }
+        {
+            ProfScope ps(KC_CCL, stream, 0.0);
+            lt_boxes_kernel<<<ceil_div(B, 32), 32, 0, stream>>>(summ, big_area, st, boxes, nbox, status, B, H, W,
+                                                               look_twice_th, dynamic, const_scale);
+        }
+        UCOD_CHECK_CUDA(cudaGetLastError());
+        return 0;
+    }
 
     UCOD_CHECK_CUDA(cudaMemsetAsync(area, 0, total * 4, stream));
     UCOD_CHECK_CUDA(cudaMemsetAsync(summ, 0, (size_t)B * sizeof(ImgSummary), stream));

@@ -9,7 +9,7 @@ constexpr int LT_MAX_BOXES = 128;
 size_t lt_boxes_workspace_bytes(int B, int H, int W);
 int lt_boxes(const uint8_t* mask, int B, int H, int W, double look_twice_th, int dynamic, double const_scale,
              int* boxes, int* nbox, int* status, int* labels_out, void* workspace, size_t ws_bytes,
-             cudaStream_t stream);
+             cudaStream_t stream, int algorithm = 0);
 size_t roi_crop_resize_workspace_bytes(int njobs, int max_crop_h, int out_h, int out_w);
 int roi_crop_resize(const uint8_t* images, int n_img, int H0, int W0, long long img_stride, long long ch_stride,
                     long long row_stride, long long px_stride, const int* jobs, int njobs, int max_crop_h,

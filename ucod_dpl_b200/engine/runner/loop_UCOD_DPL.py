@@ -39,13 +39,22 @@ class LookTwiceResult:
     `LookTwiceEvaluator.look_twice_device`).
     `bboxes` converts the box table to the reference's per-image lists (also a host read)."""
 
-    def __init__(self, final, first, boxes, nbox, counts, err, canvas=None, resume=None):
+    def __init__(self, final, first, boxes, nbox, counts, err, canvas=None, resume=None, redo=None):
         self.final, self.first, self.boxes, self.nbox, self.counts, self.err = final, first, boxes, nbox, counts, err
-        self.canvas, self._resume = canvas, resume
+        self.canvas, self._resume, self._redo = canvas, resume, redo
         self._lists = None
 
     def check(self) -> None:
         nb = self.nbox.cpu()
+        if bool((nb == -3).any()) and self._redo is not None:
+            # a mask exceeded the shared-memory labeller's run capacity (never the case for masks up-sampled from the
+            # decoder's logit grid): redo the batch with the global-memory labeller
+            other = self._redo()
+            other.check()
+            for name in ("final", "first", "boxes", "nbox", "counts", "err", "canvas"):
+                setattr(self, name, getattr(other, name))
+            self._resume = self._redo = None
+            return
         if bool((nb == -2).any()):
             raise ValueError("math domain error")  # expand_bbox: sqrt of a negative scale (reference raises too)
         if self.counts is not None:
@@ -98,6 +107,8 @@ class LookTwiceEvaluator:
         h, w = self.img_size
         mask = ops.upsample_bilinear(preds[:, 0], (h, w), binarize=True)
         boxes, nbox, status, _ = ops.lt_boxes(mask, self.look_twice_th, self.expand_type)
+        if bool((nbox == -3).any()):  # labeller capacity (see ops.lt_boxes)
+            boxes, nbox, status, _ = ops.lt_boxes(mask, self.look_twice_th, self.expand_type, algorithm="global")
         res = LookTwiceResult(None, mask, boxes, nbox, None, None)
         res.check()
         up = mask.float()
@@ -173,7 +184,8 @@ class LookTwiceEvaluator:
 
     @torch.no_grad()
     def look_twice_device(self, images: torch.Tensor, originals: torch.Tensor | None = None, layout: str = "CHW",
-                          orig_sizes=None, first_logits: torch.Tensor | None = None) -> LookTwiceResult:
+                          orig_sizes=None, first_logits: torch.Tensor | None = None,
+                          ccl_algorithm: str = "auto") -> LookTwiceResult:
         """The whole of loop_UCOD_DPL.py:297-313 for a batch, enqueued without a single host synchronisation.
         images: network-size inputs [N,3,S,S] (uint8 raw or fp32 normalised); originals: the original-resolution
         uint8 images the crops are taken from (defaults to `images` when they are uint8; with `orig_sizes` [N,2] a
@@ -189,10 +201,14 @@ class LookTwiceEvaluator:
             fg = first_logits
         ih, iw = self.img_size
         mask = ops.upsample_bilinear(fg[:, 0], (ih, iw), binarize=True)
-        boxes, nbox, _, _ = ops.lt_boxes(mask, self.look_twice_th, self.expand_type)
+        boxes, nbox, _, _ = ops.lt_boxes(mask, self.look_twice_th, self.expand_type, algorithm=ccl_algorithm)
         canvas = ops.mask_scale_u8(mask, 255)
+        redo = None
+        if ccl_algorithm != "global":
+            redo = lambda: self.look_twice_device(images, originals, layout, orig_sizes, first_logits, "global")  # noqa: E731
         if not self.enabled:
-            return LookTwiceResult(ops.to_tensor_normalize(canvas[:, None])[:, 0], mask, boxes, nbox, None, None)
+            return LookTwiceResult(ops.to_tensor_normalize(canvas[:, None])[:, 0], mask, boxes, nbox, None, None,
+                                   redo=redo)
         if originals is None:
             if images.dtype != torch.uint8:
                 raise ValueError("originals (uint8) are required when `images` are already normalised")
@@ -234,7 +250,7 @@ class LookTwiceEvaluator:
                     run_chunk(c)
                 res.final.copy_(ops.to_tensor_normalize(canvas[:, None])[:, 0])
 
-        return LookTwiceResult(final, mask, boxes, nbox, counts, err, canvas=canvas, resume=resume)
+        return LookTwiceResult(final, mask, boxes, nbox, counts, err, canvas=canvas, resume=resume, redo=redo)
 
     @torch.no_grad()
     def __call__(self, images: torch.Tensor, originals: torch.Tensor | None = None, layout: str = "CHW",

@@ -130,9 +130,14 @@ def refine_small_components(mask_u8: torch.Tensor, area_threshold: int = 4) -> t
 LT_MAX_BOXES = 128
 
 
+LT_ALGORITHMS = {"auto": 0, "global": 1, "shared": 2}
+
+
 def lt_boxes(mask_u8: torch.Tensor, look_twice_th: float, expand_type: str = "dynamic", const_scale: float = 1.3,
-             want_labels: bool = False):
-    """mask uint8 [B,H,W] -> (boxes int32 [B,128,4], nbox int32 [B], status int32 [B], labels int32 [B,H,W] | None)."""
+             want_labels: bool = False, algorithm: str = "auto"):
+    """mask uint8 [B,H,W] -> (boxes int32 [B,128,4], nbox int32 [B], status int32 [B], labels int32 [B,H,W] | None).
+    algorithm: "auto" / "shared" label each mask in one CTA's shared memory (run-based; nbox = -3 for a mask that
+    exceeds its capacity — callers re-run with "global"), "global" is the union-find over pixels in HBM."""
     _lib.require_cuda(mask_u8)
     m = mask_u8.to(torch.uint8).contiguous()
     B, H, W = m.shape
@@ -146,9 +151,9 @@ def lt_boxes(mask_u8: torch.Tensor, look_twice_th: float, expand_type: str = "dy
     ws = _ws(lib.ucod_lt_boxes_workspace_bytes(B, H, W), dev)
     wp, wn = _aligned(ws)
     with torch.cuda.device(dev):
-        _lib.call("ucod_lt_boxes", ptr(m), B, H, W, ctypes.c_double(look_twice_th),
+        _lib.call("ucod_lt_boxes_ex", ptr(m), B, H, W, ctypes.c_double(look_twice_th),
                   1 if expand_type == "dynamic" else 0, ctypes.c_double(const_scale), ptr(boxes), ptr(nbox),
-                  ptr(status), ptr(labels), wp, wn, stream_ptr(dev))
+                  ptr(status), ptr(labels), wp, wn, LT_ALGORITHMS[algorithm], stream_ptr(dev))
     return boxes, nbox, status, labels
 
 

@@ -105,8 +105,18 @@ class FirstStageTrainer:
 
     def __init__(self, model, discriminator, *, lr0: float = 2e-4, step_lr_size: int = 25, step_lr_gamma: float = 0.95,
                  feature_size: int = 68, ema_weight: float = 0.99, max_epoch: int = 25, start_finetune: int = -5,
-                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, process_group=None):
+                 betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.01, process_group=None,
+                 use_graph: bool = False):
         self.model, self.discriminator = model, discriminator
+        # CUDA-graph replay of the forward / APM / backward kernel sequence (~45 launches and 9 memsets per step, each
+        # a few microseconds of GPU time: eagerly the step is bound by the host enqueueing them).  The graph is
+        # captured after two eager steps and re-captured when the batch geometry, the epoch (the APM schedule term is
+        # a launch argument) or the finetune flag change; the gradient all-reduce and the AdamW / EMA kernel, whose
+        # scalars change every step, stay outside it.
+        self.use_graph = bool(use_graph)
+        self._graph = None
+        self._graph_key = None
+        self._eager_left = 0
         self.fs = int(feature_size)
         self.lr0, self.step_size, self.gamma = lr0, step_lr_size, step_lr_gamma
         self.ema_weight, self.max_epoch, self.start_finetune = ema_weight, max_epoch, start_finetune
@@ -161,14 +171,16 @@ class FirstStageTrainer:
         self.flat_v.zero_()
 
     @torch.no_grad()
-    def process_batch(self, key_tokens_bf16: torch.Tensor, grid_in, pseudo_labels: torch.Tensor):
-        """key_tokens_bf16 [B, gh*gw, dim] (cached backbone keys), pseudo_labels [B,1,16,16] {0,1}.
-        Returns the loss tensor (device scalar), like `_process_batch`."""
+    def _forward_backward(self, key_tokens_bf16: torch.Tensor, grid_in, pseudo_labels: torch.Tensor):
+        """teacher fwd, student fwd, APM merge, BCE + ortho loss, decoder backward into `self.flat_g`.
+        Returns (loss, dict of intermediates); only enqueues device work (graph-capturable)."""
         dec, ema = self.model.decoder, self.model.decoder_ema
         fs = (self.fs, self.fs)
         pl = ops.upsample_bilinear(pseudo_labels.float(), fs)                    # F.interpolate(pl, 68x68)
+        # both decoders' weights are rewritten in place by the fused AdamW / EMA kernel (raw pointers: torch's version
+        # counters do not move), so their cached bf16 copies of the 1x1 conv weight are rebuilt every step
+        dec._packed = ema._packed = None
         teacher, _, _ = ema.forward_tokens(key_tokens_bf16, grid_in, fs, want_bg=False)
-        dec._packed = None                                                       # weights changed last step
         fg, bg, ortho, ws = _forward_with_workspace(dec, key_tokens_bf16, grid_in, fs)
         merged, dis_loss = merge_pseudo_label(self.discriminator, pl, teacher, fg, None, cur_epoch=self.cur_epoch,
                                               max_epoch=self.max_epoch, start_finetune=self.start_finetune)
@@ -177,6 +189,10 @@ class FirstStageTrainer:
         loss = loss2.sum() + ortho
         if not self.finetune:
             loss = loss - dis_loss
+        return loss, {"merged": merged, "dis_loss": dis_loss, "ortho": ortho, "bce": loss2}
+
+    @torch.no_grad()
+    def _optimizer_step(self) -> None:
         world = 1
         if self.pg is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             world = torch.distributed.get_world_size(self.pg)
@@ -192,8 +208,37 @@ class FirstStageTrainer:
                       c_float(self.eps), c_float(self.wd), int(self.opt_steps), c_float(1.0 / world), c_float(alpha),
                       stream_ptr(dev))
         self.global_step += 2
-        self.last = {"merged": merged, "dis_loss": dis_loss, "ortho": ortho, "bce": loss2}
-        return loss
+
+    @torch.no_grad()
+    def process_batch(self, key_tokens_bf16: torch.Tensor, grid_in, pseudo_labels: torch.Tensor):
+        """key_tokens_bf16 [B, gh*gw, dim] (cached backbone keys), pseudo_labels [B,1,16,16] {0,1}.
+        Returns the loss tensor (device scalar), like `_process_batch`."""
+        if not self.use_graph:
+            loss, self.last = self._forward_backward(key_tokens_bf16, grid_in, pseudo_labels)
+            self._optimizer_step()
+            return loss
+        key = (tuple(key_tokens_bf16.shape), tuple(pseudo_labels.shape), tuple(grid_in), self.cur_epoch, self.finetune)
+        if key != self._graph_key:
+            self._graph, self._graph_key, self._eager_left = None, key, 2
+        if self._graph is None and self._eager_left > 0:       # real steps, also warm every kernel / allocation up
+            self._eager_left -= 1
+            loss, self.last = self._forward_backward(key_tokens_bf16, grid_in, pseudo_labels)
+            self._optimizer_step()
+            return loss
+        if self._graph is None:
+            self._s_tok = key_tokens_bf16.clone()
+            self._s_pl = pseudo_labels.clone()
+            torch.cuda.synchronize(self.flat_p.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._s_loss, self._s_last = self._forward_backward(self._s_tok, grid_in, self._s_pl)
+            self._graph = g
+        self._s_tok.copy_(key_tokens_bf16)
+        self._s_pl.copy_(pseudo_labels)
+        self._graph.replay()
+        self.last = self._s_last
+        self._optimizer_step()
+        return self._s_loss
 
 
 class _DiscPtrs(ctypes.Structure):
