@@ -27,7 +27,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 def main():
     rep = sys.argv[1]
     outdir = Path(sys.argv[2]) if len(sys.argv) > 2 else ROOT / "profiles"
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True,
+                         text=True).stdout
     rows = list(csv.reader(l for l in out.splitlines() if l.startswith('"')))
     hdr = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}

@@ -689,6 +689,77 @@ __global__ void crop_vpass_kernel(const uint8_t* __restrict__ tmp, const int* __
     *dst = clip8(acc);
 }
 
+// ---- crop + both resampling passes in one kernel.  CTA = (tile of CR_TY output rows, channel, job): the source rows
+// the tile's vertical taps touch are resampled horizontally into shared memory (u8, rounded like Pillow's first pass),
+// then the vertical pass reads them from there — the intermediate image never goes to HBM and the grid has one CTA per
+// 16 output rows instead of one per source row (round 1: 2 x 500 k mostly idle CTAs per chunk, 0.67 ms each).
+// When a tile needs more source rows than fit (large down-scales), it is processed in several vertical sub-tiles.
+constexpr int CR_TY = 16;        // output rows per CTA
+constexpr int CR_ROWS = 72;      // staged source rows (shared memory: CR_ROWS * out_w bytes)
+
+__global__ void __launch_bounds__(256)
+    crop_resize_fused_kernel(const uint8_t* __restrict__ images, int H0, int W0, long long img_stride,
+                             long long ch_stride, long long row_stride, long long px_stride,
+                             const int* __restrict__ jobs /*[n,5] img,x,y,w,h*/, const int2* __restrict__ bounds,
+                             const int* __restrict__ coef, uint8_t* __restrict__ out, int out_cap, int out_w, int out_h,
+                             int kmax, const int* __restrict__ njobs_dev) {
+    extern __shared__ uint8_t cr_rows[];  // [CR_ROWS][out_w]
+    const int job = blockIdx.z;
+    if (njobs_dev != nullptr && job >= __ldg(njobs_dev)) return;
+    const int c = blockIdx.y;
+    const int* jb = jobs + job * 5;
+    const int yy0 = blockIdx.x * CR_TY;
+    const int yy1 = min(out_h, yy0 + CR_TY);
+    uint8_t* dst = out + ((size_t)job * 3 + c) * out_h * out_w;
+    if (jb[3] <= 0 || jb[4] <= 0) {
+        for (int i = threadIdx.x; i < (yy1 - yy0) * out_w; i += blockDim.x) dst[(size_t)yy0 * out_w + i] = 0;
+        return;
+    }
+    const size_t vb = ((size_t)job * 2 + 1) * out_cap, hb = ((size_t)job * 2 + 0) * out_cap;
+    const int* kv = coef + ((size_t)job * 2 + 1) * kmax * out_cap;
+    const int* kh = coef + ((size_t)job * 2 + 0) * kmax * out_cap;
+    const uint8_t* plane = images + (size_t)jb[0] * img_stride + (size_t)c * ch_stride;
+    int ya = yy0;
+    while (ya < yy1) {
+        // sub-tile [ya, yb): as many output rows as their source-row span fits the staging buffer (at least one)
+        const int lo = bounds[vb + ya].x;
+        int yb = ya + 1;
+        while (yb < yy1 && bounds[vb + yb].x + bounds[vb + yb].y - lo <= CR_ROWS) ++yb;
+        const int hi = bounds[vb + yb - 1].x + bounds[vb + yb - 1].y;   // crop rows [lo, hi)
+        const int span = min(hi - lo, CR_ROWS);  // (one output row never needs more than kmax <= CR_ROWS rows: checked by the host)
+        __syncthreads();
+        // horizontal pass of the staged rows
+        for (int i = threadIdx.x; i < span * out_w; i += blockDim.x) {
+            const int r = i / out_w, xx = i - r * out_w;
+            const int sy = jb[2] + lo + r;
+            int acc = 1 << (RS_PRECISION_BITS - 1);
+            if (sy >= 0 && sy < H0) {
+                const int2 bd = bounds[hb + xx];
+                const uint8_t* row = plane + (size_t)sy * row_stride;
+                const int* kk = kh + xx;
+                for (int k = 0; k < bd.y; ++k) {
+                    const int sx = jb[1] + bd.x + k;
+                    const int px = (sx >= 0 && sx < W0) ? row[(size_t)sx * px_stride] : 0;
+                    acc += px * __ldg(kk + (size_t)k * out_cap);
+                }
+            }
+            cr_rows[i] = clip8(acc);
+        }
+        __syncthreads();
+        // vertical pass
+        for (int i = threadIdx.x; i < (yb - ya) * out_w; i += blockDim.x) {
+            const int yy = ya + i / out_w, xx = i % out_w;
+            const int2 bd = bounds[vb + yy];
+            const int* kk = kv + yy;
+            int acc = 1 << (RS_PRECISION_BITS - 1);
+            for (int k = 0; k < bd.y; ++k)
+                acc += (int)cr_rows[(bd.x - lo + k) * out_w + xx] * __ldg(kk + (size_t)k * out_cap);
+            dst[(size_t)yy * out_w + xx] = clip8(acc);
+        }
+        ya = yb;
+    }
+}
+
 // ---- paste: horizontal pass over the binarised g x g prediction ----
 __global__ void paste_hpass_kernel(const float* __restrict__ logits, int g_h, int g_w,
                                    const int* __restrict__ jobs /*[n,6] img,x,y,w,h,rank*/,
@@ -916,6 +987,22 @@ static int crop_resize_core(const uint8_t* images, int H0, int W0, long long img
         dim3 g(ceil_div(cap, 128), 2, njobs);
         resample_coeffs_kernel<<<g, 128, 0, stream>>>(sizes, sizes + njobs * 2, njobs, cap, kmax, 0, bounds, coef,
                                                       err_flag, njobs_dev);
+    }
+    if (kmax <= CR_ROWS && (size_t)CR_ROWS * out_w <= 200 * 1024) {
+        // fused path: no intermediate image in HBM
+        const size_t smem = (size_t)CR_ROWS * out_w;
+        static size_t configured = 0;
+        if (smem > configured && smem > 48 * 1024) {
+            UCOD_CHECK_CUDA(cudaFuncSetAttribute(crop_resize_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)smem));
+            configured = smem;
+        }
+        ProfScope ps(KC_RESAMPLE, stream, njobs_dev ? 0.0 : (double)njobs * 3 * ((double)max_crop_h * W0 + (double)out_h * out_w));
+        dim3 g(ceil_div(out_h, CR_TY), 3, njobs);
+        crop_resize_fused_kernel<<<g, 256, smem, stream>>>(images, H0, W0, img_stride, ch_stride, row_stride, px_stride,
+                                                           jobs, bounds, coef, out, cap, out_w, out_h, kmax, njobs_dev);
+        UCOD_CHECK_CUDA(cudaGetLastError());
+        return 0;
     }
     {
         ProfScope ps(KC_RESAMPLE, stream, njobs_dev ? 0.0 : (double)njobs * 3 * max_crop_h * (out_w + W0));
