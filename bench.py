@@ -304,7 +304,7 @@ def _side_workloads(args, dev, lib, vit_sd, dec_sd, ext, model, peaks, rank, wor
     D = Discriminator(SimpleNamespace(dis_use_features=False, dim=768, feature_size=FEATURE)).to(dev).train()
     m2 = baseline(SimpleNamespace(dim=768))
     m2.load_state_dict(dec_sd, strict=True)
-    tr = FirstStageTrainer(m2.to(dev).train(), D, lr0=2e-4)
+    tr = FirstStageTrainer(m2.to(dev).train(), D, lr0=2e-4, use_graph=True)   # CUDA-graph replay of fwd / APM / bwd
     tr.cur_epoch = 3
     g = torch.Generator().manual_seed(1 + rank)
     tok = torch.randn(16, 1369, 768, generator=g).to(torch.bfloat16).to(dev)
@@ -312,7 +312,8 @@ def _side_workloads(args, dev, lib, vit_sd, dec_sd, ext, model, peaks, rank, wor
     ms = _timed(lambda i: tr.process_batch(tok, (37, 37), pl), 100, 20, dev)
     tot, ms_c, work_c, n_c = prof.run(lambda i: tr.process_batch(tok, (37, 37), pl), 20, dev)
     finish("train_step_16", 16, ms, _kernel_table(ms_c, work_c, n_c, 20, tot, peaks),
-           {"collective": f"NCCL all-reduce of {tr.n} fp32 decoder gradients per step" if world > 1 else "none (1 GPU)"})
+           {"collective": f"NCCL all-reduce of {tr.n} fp32 decoder gradients per step" if world > 1 else "none (1 GPU)",
+            "cuda_graph": True})
     del tr, tok, pl
 
     # configs[3]: CORAL second-stage eval, 8 originals @1036^2 per launch (80 backbone passes + refiner windows)
