@@ -153,6 +153,11 @@ int ucod_upsample_bilinear(const float* in, void* out, int batch, int in_h, int 
 int ucod_pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf16, int batch, int heads, int patches,
                             float th_bkg, float epsilon, float* cos, uint8_t* bkg, int32_t* ref_idx, float* sim,
                             void* scratch, void* stream);
+/* Same with the reference's `apply_weights` switch (found_bkg_mask.py:44-47,64-65): 0 = neither the descriptors nor the
+ * per-patch attention sum are weighted by the head sparsity weights beta. */
+int ucod_pseudo_label_score_ex(const float* attn_cls, const void* keys, int keys_bf16, int batch, int heads, int patches,
+                               float th_bkg, float epsilon, int apply_weights, float* cos, uint8_t* bkg,
+                               int32_t* ref_idx, float* sim, void* scratch, void* stream);
 /* `refine_post_process` (generate_pseudo_label.py:30-67): flip 8-connected foreground components with
  * area < area_threshold whose 1-px ring is entirely the opposite label; OpenCV label order; h*w <= 1024.
  * mask_in/mask_out: uint8 {0,1} [batch, h, w] (may alias). */
@@ -312,6 +317,11 @@ int ucod_discriminator_bwd(const float* mask, int batch, int fs, const ucod_disc
  * [batch, window_size^2] (adaptive average pool > threshold); scratch: 4 device bytes. */
 int ucod_coral_entropy_select(const float* preds, int batch, int size, int window_size, float threshold,
                               float* entropy, float* scores, uint8_t* mask, void* scratch, void* stream);
+/* Same with the probability-or-logit decision taken per image (per_image != 0; scratch: batch * 4 device bytes): the
+ * reference evaluates at batch 1, so `torch.all((preds >= 0) & (preds <= 1))` (ASR.py:42) is a per-image test there. */
+int ucod_coral_entropy_select_ex(const float* preds, int batch, int size, int window_size, float threshold,
+                                 float* entropy, float* scores, uint8_t* mask, void* scratch, int per_image,
+                                 void* stream);
 /* CSF tail (CSF.py:41-42): depthwise 7x7 (pad 3) + 1x1 mask_dec folded into 49 taps per token.
  * taps fp32 [n_windows*grid*grid, ld_taps] (column ky*7+kx = sum_c mask_dec.w[c]*dw.w[c,ky,kx]*x[token,c]);
  * out fp32 [n_windows, grid, grid] = bias_const + zero-padded 7x7 gather-sum. */

@@ -22,9 +22,10 @@ from . import cc
 
 @torch.no_grad()
 def compute_img_bkg_seg(attentions, feats, featmap_dims, th_bkg, dim=64, epsilon: float = 1e-10,
-                        apply_weights: bool = True, id_ref_override=None, want_att_sum: bool = False):
+                        apply_weights: bool = True, id_ref_override=None, want_att_sum: bool = False, up_size=None):
     """attentions [B,nh,T,T] (or the CLS row [B,nh,P] directly), feats [B,T,C] incl. CLS (or [B,P,C]).
-    Returns (bkg_mask [B,h,w] float {0,1}, sim_map [B,h,w] float)."""
+    Returns (bkg_mask [B,h,w] float {0,1}, sim_map [B,h,w] float).  `up_size` (found_bkg_mask.py:19-20, :26-27,
+    :50-55): attention and descriptors are bilinearly resampled to up_size^2 before anything else."""
     w_f, h_f = featmap_dims
     P = w_f * h_f
     if attentions.dim() == 4:
@@ -35,6 +36,15 @@ def compute_img_bkg_seg(attentions, feats, featmap_dims, th_bkg, dim=64, epsilon
     att = att.reshape(nb, nh, P).float()
     descs = feats[:, 1:] if feats.shape[1] == P + 1 else feats
     descs = descs.float()
+    if up_size is not None and up_size != w_f:
+        att = F.interpolate(att.reshape(nb, nh, w_f, h_f), size=(up_size, up_size), mode="bilinear")
+        # the reference weights the descriptors by beta (constant per channel) and then interpolates; interpolation is
+        # linear per channel, so resampling first and weighting afterwards is the same arithmetic up to rounding
+        descs = F.interpolate(descs.reshape(nb, w_f, h_f, -1).permute(0, 3, 1, 2), size=(up_size, up_size), mode="bilinear")
+        descs = descs.permute(0, 2, 3, 1).reshape(nb, up_size * up_size, -1)
+        w_f = h_f = up_size
+        P = up_size * up_size
+        att = att.reshape(nb, nh, P)
     threshold = torch.mean(att.reshape(nb, -1), dim=1)
     Q = torch.sum(att > threshold[:, None, None], dim=2) / P
     beta = torch.log(torch.sum(Q + epsilon, dim=1)[:, None] / (Q + epsilon))

@@ -190,3 +190,20 @@ def test_evaluator_is_batch_independent():
     # (the mean of sigmoid(l1) is an atomic float sum: order-dependent in the last bits)
     assert torch.allclose(per[0], one0[0], atol=1e-4) and torch.allclose(per[1], one1[0], atol=1e-4)
     assert not torch.allclose(whole[1], one1[0], atol=1e-3)
+
+
+def test_entropy_select_range_test_is_per_image_when_asked():
+    """ASR.py:42 `preds if all in [0,1] else sigmoid(preds)`: image 0 holds probabilities, image 1 logits.  The whole-call
+    test (reference semantics for one call) applies the sigmoid to both; per_image evaluates each like a batch-1 call."""
+    g = torch.Generator().manual_seed(3)
+    probs = torch.rand(1, 1, 56, 56, generator=g)
+    logits = torch.randn(1, 1, 56, 56, generator=g) * 3
+    both = torch.cat([probs, logits]).cuda()
+    e_call, _, _ = ops.coral_entropy_select(both, 0.0015, 3)
+    e_img, _, m_img = ops.coral_entropy_select(both, 0.0015, 3, per_image=True)
+    e0, _, m0 = ops.coral_entropy_select(probs.cuda(), 0.0015, 3)
+    e1, _, m1 = ops.coral_entropy_select(logits.cuda(), 0.0015, 3)
+    assert torch.equal(e_img[0], e0[0]) and torch.equal(e_img[1], e1[0])
+    assert torch.equal(m_img[0], m0[0]) and torch.equal(m_img[1], m1[0])
+    assert not torch.allclose(e_call[0], e0[0])          # one flag for the call: image 0 went through the sigmoid
+    assert torch.equal(e_call[1], e1[0])

@@ -85,6 +85,19 @@ def test_pseudo_label_scoring(g_pl):
     assert 0 < g_pl["score_bkg"].mean() < 1  # the planted inputs exercise both labels
 
 
+def test_pseudo_label_scoring_optional_arguments():
+    """`up_size` != grid and `apply_weights=False` (found_bkg_mask.py:9-12) against outputs of the reference itself."""
+    from tools.make_golden_bkgseg_options import CASES, TH_BKG, planted_inputs
+    gold = np.load(GOLD / "bkgseg_options.npz")
+    att, feats = planted_inputs()
+    for name, kw in CASES:
+        bkg, sim, _, _ = opl.compute_img_bkg_seg(att, feats, (16, 16), TH_BKG, **kw)
+        assert bkg.shape == gold[f"{name}_bkg"].shape
+        assert np.array_equal(bkg.numpy().astype(np.uint8), gold[f"{name}_bkg"]), name
+        np.testing.assert_allclose(sim.numpy(), gold[f"{name}_sim"], atol=2e-6)
+        assert 0 < gold[f"{name}_bkg"].mean() < 1
+
+
 # ---- a4: refine_post_process (cv2.connectedComponentsWithStats semantics) -----------------------------------
 def test_refine_post_process(g_pl):
     changed = 0

@@ -58,6 +58,28 @@ def test_dropin_signature():
     assert (sim.cpu() - sim_r).abs().max().item() < 1e-4
 
 
+def test_dropin_optional_arguments_match_reference_goldens():
+    """`up_size` != grid and `apply_weights=False` (found_bkg_mask.py:9-12): masks bit-equal to the reference's own
+    outputs except where the cosine sits within 1e-5 of the threshold; similarity maps to 1e-4."""
+    import pathlib
+    from tools.make_golden_bkgseg_options import CASES, TH_BKG, planted_inputs
+    from ucod_dpl_b200.data.utils.found_bkg_mask import compute_img_bkg_seg
+    gold = np.load(pathlib.Path(__file__).parent / "golden" / "bkgseg_options.npz")
+    att, feats = planted_inputs()
+    compared = 0
+    for name, kw in CASES:
+        bkg, sim = compute_img_bkg_seg(att.cuda(), feats.cuda(), (16, 16), TH_BKG, dim=64, **kw)
+        _, _, row, _ = opl.compute_img_bkg_seg(att, feats, (16, 16), TH_BKG, **kw)
+        want = torch.from_numpy(gold[f"{name}_bkg"]).float()
+        assert bkg.shape == want.shape
+        differ = bkg.cpu() != want
+        assert ((row - TH_BKG).abs()[differ] < 1e-5).all(), name
+        assert differ.float().mean().item() < 0.005
+        assert (sim.cpu() - torch.from_numpy(gold[f"{name}_sim"]))[~differ].abs().max().item() < 1e-4
+        compared += 1
+    assert compared == 3
+
+
 def _edge_masks():
     ms = []
     m = np.zeros((16, 16), np.uint8); ms.append(m.copy())                       # empty

@@ -93,11 +93,13 @@ def test_rank_sharding_and_ragged_tail(monkeypatch):
         tr = _Trainer()
         TrainLoop(cfg, tr, _Dis(), keys, pl, (2, 2), seed=7, rank=rank, world_size=2).run()
         per_rank.append([c[2] for c in tr.calls])
-    # 40 images, 2 ranks x 16: step 0 uses 32 images, step 1 has 8 left -> rank 0 takes them, rank 1 repeats the head
-    assert [len(b) for b in per_rank[0]] == [16, 8] and [len(b) for b in per_rank[1]] == [16, 16]
-    first = per_rank[0][0] + per_rank[1][0] + per_rank[0][1]
-    assert sorted(first) == [float(i) for i in range(40)]
-    assert per_rank[1][1] == per_rank[0][0]    # same step count on both ranks (every rank joins every all-reduce)
+    # 40 images, 2 ranks x 16: step 0 uses 32 images; the last global batch (8 left) is completed by wrapping around to
+    # the head of the permutation like accelerate's BatchSamplerShard(even_batches=True): every rank gets a full batch
+    # in every step (so every rank joins every all-reduce and no sample is weighted more than another within a step)
+    assert [len(b) for b in per_rank[0]] == [16, 16] and [len(b) for b in per_rank[1]] == [16, 16]
+    epoch = per_rank[0][0] + per_rank[1][0] + per_rank[0][1] + per_rank[1][1]
+    assert sorted(epoch[:40]) == [float(i) for i in range(40)]
+    assert epoch[40:] == epoch[:24]            # the 24 fill-in samples are the head of the same permutation
 
 
 def test_no_discriminator_when_merge_method_differs(monkeypatch):

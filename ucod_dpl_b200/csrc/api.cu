@@ -119,6 +119,12 @@ int ucod_pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf
     return pseudo_label_score(attn_cls, keys, keys_bf16, batch, heads, patches, th_bkg, epsilon, cos, bkg, ref_idx,
                               sim, static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream));
 }
+int ucod_pseudo_label_score_ex(const float* attn_cls, const void* keys, int keys_bf16, int batch, int heads, int patches,
+                               float th_bkg, float epsilon, int apply_weights, float* cos, uint8_t* bkg,
+                               int32_t* ref_idx, float* sim, void* scratch, void* stream) {
+    return pseudo_label_score(attn_cls, keys, keys_bf16, batch, heads, patches, th_bkg, epsilon, cos, bkg, ref_idx,
+                              sim, static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream), apply_weights);
+}
 int ucod_refine_small_components(const uint8_t* mask_in, uint8_t* mask_out, int batch, int h, int w,
                                  int area_threshold, void* stream) {
     return refine_small_components(mask_in, mask_out, batch, h, w, area_threshold,
@@ -264,6 +270,12 @@ int ucod_coral_entropy_select(const float* preds, int batch, int size, int windo
                               float* entropy, float* scores, uint8_t* mask, void* scratch, void* stream) {
     return coral_entropy_select(preds, batch, size, window_size, threshold, entropy, scores, mask,
                                 static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream));
+}
+int ucod_coral_entropy_select_ex(const float* preds, int batch, int size, int window_size, float threshold,
+                                 float* entropy, float* scores, uint8_t* mask, void* scratch, int per_image,
+                                 void* stream) {
+    return coral_entropy_select(preds, batch, size, window_size, threshold, entropy, scores, mask,
+                                static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream), per_image);
 }
 int ucod_coral_window_head(const float* taps, int ld_taps, int n_windows, int grid, float bias_const, float* out,
                            void* stream) {

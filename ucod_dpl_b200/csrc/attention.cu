@@ -138,7 +138,7 @@ __device__ __forceinline__ void ex2_poly2(float x0, float x1, float& p0, float& 
     p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 #ifndef UCOD_ATT_POLY8
-#define UCOD_ATT_POLY8 3  // pairs out of every 8 (16 elements) whose exponentials go to the FMA pipe (0 = all on MUFU)
+#define UCOD_ATT_POLY8 2  // pairs out of every 8 (16 elements) whose exponentials go to the FMA pipe (0 = all on MUFU)
 #endif
 // Non-blocking phase test: issued early, its result is consumed later, so the ~100 clk barrier round trip overlaps
 // arithmetic instead of sitting between two phases of a softmax warp's tile.

@@ -18,22 +18,24 @@
 namespace ucod {
 
 // ------------------------------------------------------------------------------------------------
-__global__ void range_flag_kernel(const float* __restrict__ x, size_t n, int* flag) {
+// flag[stride * blockIdx.y] |= 1 when any of that slice's n values lies outside [0, 1] (stride 0: one flag per call)
+__global__ void range_flag_kernel(const float* __restrict__ x, size_t n, int* flag, int stride) {
+    const float* xs = x + (size_t)blockIdx.y * n;
     bool bad = false;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        const float v = x[i];
+        const float v = xs[i];
         bad |= !(v >= 0.f && v <= 1.f);
     }
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag + (size_t)stride * blockIdx.y, 1);
 }
 
 // one CTA per image; bins of adaptive_avg_pool2d: [floor(i*n/w), ceil((i+1)*n/w))
 __global__ void entropy_select_kernel(const float* __restrict__ preds, int P, int ws, float threshold,
-                                      const int* __restrict__ flag, float* __restrict__ entropy,
+                                      const int* __restrict__ flag, int flag_stride, float* __restrict__ entropy,
                                       float* __restrict__ scores, uint8_t* __restrict__ mask) {
     extern __shared__ float s_bins[];  // ws*ws partial sums
     const int b = blockIdx.x;
-    const bool logits = (*flag != 0);
+    const bool logits = (flag[(size_t)flag_stride * b] != 0);
     const int nb = ws * ws;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) s_bins[i] = 0.f;
     __syncthreads();
@@ -69,19 +71,23 @@ __global__ void entropy_select_kernel(const float* __restrict__ preds, int P, in
 }
 
 int coral_entropy_select(const float* preds, int B, int P, int ws, float threshold, float* entropy, float* scores,
-                         uint8_t* mask, int* flag, cudaStream_t stream) {
+                         uint8_t* mask, int* flag, cudaStream_t stream, int per_image) {
     UCOD_REQUIRE(preds && entropy && scores && mask && flag, "coral_entropy_select: null pointer");
     UCOD_REQUIRE(B > 0 && P > 0 && ws > 0 && ws <= 16 && ws <= P, "coral_entropy_select: bad geometry");
-    UCOD_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), stream));
+    // `preds if all in [0,1] else sigmoid(preds)` (ASR.py:42): the reference decides per CALL and evaluates at batch 1,
+    // i.e. per image; per_image != 0 keeps that when several images share a launch (flag: B ints instead of one)
+    UCOD_CHECK_CUDA(cudaMemsetAsync(flag, 0, sizeof(int) * (per_image ? B : 1), stream));
     const size_t n = (size_t)B * P * P;
     {
         ProfScope ps(KC_OTHER, stream, (double)n * 4);
-        range_flag_kernel<<<(unsigned)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024), 256, 0, stream>>>(preds, n, flag);
+        const size_t per = per_image ? (size_t)P * P : n;
+        const unsigned gx = (unsigned)((per + 255) / 256 < 1024 ? (per + 255) / 256 : 1024);
+        range_flag_kernel<<<dim3(gx, per_image ? B : 1), 256, 0, stream>>>(preds, per, flag, per_image ? 1 : 0);
     }
     {
         ProfScope ps(KC_OTHER, stream, (double)n * 8);
-        entropy_select_kernel<<<B, 256, ws * ws * sizeof(float), stream>>>(preds, P, ws, threshold, flag, entropy,
-                                                                           scores, mask);
+        entropy_select_kernel<<<B, 256, ws * ws * sizeof(float), stream>>>(preds, P, ws, threshold, flag,
+                                                                           per_image ? 1 : 0, entropy, scores, mask);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -5,7 +5,7 @@
 namespace ucod {
 
 int coral_entropy_select(const float* preds, int B, int P, int window_size, float threshold, float* entropy,
-                         float* scores, uint8_t* mask, int* flag_scratch, cudaStream_t stream);
+                         float* scores, uint8_t* mask, int* flag_scratch, cudaStream_t stream, int per_image = 0);
 int coral_window_head(const float* taps, int ld_taps, int n_windows, int g, float bias_const, float* out,
                       cudaStream_t stream);
 int coral_scatter_windows(const float* window_preds, const int* slot_of_cell, int B, int window_size, int g, float* out,

@@ -42,7 +42,7 @@ template <typename TK>
 __global__ void __launch_bounds__(PL_THREADS)
     pseudo_label_score_kernel(const float* __restrict__ attn, const TK* __restrict__ keys, float* __restrict__ cos_out,
                               uint8_t* __restrict__ bkg_out, int* __restrict__ ref_out, int* __restrict__ gmax,
-                              int nh, int P, float th_bkg, float epsilon) {
+                              int nh, int P, float th_bkg, float epsilon, int apply_weights) {
     extern __shared__ float sm[];
     float* s_att = sm;              // nh * P
     float* s_ref = s_att + nh * P;  // nh * 64 (normalised, beta-weighted reference descriptor)
@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(PL_THREADS)
     if (threadIdx.x == 0) {
         float tot = 0.f;
         for (int h = 0; h < nh; ++h) tot += (float)s_cnt[h] / (float)P + epsilon;
-        for (int h = 0; h < nh; ++h) s_beta[h] = logf(tot / ((float)s_cnt[h] / (float)P + epsilon));
+        // apply_weights = False (found_bkg_mask.py:44-47,64-65): neither the descriptors nor the attention sum are weighted
+        for (int h = 0; h < nh; ++h) s_beta[h] = apply_weights ? logf(tot / ((float)s_cnt[h] / (float)P + epsilon)) : 1.f;
     }
     __syncthreads();
 
@@ -311,7 +312,7 @@ __global__ void __launch_bounds__(256)
 
 int pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf16, int B, int nh, int P, float th_bkg,
                        float epsilon, float* cos_out, uint8_t* bkg_out, int* ref_out, float* sim_out, int* scratch,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, int apply_weights) {
     UCOD_REQUIRE(attn_cls && keys && cos_out && bkg_out && ref_out, "pseudo_label_score: null argument");
     UCOD_REQUIRE(B > 0 && P > 0 && nh > 0 && nh <= PL_MAX_HEADS, "pseudo_label_score: bad geometry (heads <= 16)");
     UCOD_REQUIRE(sim_out == nullptr || scratch != nullptr, "pseudo_label_score: sim_map needs the 4-byte scratch");
@@ -328,14 +329,14 @@ int pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf16, i
             UCOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(KC_PSEUDO, stream, bytes);
         kern<<<B, PL_THREADS, smem, stream>>>(attn_cls, static_cast<const __nv_bfloat16*>(keys), cos_out, bkg_out,
-                                              ref_out, scratch, nh, P, th_bkg, epsilon);
+                                              ref_out, scratch, nh, P, th_bkg, epsilon, apply_weights);
     } else {
         auto kern = pseudo_label_score_kernel<float>;
         if (smem > 48 * 1024)
             UCOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ProfScope ps(KC_PSEUDO, stream, bytes);
         kern<<<B, PL_THREADS, smem, stream>>>(attn_cls, static_cast<const float*>(keys), cos_out, bkg_out, ref_out,
-                                              scratch, nh, P, th_bkg, epsilon);
+                                              scratch, nh, P, th_bkg, epsilon, apply_weights);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     if (sim_out) {

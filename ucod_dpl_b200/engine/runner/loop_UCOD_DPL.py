@@ -327,10 +327,14 @@ class TrainLoop:
         n = self.keys.shape[0]
         order = torch.randperm(n, generator=self._gen) if self.shuffle else torch.arange(n)
         per_step = self.batch_size * self.world
-        for s in range(0, n, per_step):
+        if self.world > 1 and n % per_step:
+            # accelerate's BatchSamplerShard(even_batches=True): the last global batch is completed by wrapping around
+            # to the start of the permutation, so every rank contributes a full batch to every gradient all-reduce and
+            # no sample is weighted more than another within a step
+            pad = per_step - n % per_step
+            order = torch.cat([order, order[:pad]] if pad <= n else [order] + [order] * (pad // n) + [order[: pad % n]])
+        for s in range(0, order.numel(), per_step):
             idx = order[s + self.rank * self.batch_size: s + (self.rank + 1) * self.batch_size]
-            if idx.numel() == 0:       # ragged tail: ranks without data repeat the head of the permutation, so that
-                idx = order[: self.batch_size]  # every rank joins every gradient all-reduce
             yield idx.to(self.keys.device)
 
     def _log(self, msg: str) -> None:
@@ -345,9 +349,17 @@ class TrainLoop:
             if self._cur_epoch % self.log_interval == 0:
                 self._log("dis:loss:{:.4f}".format(float(loss)))
 
+    def _sync_discriminator_buffers(self) -> None:
+        """DDP broadcasts module buffers from rank 0 at every forward (broadcast_buffers=True); the BatchNorm running
+        statistics of the discriminator are per-rank here, so they are aligned once per discriminator epoch."""
+        if self.world > 1 and torch.distributed.is_available() and torch.distributed.is_initialized():
+            for buf in self.dis_trainer.D.buffers():
+                torch.distributed.broadcast(buf, src=0)
+
     def Discriminator_train(self) -> None:
         for _ in range(self.cfg.train_cfg.dis_epoch):
             self.Discriminator_epoch()
+            self._sync_discriminator_buffers()
 
     def run_epoch(self) -> None:
         self.trainer.cur_epoch = self._cur_epoch

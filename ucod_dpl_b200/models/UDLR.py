@@ -36,8 +36,9 @@ class SparseRefiner(nn.Module):
     def forward_tokens(self, l_tokens, h_tokens_all, preds, grid: int, per_image: bool = False):
         """Device-pipeline entry: l_tokens fp32 [B,g*g,C]; h_tokens_all fp32 [B, w*w, g*g, C] (all windows,
         token-major); preds [B,1,P,P].  Same outputs as `forward`.  per_image: every image is treated as its own
-        batch-1 call (the gated ensemble's entropy maximum is per image) — what the reference's eval loop computes."""
-        mask, entropy, win_img, coords, flat = self.selector.select(preds)
+        batch-1 call (the gated ensemble's entropy maximum and the selector's probabilities-or-logits test are per image)
+        — what the reference's eval loop computes."""
+        mask, entropy, win_img, coords, flat = self.selector.select(preds, per_image=per_image)
         dev = preds.device
         B = preds.shape[0]
         N = len(win_img)

@@ -27,9 +27,9 @@ class EntropySelector(nn.Module):
         self.window_size = window_size
 
     @torch.no_grad()
-    def select(self, preds):
+    def select(self, preds, per_image: bool = False):
         """-> (mask bool [B,1,w,w], entropy [B,1,P,P], window->image index list, coords [N,2] CPU)."""
-        entropy, _, mask = ops.coral_entropy_select(preds, self.threshold, self.window_size)
+        entropy, _, mask = ops.coral_entropy_select(preds, self.threshold, self.window_size, per_image=per_image)
         flat = mask.flatten(1).cpu()  # the one host round trip of the refiner: the number of selected windows
         win_img, coords = [], []
         for b in range(flat.shape[0]):

@@ -92,7 +92,7 @@ def upsample_bilinear(x: torch.Tensor, size, binarize=False) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------------
 def pseudo_label_score(attn_cls: torch.Tensor, keys: torch.Tensor, th_bkg: float, epsilon: float = 1e-10,
-                       want_sim: bool = False):
+                       want_sim: bool = False, apply_weights: bool = True):
     """attn_cls [B,heads,P] fp32, keys [B,P,heads*64] fp32|bf16 -> (cos [B,P], bkg u8 [B,P], ref_idx [B], sim|None)."""
     _lib.require_cuda(attn_cls, keys)
     attn_cls = attn_cls.float().contiguous()
@@ -109,9 +109,9 @@ def pseudo_label_score(attn_cls: torch.Tensor, keys: torch.Tensor, th_bkg: float
     sim = torch.empty(B, P, device=dev, dtype=torch.float32) if want_sim else None
     scratch = torch.empty(1, device=dev, dtype=torch.int32)
     with torch.cuda.device(dev):
-        _lib.call("ucod_pseudo_label_score", ptr(attn_cls), ptr(keys), 1 if keys.dtype == torch.bfloat16 else 0, B,
-                  nh, P, c_float(th_bkg), c_float(epsilon), ptr(cos), ptr(bkg), ptr(ref), ptr(sim), ptr(scratch),
-                  stream_ptr(dev))
+        _lib.call("ucod_pseudo_label_score_ex", ptr(attn_cls), ptr(keys), 1 if keys.dtype == torch.bfloat16 else 0, B,
+                  nh, P, c_float(th_bkg), c_float(epsilon), 1 if apply_weights else 0, ptr(cos), ptr(bkg), ptr(ref),
+                  ptr(sim), ptr(scratch), stream_ptr(dev))
     return cos, bkg, ref, sim
 
 
@@ -468,8 +468,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, heads: int, hea
 
 # ------------------------------------------------------------------------------------------------
 # CORAL second stage
-def coral_entropy_select(preds: torch.Tensor, threshold: float, window_size: int):
-    """preds [B,1,P,P] -> (entropy [B,1,P,P], scores [B,1,w,w], mask bool [B,1,w,w])."""
+def coral_entropy_select(preds: torch.Tensor, threshold: float, window_size: int, per_image: bool = False):
+    """preds [B,1,P,P] -> (entropy [B,1,P,P], scores [B,1,w,w], mask bool [B,1,w,w]).
+    per_image: decide "probabilities or logits" (ASR.py:42) for every image on its own, as the reference's batch-1 eval
+    loop does, instead of once for the whole call."""
     _lib.require_cuda(preds)
     p = preds.float().contiguous()
     B, _, P, _ = p.shape
@@ -477,10 +479,10 @@ def coral_entropy_select(preds: torch.Tensor, threshold: float, window_size: int
     entropy = torch.empty_like(p)
     scores = torch.empty(B, 1, window_size, window_size, device=dev, dtype=torch.float32)
     mask = torch.empty(B, 1, window_size, window_size, device=dev, dtype=torch.uint8)
-    scratch = torch.empty(1, device=dev, dtype=torch.int32)
+    scratch = torch.empty(B, device=dev, dtype=torch.int32)
     with torch.cuda.device(dev):
-        _lib.call("ucod_coral_entropy_select", ptr(p), B, P, window_size, c_float(threshold), ptr(entropy),
-                  ptr(scores), ptr(mask), ptr(scratch), stream_ptr(dev))
+        _lib.call("ucod_coral_entropy_select_ex", ptr(p), B, P, window_size, c_float(threshold), ptr(entropy),
+                  ptr(scores), ptr(mask), ptr(scratch), 1 if per_image else 0, stream_ptr(dev))
     return entropy, scores, mask.bool()
 
 
