@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --set full` capture of bench.py into the JSON bench.py reads for `roofline.traffic`
 (profiles/r02_ncu_traffic.json) and a readable per-kernel table (profiles/r02_ncu_kernels.txt).
-usage: python tools/ncu_traffic.py gpurun_out/r2_bench_full.ncu-rep"""
+usage: python tools/ncu_traffic.py <outdir> a.ncu-rep [b.ncu-rep ...]   (see tools/ncu_capture.sh)"""
 import csv
 import json
 import subprocess
@@ -14,7 +14,8 @@ CLASS = [("gemm", ("gemm_bf16_tcgen05", "gemm2_bf16_tcgen05", "wgrad_tcgen05")),
          ("layernorm", ("layernorm",)), ("embed", ("im2col", "cls_init", "cls_row")),
          ("decoder", ("decoder_",)), ("ccl", ("ccl_", "lt_boxes", "lt_build", "lt_init")),
          ("resample", ("upsample", "crop_", "paste_", "resample_", "fill_", "mask_scale", "to_tensor")),
-         ("pseudo_label", ("pseudo_", "pl_", "refine_"))]
+         ("pseudo_label", ("pseudo_", "pl_", "refine_")), ("coral", ("entropy", "coral_", "window_")),
+         ("train", ("apm_", "discriminator", "disc_", "adamw", "ema_", "bce_"))]
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_tensor_subpipe_hmma.sum", "sm__cycles_elapsed.avg",
@@ -25,15 +26,23 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 
 
 def main():
-    rep = sys.argv[1]
-    outdir = Path(sys.argv[2]) if len(sys.argv) > 2 else ROOT / "profiles"
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True,
-                         text=True).stdout
-    rows = list(csv.reader(l for l in out.splitlines() if l.startswith('"')))
+    outdir, reps = Path(sys.argv[1]), sys.argv[2:]
+    per = defaultdict(list)
+    for rep in reps:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv", "--print-units", "base"], capture_output=True,
+                             text=True).stdout
+        rows = list(csv.reader(l for l in out.splitlines() if l.startswith('"')))
+        if len(rows) < 3:
+            print(f"{rep}: no kernels captured")
+            continue
+        collect(rows, per)
+    report(per, outdir, reps)
+
+
+def collect(rows, per):
     hdr = rows[0]
     ix = {h: i for i, h in enumerate(hdr)}
     name_i = ix["Kernel Name"]
-    per = defaultdict(list)
     for r in rows[2:]:
         nm = r[name_i]
         cls = next((c for c, pats in CLASS if any(p in nm for p in pats)), "other")
@@ -46,6 +55,9 @@ def main():
                 d[w] = None
         d["name"] = nm
         per[cls].append(d)
+
+
+def report(per, outdir, reps):
     traffic, lines = {}, []
     for cls, ks in per.items():
         tot = [(k["dram__bytes_read.sum"] or 0) + (k["dram__bytes_write.sum"] or 0) for k in ks]
@@ -66,7 +78,7 @@ def main():
                          f"{avg('smsp__issue_active.avg.pct_of_peak_sustained_active'):5.1f} %  regs "
                          f"{avg('launch__registers_per_thread'):.0f}")
     (outdir / "r02_ncu_traffic.json").write_text(json.dumps(
-        {"source": f"ncu --set full --clock-control none, {Path(rep).name}; dram__bytes_read.sum + dram__bytes_write.sum, "
+        {"source": f"ncu --set full --clock-control none, {', '.join(Path(r).name for r in reps)}; dram__bytes_read.sum + dram__bytes_write.sum, "
                    "mean per launch of the class", "bytes_per_launch": traffic}, indent=1))
     (outdir / "r02_ncu_kernels.txt").write_text("\n".join(lines) + "\n")
     print("\n".join(lines))

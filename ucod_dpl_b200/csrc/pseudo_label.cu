@@ -59,6 +59,19 @@ __global__ void __launch_bounds__(PL_THREADS)
     const float* att_b = attn + (size_t)b * nh * P;
     const TK* keys_b = keys + (size_t)b * P * C;
 
+    // The weights / reference-patch prologue below only touches the 12 KB of attention; the image's key block is
+    // pulled into L2 meanwhile (bulk L2 prefetch, no register or shared-memory destination), so the streaming pass
+    // that follows is not serialised behind the prologue's latency chain.
+    {
+        const size_t bytes = (size_t)P * C * sizeof(TK);  // C = nh*64: a multiple of 128 bytes
+        const char* base = reinterpret_cast<const char*>(keys_b);
+        constexpr unsigned CH = 16384;
+        for (size_t off = (size_t)threadIdx.x * CH; off < bytes; off += (size_t)blockDim.x * CH) {
+            const unsigned n = (unsigned)(bytes - off < CH ? bytes - off : CH);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(n) : "memory");
+        }
+    }
+
     // ---- threshold = mean attention; Q_h = fraction of patches above it; beta_h ----
     float acc = 0.f;
     for (int i = threadIdx.x; i < nh * P; i += blockDim.x) {
