@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define UCOD_B200_ABI_VERSION 4
+#define UCOD_B200_ABI_VERSION 5
 
 /* Last error message of the calling thread ("" if none). */
 const char* ucod_last_error(void);
@@ -261,6 +261,14 @@ typedef struct ucod_disc_weights {
 uint64_t ucod_discriminator_workspace_bytes(int batch, int fs);
 int ucod_discriminator_fwd(const float* mask, int batch, int fs, const ucod_disc_weights* w, int bn_train,
                            int update_running, float* prob, void* workspace, uint64_t workspace_bytes, void* stream);
+/* Several consecutive `Discriminator.forward` calls of the same batch size in one set of launches: masks
+ * [calls*batch, 1, fs, fs] (call-major), prob [calls*batch].  Each call keeps its own BatchNorm batch statistics and the
+ * running buffers are updated in call order, i.e. exactly what `merge_pseudo_label`'s two calls
+ * (engine/runner/loop_UCOD_DPL.py:262-263) produce one after the other. */
+uint64_t ucod_discriminator_workspace_bytes_calls(int batch, int fs, int calls);
+int ucod_discriminator_fwd_calls(const float* masks, int batch, int calls, int fs, const ucod_disc_weights* w,
+                                 int bn_train, int update_running, float* prob, void* workspace,
+                                 uint64_t workspace_bytes, void* stream);
 /* `TrainLoop.merge_pseudo_label` (engine/runner/loop_UCOD_DPL.py:257-272), split around the two discriminator calls:
  * binarize: s_mask = sigmoid(student) > 0.5, t_mask = sigmoid(teacher) > 0.5, p_mask = pl > 0.5 (fp32 {0,1}, n elements)
  * merge:    w_b = clamp(0.5*(1+cos(pi*|p_s-p_p|)) + epoch_term, 0, 1); merged = pl*(1-w_b) + t_mask*w_b;
@@ -275,11 +283,12 @@ int ucod_apm_merge(const float* pl, const float* t_mask, const float* p_s, const
  * loss = BCEWithLogits(fg, target) + BCEWithLogits(bg, 1 - target) + ortho, target = APM-merged pseudo labels
  * [batch, out_h*out_w] (constant).  Call after ucod_decoder_fwd(... ortho != NULL ...) on the same keys, passing
  * that call's workspace; fg / bg are its outputs.  Gradients (fp32, zeroed here): g_w_dec [128,dim], g_b_dec [128],
- * g_w_fg [64], g_b_fg [1], g_w_bg [64], g_b_bg [1]; the gradient of learnable_embedding is identically zero
+ * g_w_fg [64], g_b_fg [1], g_w_bg [64], g_b_bg [1] (all written, none accumulated; every sum runs in a fixed order, so
+ * the gradients are bit-reproducible); the gradient of learnable_embedding is identically zero
  * (F.normalize).  loss2: device float[2] = the two BCE means (add the forward's ortho for the total).
  * Autograd entry: pass target = NULL and the upstream gradients dfg, dbg [batch, out_h*out_w] and dortho (device
  * scalar) instead; then no loss is computed. */
-uint64_t ucod_decoder_bwd_workspace_bytes(int batch, int gin_h, int gin_w);
+uint64_t ucod_decoder_bwd_workspace_bytes(int batch, int gin_h, int gin_w, int out_h, int out_w);
 int ucod_decoder_bwd(const void* keys_bf16, int batch, int dim, int gin_h, int gin_w, int out_h, int out_w,
                      const void* w_dec, const float* b_dec, const float* emb, const float* w_fg, const float* b_fg,
                      const float* w_bg, const float* b_bg, const float* fg, const float* bg, const float* target,

@@ -51,6 +51,27 @@ def test_discriminator_eval_bn():
     assert (got - ref).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("train", [True, False])
+@pytest.mark.parametrize("B,fs", [(16, 68), (3, 16)])
+def test_two_calls_in_one_launch_equal_two_forwards(train, B, fs):
+    """`forward_calls(masks, 2)` (what the APM uses) == forward(a) then forward(b): probabilities, every BatchNorm
+    running buffer (updated in call order) and the batch counters."""
+    d1, _ = _disc(fs, 7)
+    d2 = copy.deepcopy(d1)
+    d1.train(train), d2.train(train)
+    a, b = _masks(B, fs, 8).cuda(), _masks(B, fs, 9).cuda()
+    want = torch.cat([d1(a, None), d1(b, None)])
+    got = d2.forward_calls(torch.cat([a, b]), 2)
+    assert got.shape == (2 * B, 1)
+    assert (got - want).abs().max().item() < 1e-6
+    sd1, sd2 = d1.state_dict(), d2.state_dict()
+    for k in sd1:
+        if "running" in k:
+            assert (sd1[k] - sd2[k]).abs().max().item() < 1e-6, k
+        elif "num_batches" in k:
+            assert int(sd1[k]) == int(sd2[k]) == (2 if train else 0), k
+
+
 @pytest.mark.parametrize("epoch", [0, 3, 19])
 def test_apm_merge(epoch):
     B, fs = 16, 68

@@ -212,7 +212,7 @@ def test_discriminator_epoch_steps_match_reference_golden():
 
 def test_graph_replay_matches_eager_steps():
     """CUDA-graph replay of the forward / APM / backward sequence: same losses and parameters as the eager path over
-    six steps with changing inputs (float atomics make both paths order-dependent in the last bits)."""
+    six steps with changing inputs."""
     outs = []
     for use_graph in (False, True):
         _, model, D = _models()
@@ -229,9 +229,27 @@ def test_graph_replay_matches_eager_steps():
     (l0, p0), (l1, p1) = outs
     assert np.allclose(l0, l1, rtol=2e-4, atol=2e-5), (l0, l1)
     for k in p0:
-        # AdamW's first steps move every weight by ~lr whatever the gradient's size, so last-bit gradient differences
-        # (float atomics in the scatter kernels) show up as a small fraction of 6 * lr = 1.2e-3
         assert torch.allclose(p0[k], p1[k], rtol=1e-4, atol=5e-5), k
+
+
+def test_training_steps_are_bit_reproducible():
+    """No float atomics on the step's path (fixed-order partial sums in the decoder forward / backward, split-K weight
+    gradient reduced in order): two runs from the same state give bit-identical gradients, losses and parameters."""
+    outs = []
+    for _ in range(2):
+        _, model, D = _models()
+        tr = FirstStageTrainer(model, D, lr0=2e-4)
+        tr.cur_epoch = 3
+        grads, losses = [], []
+        for step in range(4):
+            feats, pl = train_inputs(900 + step, B=4)
+            tok = ops.features_to_tokens_bf16(feats.cuda())
+            losses.append(tr.process_batch(tok, (37, 37), pl.cuda()).clone())
+            grads.append(tr.flat_g.clone())
+        outs.append((torch.stack(losses), torch.stack(grads), tr.flat_p.clone(), tr.flat_ema.clone()))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+    assert outs[0][1].abs().max().item() > 0
 
 
 def _ddp_worker(rank, world, port, out):

@@ -214,6 +214,18 @@ int ucod_discriminator_fwd(const float* mask, int batch, int fs, const ucod_disc
     return discriminator_forward(mask, batch, fs, d, bn_train, update_running, prob, workspace,
                                  (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream));
 }
+uint64_t ucod_discriminator_workspace_bytes_calls(int batch, int fs, int calls) {
+    return (uint64_t)discriminator_workspace_bytes_groups(batch, fs, calls);
+}
+int ucod_discriminator_fwd_calls(const float* masks, int batch, int calls, int fs, const ucod_disc_weights* w,
+                                 int bn_train, int update_running, float* prob, void* workspace,
+                                 uint64_t workspace_bytes, void* stream) {
+    UCOD_REQUIRE(w != nullptr, "ucod_discriminator_fwd_calls: null weights");
+    DiscWeights d{w->conv1, w->bn1_w, w->bn1_b, w->bn1_mean, w->bn1_var, w->conv2, w->bn2_w, w->bn2_b, w->bn2_mean,
+                  w->bn2_var, w->conv3, w->bn3_w, w->bn3_b, w->bn3_mean, w->bn3_var, w->lin_w, w->lin_b};
+    return discriminator_forward(masks, batch, fs, d, bn_train, update_running, prob, workspace,
+                                 (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream), calls);
+}
 int ucod_apm_binarize(const float* student, const float* teacher, const float* pl, float* s_mask, float* t_mask,
                       float* p_mask, uint64_t n, void* stream) {
     return apm_binarize(student, teacher, pl, s_mask, t_mask, p_mask, (size_t)n,
@@ -226,8 +238,8 @@ int ucod_apm_merge(const float* pl, const float* t_mask, const float* p_s, const
 }
 
 // ---- first-stage training ----
-uint64_t ucod_decoder_bwd_workspace_bytes(int batch, int gin_h, int gin_w) {
-    return (uint64_t)decoder_backward_workspace_bytes(batch, gin_h, gin_w);
+uint64_t ucod_decoder_bwd_workspace_bytes(int batch, int gin_h, int gin_w, int out_h, int out_w) {
+    return (uint64_t)decoder_backward_workspace_bytes(batch, gin_h, gin_w, out_h, out_w);
 }
 int ucod_decoder_bwd(const void* keys_bf16, int batch, int dim, int gin_h, int gin_w, int out_h, int out_w,
                      const void* w_dec, const float* b_dec, const float* emb, const float* w_fg, const float* b_fg,

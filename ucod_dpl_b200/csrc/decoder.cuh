@@ -22,7 +22,7 @@ int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_
 struct DecoderGrads {  // fp32 gradients, same shapes as the weights (w_dec as fp32 [128, dim])
     float* w_dec; float* b_dec; float* w_fg; float* b_fg; float* w_bg; float* b_bg;
 };
-size_t decoder_backward_workspace_bytes(int B, int gin_h, int gin_w);
+size_t decoder_backward_workspace_bytes(int B, int gin_h, int gin_w, int out_h, int out_w);
 // fwd_workspace: the workspace a decoder_forward(... ortho != NULL ...) call on the same inputs left behind.
 // loss2: device float[2] = {BCEwL(fg, target), BCEwL(bg, 1 - target)} (means over B*npix).
 int decoder_backward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_h, int out_w, const DecoderWeights& w,

@@ -23,13 +23,25 @@ struct BnParams {
     float* running_var;
 };
 
+// The BatchNorm sums of a forward call live in DISC_SLOTS copies of a [32+16+8][2] fp64 table: a producer CTA adds into
+// slot (blockIdx.x % DISC_SLOTS) so that thousands of small CTAs do not serialise on 112 addresses; readers add the slots.
+constexpr int DISC_SLOTS = 8;
+constexpr int DISC_SUMS = (32 + 16 + 8) * 2;                       // doubles per slot
+constexpr size_t DISC_SUMS_BYTES = (size_t)DISC_SLOTS * DISC_SUMS * 8;
+__device__ __forceinline__ double slot_sum(const double* sums, int i) {
+    double t = 0.0;
+#pragma unroll
+    for (int s = 0; s < DISC_SLOTS; ++s) t += sums[s * DISC_SUMS + i];
+    return t;
+}
+
 // scale/shift for channel c from either batch sums (train) or running buffers (eval)
 __device__ __forceinline__ void bn_affine(int c, const double* sums, double count, const BnParams& bn, int train,
                                           float eps, float& scale, float& shift) {
     float mean, var;
     if (train) {
-        const double m = sums[2 * c] / count;
-        double v = sums[2 * c + 1] / count - m * m;
+        const double m = slot_sum(sums, 2 * c) / count;
+        double v = slot_sum(sums, 2 * c + 1) / count - m * m;
         if (v < 0) v = 0;
         mean = (float)m, var = (float)v;
     } else {
@@ -42,8 +54,8 @@ __device__ __forceinline__ void bn_affine(int c, const double* sums, double coun
 
 __device__ __forceinline__ void bn_update_running(int c, const double* sums, double count, const BnParams& bn,
                                                   float momentum) {
-    const double m = sums[2 * c] / count;
-    double v = sums[2 * c + 1] / count - m * m;
+    const double m = slot_sum(sums, 2 * c) / count;
+    double v = slot_sum(sums, 2 * c + 1) / count - m * m;
     if (v < 0) v = 0;
     const double unbiased = count > 1 ? v * count / (count - 1) : v;
     bn.running_mean[c] = (1.f - momentum) * bn.running_mean[c] + momentum * (float)m;
@@ -57,32 +69,55 @@ __global__ void __launch_bounds__(128)
     disc_conv_kernel(const float* __restrict__ in, const float* __restrict__ weight /*[COUT,CIN,3,3]*/,
                      float* __restrict__ out, double* __restrict__ out_sums /*[COUT,2]*/,
                      const double* __restrict__ in_sums, BnParams in_bn, int bn_train, int update_running,
-                     float eps, float momentum, int B, int Hin, int Win, int Hout, int Wout) {
-    __shared__ float s_w[COUT * CIN * 9];
+                     float eps, float momentum, int B, int Hin, int Win, int Hout, int Wout, size_t in_gstride,
+                     size_t ws_gstride /*bytes between the groups' workspaces*/) {
+    // blockIdx.z = group: an independent forward call (own batch statistics, own workspace) sharing the launch
+    const int grp = blockIdx.z;
+    in += (size_t)grp * in_gstride;
+    out = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(out) + (size_t)grp * ws_gstride);
+    out_sums = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(out_sums) + (size_t)grp * ws_gstride);
+    const double* in_sums0 = in_sums;
+    if (IN_BN) in_sums = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(in_sums) + (size_t)grp * ws_gstride);
+    __shared__ __align__(16) float s_w[CIN * 9 * COUT];  // [c][k][o]: the COUT weights of one tap are contiguous (LDS.128)
     __shared__ float s_scale[CIN], s_shift[CIN];
-    __shared__ float s_red[COUT * 2];
-    for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) s_w[i] = weight[i];
+    for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) s_w[(i % (CIN * 9)) * COUT + i / (CIN * 9)] = weight[i];
     if (IN_BN) {
         const double count = (double)B * Hin * Win;
         for (int c = threadIdx.x; c < CIN; c += blockDim.x) {
             bn_affine(c, in_sums, count, in_bn, bn_train, eps, s_scale[c], s_shift[c]);
-            if (bn_train && update_running && blockIdx.x == 0 && blockIdx.y == 0)
-                bn_update_running(c, in_sums, count, in_bn, momentum);
+            // running buffers: the groups are the reference's consecutive calls, applied in call order by one thread
+            if (bn_train && update_running && blockIdx.x == 0 && blockIdx.y == 0 && grp == 0)
+                for (int g = 0; g < (int)gridDim.z; ++g)
+                    bn_update_running(c, reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(in_sums0) +
+                                                                         (size_t)g * ws_gstride),
+                                      count, in_bn, momentum);
         }
     }
-    for (int i = threadIdx.x; i < COUT * 2; i += blockDim.x) s_red[i] = 0.f;
     __syncthreads();
 
+    // CTA = 32 output pixels x 4 warps (four times the threads of a pixel-per-thread mapping: the layers are tiny and
+    // the launch is latency-bound).  CIN >= 4: the warps split the INPUT channels (every input value is loaded and
+    // normalised once per CTA) and their partial sums are added in warp order through shared memory; CIN == 1: the warps
+    // split the output channels.  Either way a warp's lanes end up holding the same OG output channels, so the
+    // BatchNorm sums are plain warp reductions.
+    constexpr int OG = COUT / 4;
+    constexpr bool KSPLIT = CIN >= 4;
+    static_assert(COUT % 4 == 0 && (!KSPLIT || CIN % 4 == 0), "channel split");
+    constexpr int NACC = KSPLIT ? COUT : OG;
+    __shared__ float s_part[KSPLIT ? 4 * COUT * 32 : 1];
     const int b = blockIdx.y;
-    const int pix = blockIdx.x * blockDim.x + threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int pix = blockIdx.x * 32 + lane;
     const bool active = pix < Hout * Wout;
-    float acc[COUT];
+    const int c_begin = KSPLIT ? warp * (CIN / 4) : 0, c_end = KSPLIT ? c_begin + CIN / 4 : CIN;
+    const int o_first = KSPLIT ? 0 : warp * OG;  // first output channel of acc[]
+    float acc[NACC];
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+    for (int o = 0; o < NACC; ++o) acc[o] = 0.f;
     if (active) {
         const int oy = pix / Wout, ox = pix - oy * Wout;
         const float* img = in + (size_t)b * CIN * Hin * Win;
-        for (int c = 0; c < CIN; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
             float v[9];
 #pragma unroll
             for (int ky = 0; ky < 3; ++ky)
@@ -100,31 +135,50 @@ __global__ void __launch_bounds__(128)
                     v[ky * 3 + kx] = t;
                 }
 #pragma unroll
-            for (int o = 0; o < COUT; ++o) {
-                const float* w = s_w + (o * CIN + c) * 9;
-                float a = acc[o];
+            for (int k = 0; k < 9; ++k) {
+                const float4* w4 = reinterpret_cast<const float4*>(s_w + (c * 9 + k) * COUT + o_first);
 #pragma unroll
-                for (int k = 0; k < 9; ++k) a += v[k] * w[k];
-                acc[o] = a;
+                for (int o4 = 0; o4 < NACC / 4; ++o4) {
+                    const float4 w = w4[o4];
+                    acc[4 * o4 + 0] += v[k] * w.x, acc[4 * o4 + 1] += v[k] * w.y;
+                    acc[4 * o4 + 2] += v[k] * w.z, acc[4 * o4 + 3] += v[k] * w.w;
+                }
             }
         }
-        float* dst = out + (size_t)b * COUT * Hout * Wout + pix;
-#pragma unroll
-        for (int o = 0; o < COUT; ++o) dst[(size_t)o * Hout * Wout] = acc[o];
     }
-    // per-channel sum / sum of squares of the raw outputs (for the next BatchNorm)
+    float fin[OG];  // this warp's OG output channels [warp*OG, ...) of pixel `pix`
+    if constexpr (KSPLIT) {
 #pragma unroll
-    for (int o = 0; o < COUT; ++o) {
-        float s = active ? acc[o] : 0.f, q = s * s;
-        s = warp_sum(s);
+        for (int o = 0; o < COUT; ++o) s_part[(warp * COUT + o) * 32 + lane] = acc[o];
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < OG; ++j) {
+            const int o = warp * OG + j;
+            fin[j] = (s_part[(0 * COUT + o) * 32 + lane] + s_part[(1 * COUT + o) * 32 + lane]) +
+                     (s_part[(2 * COUT + o) * 32 + lane] + s_part[(3 * COUT + o) * 32 + lane]);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < OG; ++j) fin[j] = acc[j];
+    }
+    if (active) {
+        float* dst = out + ((size_t)b * COUT + warp * OG) * Hout * Wout + pix;
+#pragma unroll
+        for (int j = 0; j < OG; ++j) dst[(size_t)j * Hout * Wout] = fin[j];
+    }
+    // per-channel sum / sum of squares of the raw outputs (for the next BatchNorm): a warp reduction (fixed order), then
+    // one fp64 atomic per channel and CTA into this CTA's slot, whose order only matters below fp32 resolution
+#pragma unroll
+    for (int j = 0; j < OG; ++j) {
+        float sv = active ? fin[j] : 0.f, q = sv * sv;
+        sv = warp_sum(sv);
         q = warp_sum(q);
-        if ((threadIdx.x & 31) == 0) {
-            atomicAdd(&s_red[2 * o], s);
-            atomicAdd(&s_red[2 * o + 1], q);
+        if (lane == 0) {
+            double* slot = out_sums + (blockIdx.x % DISC_SLOTS) * DISC_SUMS;
+            atomicAdd(&slot[2 * (warp * OG + j)], (double)sv);
+            atomicAdd(&slot[2 * (warp * OG + j) + 1], (double)q);
         }
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < COUT * 2; i += blockDim.x) atomicAdd(&out_sums[i], (double)s_red[i]);
 }
 
 // BN3 + LeakyReLU + flatten + Linear + sigmoid: one CTA per image
@@ -133,13 +187,22 @@ __global__ void __launch_bounds__(256)
     disc_head_kernel(const float* __restrict__ in /*[B,C,H,W] raw*/, const double* __restrict__ in_sums, BnParams bn,
                      int bn_train, int update_running, float eps, float momentum,
                      const float* __restrict__ lin_w /*[C*H*W]*/, const float* __restrict__ lin_b,
-                     float* __restrict__ prob /*[B]*/, int B, int H, int W) {
+                     float* __restrict__ prob /*[groups*B]*/, int B, int H, int W, size_t ws_gstride) {
     __shared__ float s_scale[C], s_shift[C];
     __shared__ float red[8];
+    const int grp = blockIdx.y;
+    const double* in_sums0 = in_sums;
+    in = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(in) + (size_t)grp * ws_gstride);
+    in_sums = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(in_sums) + (size_t)grp * ws_gstride);
+    prob += (size_t)grp * B;
     const double count = (double)B * H * W;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
         bn_affine(c, in_sums, count, bn, bn_train, eps, s_scale[c], s_shift[c]);
-        if (bn_train && update_running && blockIdx.x == 0) bn_update_running(c, in_sums, count, bn, momentum);
+        if (bn_train && update_running && blockIdx.x == 0 && grp == 0)
+            for (int g = 0; g < (int)gridDim.y; ++g)
+                bn_update_running(c, reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(in_sums0) +
+                                                                     (size_t)g * ws_gstride),
+                                  count, bn, momentum);
     }
     __syncthreads();
     const int b = blockIdx.x;
@@ -205,8 +268,8 @@ __global__ void apm_merge_kernel(const float* __restrict__ pl, const float* __re
 //   dz = gamma / sigma * (dy - mean(dy) - xh * mean(dy xh))
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void bn_stats(int c, const double* sums, double count, float eps, float& mean, float& inv) {
-    const double m = sums[2 * c] / count;
-    double v = sums[2 * c + 1] / count - m * m;
+    const double m = slot_sum(sums, 2 * c) / count;
+    double v = slot_sum(sums, 2 * c + 1) / count - m * m;
     if (v < 0) v = 0;
     mean = (float)m;
     inv = rsqrtf((float)v + eps);
@@ -375,38 +438,46 @@ __global__ void disc_bce_grad_kernel(const float* __restrict__ prob, float label
 
 size_t discriminator_workspace_bytes(int B, int fs) {
     const int h2 = (fs + 1) / 2, h3 = (h2 + 1) / 2;
-    return ((size_t)B * 32 * fs * fs + (size_t)B * 16 * h2 * h2 + (size_t)B * 8 * h3 * h3) * 4 + (32 + 16 + 8) * 2 * 8 +
+    return ((size_t)B * 32 * fs * fs + (size_t)B * 16 * h2 * h2 + (size_t)B * 8 * h3 * h3) * 4 + DISC_SUMS_BYTES +
            1024;
 }
+static size_t disc_group_stride(int B, int fs) { return (discriminator_workspace_bytes(B, fs) + 255) / 256 * 256; }
+size_t discriminator_workspace_bytes_groups(int B, int fs, int groups) { return disc_group_stride(B, fs) * (size_t)groups; }
 
 int discriminator_forward(const float* mask, int B, int fs, const DiscWeights& w, int bn_train, int update_running,
-                          float* prob, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+                          float* prob, void* workspace, size_t ws_bytes, cudaStream_t stream, int groups) {
     UCOD_REQUIRE(mask && prob && workspace, "discriminator_forward: null argument");
-    UCOD_REQUIRE(B > 0 && fs > 0, "discriminator_forward: bad geometry");
-    UCOD_REQUIRE(ws_bytes >= discriminator_workspace_bytes(B, fs), "discriminator_forward: workspace too small");
+    UCOD_REQUIRE(B > 0 && fs > 0 && groups >= 1 && groups <= 8, "discriminator_forward: bad geometry");
+    const size_t gstride = groups > 1 ? disc_group_stride(B, fs) : 0;
+    UCOD_REQUIRE(ws_bytes >= (groups > 1 ? gstride * groups : discriminator_workspace_bytes(B, fs)),
+                 "discriminator_forward: workspace too small");
+    UCOD_REQUIRE(groups == 1 || (reinterpret_cast<uintptr_t>(workspace) & 7) == 0,
+                 "discriminator_forward: workspace must be 8-byte aligned");
     const int h1 = fs, h2 = (fs + 2 - 3) / 2 + 1, h3 = (h2 + 2 - 3) / 2 + 1;
     uint8_t* p = static_cast<uint8_t*>(workspace);
-    double* sums = reinterpret_cast<double*>(p);  // [32+16+8][2]
-    p += (32 + 16 + 8) * 2 * 8;
+    double* sums = reinterpret_cast<double*>(p);  // [DISC_SLOTS][32+16+8][2]
+    p += DISC_SUMS_BYTES;
     float* a1 = reinterpret_cast<float*>(p);
     p += (size_t)B * 32 * h1 * h1 * 4;
     float* a2 = reinterpret_cast<float*>(p);
     p += (size_t)B * 16 * h2 * h2 * 4;
     float* a3 = reinterpret_cast<float*>(p);
     double *s1 = sums, *s2 = sums + 64, *s3 = sums + 96;
-    UCOD_CHECK_CUDA(cudaMemsetAsync(sums, 0, (32 + 16 + 8) * 2 * 8, stream));
+    for (int g = 0; g < groups; ++g)
+        UCOD_CHECK_CUDA(cudaMemsetAsync(reinterpret_cast<uint8_t*>(sums) + g * gstride, 0, DISC_SUMS_BYTES, stream));
     const float eps = 1e-5f, mom = 0.1f;
     BnParams bn1{w.bn1_w, w.bn1_b, w.bn1_mean, w.bn1_var}, bn2{w.bn2_w, w.bn2_b, w.bn2_mean, w.bn2_var},
         bn3{w.bn3_w, w.bn3_b, w.bn3_mean, w.bn3_var}, none{nullptr, nullptr, nullptr, nullptr};
-    ProfScope ps(KC_OTHER, stream, (double)B * (32 * h1 * h1 + 16 * h2 * h2 + 8 * h3 * h3) * 8);
-    disc_conv_kernel<1, 32, 1, false><<<dim3(ceil_div(h1 * h1, 128), B), 128, 0, stream>>>(
-        mask, w.conv1, a1, s1, nullptr, none, 0, 0, eps, mom, B, fs, fs, h1, h1);
-    disc_conv_kernel<32, 16, 2, true><<<dim3(ceil_div(h2 * h2, 128), B), 128, 0, stream>>>(
-        a1, w.conv2, a2, s2, s1, bn1, bn_train, update_running, eps, mom, B, h1, h1, h2, h2);
-    disc_conv_kernel<16, 8, 2, true><<<dim3(ceil_div(h3 * h3, 128), B), 128, 0, stream>>>(
-        a2, w.conv3, a3, s3, s2, bn2, bn_train, update_running, eps, mom, B, h2, h2, h3, h3);
-    disc_head_kernel<8><<<B, 256, 0, stream>>>(a3, s3, bn3, bn_train, update_running, eps, mom, w.lin_w, w.lin_b, prob,
-                                               B, h3, h3);
+    ProfScope ps(KC_OTHER, stream, (double)groups * B * (32 * h1 * h1 + 16 * h2 * h2 + 8 * h3 * h3) * 8);
+    const size_t gf = gstride / 4;  // group stride of an activation pointer, in floats
+    disc_conv_kernel<1, 32, 1, false><<<dim3(ceil_div(h1 * h1, 32), B, groups), 128, 0, stream>>>(
+        mask, w.conv1, a1, s1, nullptr, none, 0, 0, eps, mom, B, fs, fs, h1, h1, (size_t)B * fs * fs, gstride);
+    disc_conv_kernel<32, 16, 2, true><<<dim3(ceil_div(h2 * h2, 32), B, groups), 128, 0, stream>>>(
+        a1, w.conv2, a2, s2, s1, bn1, bn_train, update_running, eps, mom, B, h1, h1, h2, h2, gf, gstride);
+    disc_conv_kernel<16, 8, 2, true><<<dim3(ceil_div(h3 * h3, 32), B, groups), 128, 0, stream>>>(
+        a2, w.conv3, a3, s3, s2, bn2, bn_train, update_running, eps, mom, B, h2, h2, h3, h3, gf, gstride);
+    disc_head_kernel<8><<<dim3(B, groups), 256, 0, stream>>>(a3, s3, bn3, bn_train, update_running, eps, mom, w.lin_w,
+                                                              w.lin_b, prob, B, h3, h3, gstride);
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }
@@ -425,7 +496,7 @@ int discriminator_backward(const float* mask, int B, int fs, const DiscWeights& 
     const int h1 = fs, h2 = (fs + 2 - 3) / 2 + 1, h3 = (h2 + 2 - 3) / 2 + 1;
     uint8_t* p = static_cast<uint8_t*>(fwd_workspace);
     const double* sums = reinterpret_cast<const double*>(p);
-    p += 56 * 2 * 8;
+    p += DISC_SUMS_BYTES;
     const float* z1 = reinterpret_cast<const float*>(p);
     p += (size_t)B * 32 * h1 * h1 * 4;
     const float* z2 = reinterpret_cast<const float*>(p);

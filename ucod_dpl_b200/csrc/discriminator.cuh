@@ -19,8 +19,11 @@ struct DiscWeights {
 };
 
 size_t discriminator_workspace_bytes(int B, int fs);
+size_t discriminator_workspace_bytes_groups(int B, int fs, int groups);
+// `groups` > 1: mask [groups*B, 1, fs, fs] holds that many independent forward calls (each with its own batch statistics,
+// running buffers updated in call order), run by one set of launches; prob [groups*B]; workspace from the _groups query.
 int discriminator_forward(const float* mask, int B, int fs, const DiscWeights& w, int bn_train, int update_running,
-                          float* prob, void* workspace, size_t ws_bytes, cudaStream_t stream);
+                          float* prob, void* workspace, size_t ws_bytes, cudaStream_t stream, int groups = 1);
 struct DiscGrads {  // fp32, same shapes as the weights; accumulated into
     float *conv1, *bn1_w, *bn1_b, *conv2, *bn2_w, *bn2_b, *conv3, *bn3_w, *bn3_b, *lin_w, *lin_b;
 };

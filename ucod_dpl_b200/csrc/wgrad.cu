@@ -4,8 +4,9 @@
 //     dW[c, k] = sum_t dD[t, c] * X[t, k]          c < 128 output channels, k < dim input features, t < T tokens
 //
 // A contraction over the TOKEN index of two token-major tensors: neither operand has the reduction index contiguous.
-//   * dD is small (T x 128): `wgrad_pack_kernel` fuses the last step of the backward (dD = A - r^2 t E, see decoder.cu)
-//     with a transpose to dDt bf16 [128, Tpad] (K-major A operand) and writes per-block column sums for db.
+//   * dD is small (T x 128): `decoder_bwd_pack_kernel` (decoder.cu) fuses the last step of the backward
+//     (dD = A - r^2 t E) with a transpose to dDt bf16 [128, Tpad] (K-major A operand) and writes per-block column
+//     sums for db into the buffers `wgrad_plan` lays out.
 //   * X (the cached backbone keys, T x dim bf16, the only HBM-sized read) is consumed in place as an MN-MAJOR B operand:
 //     a TMA box of 64 tokens x 64 features lands as 64 rows of 128 bytes, which is exactly the tcgen05 MN-major SW128
 //     layout (the same trick the attention kernel uses for V).
@@ -132,42 +133,6 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
     if (warp == 1) tmem_dealloc(tmem_acc, WG_BN);
 }
 
-// dD = A - (r_c^2 t_c) E for 64 tokens per CTA, written transposed as bf16 (dDt [128, Tpad], zero beyond T) for the
-// tensor-core contraction above; bpart[blk, c] = this block's column sums (db_dec, reduced later in a fixed order).
-__global__ void __launch_bounds__(256)
-    wgrad_pack_kernel(const float* __restrict__ a_buf, const float* __restrict__ e_buf, const float* __restrict__ tsum,
-                      const float* __restrict__ sumsq, const float* __restrict__ emb, __nv_bfloat16* __restrict__ dDt,
-                      float* __restrict__ bpart, int rows_per_img, int total_rows, int t_pad) {
-    __shared__ float tile[64][129];
-    __shared__ float colsum[2][128];
-    const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
-    const int r0 = blockIdx.x * 64;
-    const float e = __ldg(emb + c);
-    float acc = 0.f;
-    for (int i = half; i < 64; i += 2) {
-        const int row = r0 + i;
-        float v = 0.f;
-        if (row < total_rows) {
-            const int b = row / rows_per_img;
-            const float g = e / fmaxf(fabsf(e) * sqrtf(sumsq[b * 128 + c]), 1e-12f);
-            v = a_buf[(size_t)row * 128 + c] - g * g * tsum[b * 128 + c] * e_buf[(size_t)row * 128 + c];
-        }
-        tile[i][c] = v;
-        acc += v;
-    }
-    colsum[half][c] = acc;
-    __syncthreads();
-    if (half == 0) bpart[(size_t)blockIdx.x * 128 + c] = colsum[0][c] + colsum[1][c];
-    // transposed store: thread -> (channel cc, 32-token half hh): 32 bf16 = 64 bytes
-    const int cc = threadIdx.x >> 1, hh = threadIdx.x & 1;
-    uint32_t w[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) w[i] = pack_bf16x2(tile[hh * 32 + 2 * i][cc], tile[hh * 32 + 2 * i + 1][cc]);
-    uint4* dst = reinterpret_cast<uint4*>(dDt + (size_t)cc * t_pad + r0 + hh * 32);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dst[i] = make_uint4(w[4 * i], w[4 * i + 1], w[4 * i + 2], w[4 * i + 3]);
-}
-
 // dW = sum of the split partials, db = sum of the block column sums — both in a fixed order
 __global__ void __launch_bounds__(256)
     wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, float* __restrict__ dW, int n_elem,
@@ -208,30 +173,26 @@ size_t wgrad_workspace_bytes(int T, int dim) {
     return 128 * t_pad * 2 + (size_t)splits * 128 * dim * 4 + (size_t)n_kblocks * 128 * 4 + 4096;
 }
 
-int wgrad_tensor_core(const float* a_buf, const float* e_buf, const float* tsum, const float* sumsq, const float* emb,
-                      const void* keys_bf16, int rows_per_img, int T, int dim, float* dW, float* db, void* workspace,
-                      size_t ws_bytes, cudaStream_t stream) {
+int wgrad_plan(int T, int dim, void* workspace, size_t ws_bytes, WgradPlan* plan) {
     UCOD_REQUIRE(dim % WG_BN == 0, "wgrad: dim must be a multiple of %d", WG_BN);
     UCOD_REQUIRE(ws_bytes >= wgrad_workspace_bytes(T, dim), "wgrad: workspace too small");
     UCOD_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "wgrad: workspace must be 256-byte aligned");
-    const int n_kblocks = ceil_div(T, WG_BK);
-    const int t_pad = n_kblocks * WG_BK;
-    int kps = 1;
-    const int splits = wg_splits(n_kblocks, dim / WG_BN, &kps);
+    plan->n_kblocks = ceil_div(T, WG_BK);
+    plan->t_pad = plan->n_kblocks * WG_BK;
+    plan->splits = wg_splits(plan->n_kblocks, dim / WG_BN, &plan->kb_per_split);
     uint8_t* p = static_cast<uint8_t*>(workspace);
-    __nv_bfloat16* dDt = reinterpret_cast<__nv_bfloat16*>(p);
-    p += (128 * (size_t)t_pad * 2 + 255) / 256 * 256;
-    float* partial = reinterpret_cast<float*>(p);
-    p += (size_t)splits * 128 * dim * 4;
-    float* bpart = reinterpret_cast<float*>(p);
-    {
-        ProfScope ps(KC_DECODER, stream, (double)T * 128 * 4 * 3);
-        wgrad_pack_kernel<<<n_kblocks, 256, 0, stream>>>(a_buf, e_buf, tsum, sumsq, emb, dDt, bpart, rows_per_img, T,
-                                                         t_pad);
-    }
-    UCOD_CHECK_CUDA(cudaGetLastError());
+    plan->dDt = reinterpret_cast<__nv_bfloat16*>(p);
+    p += (128 * (size_t)plan->t_pad * 2 + 255) / 256 * 256;
+    plan->partial = reinterpret_cast<float*>(p);
+    p += (size_t)plan->splits * 128 * dim * 4;
+    plan->bpart = reinterpret_cast<float*>(p);
+    return 0;
+}
+
+int wgrad_contract(const WgradPlan& plan, const void* keys_bf16, int T, int dim, float* dW, float* db,
+                   cudaStream_t stream) {
     CUtensorMap ta, tb;
-    if (int rc = make_tmap_2d_bf16(&ta, dDt, 128, (uint64_t)t_pad, (uint64_t)t_pad, 128, 64)) return rc;
+    if (int rc = make_tmap_2d_bf16(&ta, plan.dDt, 128, (uint64_t)plan.t_pad, (uint64_t)plan.t_pad, 128, 64)) return rc;
     if (int rc = make_tmap_2d_bf16(&tb, keys_bf16, (uint64_t)T, (uint64_t)dim, (uint64_t)dim, 64, 64)) return rc;
     static bool configured = false;
     if (!configured) {
@@ -240,15 +201,15 @@ int wgrad_tensor_core(const float* a_buf, const float* e_buf, const float* tsum,
     }
     {
         ProfScope ps(KC_GEMM, stream, 2.0 * 128 * (double)dim * T);
-        wgrad_tcgen05_kernel<<<dim3(dim / WG_BN, splits), WG_THREADS, WG_SMEM, stream>>>(ta, tb, partial, dim, n_kblocks,
-                                                                                         kps);
+        wgrad_tcgen05_kernel<<<dim3(dim / WG_BN, plan.splits), WG_THREADS, WG_SMEM, stream>>>(
+                ta, tb, plan.partial, dim, plan.n_kblocks, plan.kb_per_split);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     {
         const int n_elem = 128 * dim;
-        ProfScope ps(KC_DECODER, stream, (double)splits * n_elem * 4);
-        wgrad_reduce_kernel<<<ceil_div(n_elem / 4, 256), 256, 0, stream>>>(partial, splits, dW, n_elem, bpart, n_kblocks,
-                                                                           db);
+        ProfScope ps(KC_DECODER, stream, (double)plan.splits * n_elem * 4);
+        wgrad_reduce_kernel<<<ceil_div(n_elem / 4, 256), 256, 0, stream>>>(plan.partial, plan.splits, dW, n_elem,
+                                                                           plan.bpart, plan.n_kblocks, db);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;

@@ -58,13 +58,29 @@ class Discriminator(nn.Module):
         return out
 
 
+    def forward_calls(self, masks, calls: int):
+        """`calls` consecutive `forward`s (masks [calls*B,1,fs,fs], call-major) in one set of launches; same results,
+        BatchNorm statistics and buffer updates as calling `forward` on each slice in turn."""
+        train = self.training
+        out = ops.discriminator_forward_calls(masks, calls, self._tensors(), bn_train=train, update_running=train)
+        if train:  # one fused launch for the three BatchNorm counters
+            torch._foreach_add_([blk[1].num_batches_tracked for blk in
+                                 (self.maskConv.layers, self.convs[0].layers, self.convs[1].layers)], calls)
+        return out
+
+
 def merge_pseudo_label(discriminator: Discriminator, pseudo_labels, p_teachers, p_students, features=None, *,
                        cur_epoch: int, max_epoch: int = 25, start_finetune: int = -5):
     """APM (`TrainLoop.merge_pseudo_label`, engine/runner/loop_UCOD_DPL.py:257-272).
     Returns (merged pseudo labels, dis_loss) like the reference; `.weight`/p_s/p_p are attached for logging."""
     s_mask, t_mask, p_mask = ops.apm_binarize(p_students, p_teachers, pseudo_labels)
-    p_s = discriminator(s_mask, features)
-    p_p = discriminator(p_mask, features)
+    pair = getattr(s_mask, "pair", None)
+    if pair is not None and hasattr(discriminator, "forward_calls"):
+        p_both = discriminator.forward_calls(pair, 2)                            # student call, then pseudo-label call
+        p_s, p_p = p_both[:s_mask.shape[0]], p_both[s_mask.shape[0]:]
+    else:
+        p_s = discriminator(s_mask, features)
+        p_p = discriminator(p_mask, features)
     merged, weight, loss = ops.apm_merge(pseudo_labels, t_mask, p_s, p_p, cur_epoch / (max_epoch + start_finetune))
     merge_pseudo_label.last = {"weight": weight, "p_s": p_s, "p_p": p_p}
     return merged, loss

@@ -352,10 +352,37 @@ def discriminator_forward(mask: torch.Tensor, tensors: dict, bn_train: bool = Tr
     return prob
 
 
+def discriminator_forward_calls(masks: torch.Tensor, calls: int, tensors: dict, bn_train: bool = True,
+                                update_running: bool = True) -> torch.Tensor:
+    """`calls` consecutive discriminator forwards in one set of launches: masks fp32 [calls*B,1,fs,fs] (call-major)
+    -> prob [calls*B,1]; batch statistics per call, running buffers updated in call order."""
+    _lib.require_cuda(masks)
+    m = masks.float().contiguous()
+    n, _, fs, fs2 = m.shape
+    if fs != fs2 or n % calls:
+        raise UcodError("discriminator_forward_calls expects square masks, calls * B of them")
+    B, dev = n // calls, m.device
+    w = _DiscW(*[tensors[k].data_ptr() for k, _ in _DiscW._fields_])
+    prob = torch.empty(n, 1, device=dev, dtype=torch.float32)
+    lib = _lib.load()
+    lib.ucod_discriminator_workspace_bytes_calls.restype = _u64
+    ws = _ws(lib.ucod_discriminator_workspace_bytes_calls(B, fs, calls), dev)
+    wp, wn = _aligned(ws)
+    with torch.cuda.device(dev):
+        _lib.call("ucod_discriminator_fwd_calls", ptr(m), B, calls, fs, ctypes.byref(w), 1 if bn_train else 0,
+                  1 if update_running else 0, ptr(prob), wp, wn, stream_ptr(dev))
+    return prob
+
+
 def apm_binarize(student: torch.Tensor, teacher: torch.Tensor, pl: torch.Tensor):
+    """-> (s_mask, t_mask, p_mask); s_mask and p_mask are the two halves of one [2B,...] buffer (`.pair`) so that both
+    discriminator calls of the APM can share a launch."""
     _lib.require_cuda(student, teacher, pl)
     s, t, p = student.float().contiguous(), teacher.float().contiguous(), pl.float().contiguous()
-    sm, tm, pm = torch.empty_like(s), torch.empty_like(t), torch.empty_like(p)
+    pair = torch.empty((2 * s.shape[0],) + tuple(s.shape[1:]), device=s.device, dtype=torch.float32)
+    sm, pm = pair[:s.shape[0]], pair[s.shape[0]:]
+    tm = torch.empty_like(t)
+    sm.pair = pair
     with torch.cuda.device(s.device):
         _lib.call("ucod_apm_binarize", ptr(s), ptr(t), ptr(p), ptr(sm), ptr(tm), ptr(pm), _u64(s.numel()),
                   stream_ptr(s.device))

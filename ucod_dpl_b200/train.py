@@ -52,7 +52,7 @@ def _backward(dec, tokens, grid_in, grid_out, fg, bg, fwd_ws, grads, *, target=N
     dev = tokens.device
     lib = _lib.load()
     lib.ucod_decoder_bwd_workspace_bytes.restype = _u64
-    bws = torch.empty(int(lib.ucod_decoder_bwd_workspace_bytes(B, gh, gw)) + 1024, dtype=torch.uint8, device=dev)
+    bws = torch.empty(int(lib.ucod_decoder_bwd_workspace_bytes(B, gh, gw, oh, ow)) + 1024, dtype=torch.uint8, device=dev)
     boff = (-bws.data_ptr()) % 1024
     ws, off = fwd_ws
     loss2 = torch.empty(2, device=dev)
