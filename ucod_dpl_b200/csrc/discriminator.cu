@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(128)
                      float* __restrict__ out, double* __restrict__ out_sums /*[COUT,2]*/,
                      const double* __restrict__ in_sums, BnParams in_bn, int bn_train, int update_running,
                      float eps, float momentum, int B, int Hin, int Win, int Hout, int Wout, size_t in_gstride,
-                     size_t ws_gstride /*bytes between the groups' workspaces*/) {
+                     size_t ws_gstride /*bytes between the groups' workspaces*/, int tiles_per_block) {
     // blockIdx.z = group: an independent forward call (own batch statistics, own workspace) sharing the launch
     const int grp = blockIdx.z;
     in += (size_t)grp * in_gstride;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(128)
     if (IN_BN) in_sums = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(in_sums) + (size_t)grp * ws_gstride);
     __shared__ __align__(16) float s_w[CIN * 9 * COUT];  // [c][k][o]: the COUT weights of one tap are contiguous (LDS.128)
     __shared__ float s_scale[CIN], s_shift[CIN];
-    for (int i = threadIdx.x; i < COUT * CIN * 9; i += blockDim.x) s_w[(i % (CIN * 9)) * COUT + i / (CIN * 9)] = weight[i];
+    for (int j = threadIdx.x; j < COUT * CIN * 9; j += blockDim.x) s_w[j] = weight[(j % COUT) * (CIN * 9) + j / COUT];
     if (IN_BN) {
         const double count = (double)B * Hin * Win;
         for (int c = threadIdx.x; c < CIN; c += blockDim.x) {
@@ -107,72 +107,82 @@ __global__ void __launch_bounds__(128)
     __shared__ float s_part[KSPLIT ? 4 * COUT * 32 : 1];
     const int b = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pix = blockIdx.x * 32 + lane;
-    const bool active = pix < Hout * Wout;
     const int c_begin = KSPLIT ? warp * (CIN / 4) : 0, c_end = KSPLIT ? c_begin + CIN / 4 : CIN;
     const int o_first = KSPLIT ? 0 : warp * OG;  // first output channel of acc[]
-    float acc[NACC];
+    const float* img = in + (size_t)b * CIN * Hin * Win;
+    const int n_tiles = (Hout * Wout + 31) / 32;
+    const int tile_end = min(n_tiles, ((int)blockIdx.x + 1) * tiles_per_block);
+    float ssum[OG], qsum[OG];  // BatchNorm sums of this warp's channels over the CTA's tiles
 #pragma unroll
-    for (int o = 0; o < NACC; ++o) acc[o] = 0.f;
-    if (active) {
-        const int oy = pix / Wout, ox = pix - oy * Wout;
-        const float* img = in + (size_t)b * CIN * Hin * Win;
-        for (int c = c_begin; c < c_end; ++c) {
-            float v[9];
+    for (int j = 0; j < OG; ++j) ssum[j] = 0.f, qsum[j] = 0.f;
+    // several 32-pixel tiles per CTA: the weight / BatchNorm prologue above costs more than one tile's arithmetic
+    for (int tile = blockIdx.x * tiles_per_block; tile < tile_end; ++tile) {
+        const int pix = tile * 32 + lane;
+        const bool active = pix < Hout * Wout;
+        float acc[NACC];
 #pragma unroll
-            for (int ky = 0; ky < 3; ++ky)
+        for (int o = 0; o < NACC; ++o) acc[o] = 0.f;
+        if (active) {
+            const int oy = pix / Wout, ox = pix - oy * Wout;
+            for (int c = c_begin; c < c_end; ++c) {
+                float v[9];
 #pragma unroll
-                for (int kx = 0; kx < 3; ++kx) {
-                    const int iy = oy * STRIDE + ky - 1, ix = ox * STRIDE + kx - 1;
-                    float t = 0.f;  // zero padding applies AFTER BN + LeakyReLU of the previous block
-                    if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
-                        t = img[((size_t)c * Hin + iy) * Win + ix];
-                        if (IN_BN) {
-                            t = t * s_scale[c] + s_shift[c];
-                            t = t > 0.f ? t : LRELU * t;
+                for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+                    for (int kx = 0; kx < 3; ++kx) {
+                        const int iy = oy * STRIDE + ky - 1, ix = ox * STRIDE + kx - 1;
+                        float t = 0.f;  // zero padding applies AFTER BN + LeakyReLU of the previous block
+                        if (iy >= 0 && iy < Hin && ix >= 0 && ix < Win) {
+                            t = img[((size_t)c * Hin + iy) * Win + ix];
+                            if (IN_BN) {
+                                t = t * s_scale[c] + s_shift[c];
+                                t = t > 0.f ? t : LRELU * t;
+                            }
                         }
+                        v[ky * 3 + kx] = t;
                     }
-                    v[ky * 3 + kx] = t;
-                }
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const float4* w4 = reinterpret_cast<const float4*>(s_w + (c * 9 + k) * COUT + o_first);
+                for (int k = 0; k < 9; ++k) {
+                    const float4* w4 = reinterpret_cast<const float4*>(s_w + (c * 9 + k) * COUT + o_first);
 #pragma unroll
-                for (int o4 = 0; o4 < NACC / 4; ++o4) {
-                    const float4 w = w4[o4];
-                    acc[4 * o4 + 0] += v[k] * w.x, acc[4 * o4 + 1] += v[k] * w.y;
-                    acc[4 * o4 + 2] += v[k] * w.z, acc[4 * o4 + 3] += v[k] * w.w;
+                    for (int o4 = 0; o4 < NACC / 4; ++o4) {
+                        const float4 w = w4[o4];
+                        acc[4 * o4 + 0] += v[k] * w.x, acc[4 * o4 + 1] += v[k] * w.y;
+                        acc[4 * o4 + 2] += v[k] * w.z, acc[4 * o4 + 3] += v[k] * w.w;
+                    }
                 }
             }
         }
-    }
-    float fin[OG];  // this warp's OG output channels [warp*OG, ...) of pixel `pix`
-    if constexpr (KSPLIT) {
+        float fin[OG];  // this warp's OG output channels [warp*OG, ...) of pixel `pix`
+        if constexpr (KSPLIT) {
+            if (tile != (int)blockIdx.x * tiles_per_block) __syncthreads();  // previous tile's partials consumed
 #pragma unroll
-        for (int o = 0; o < COUT; ++o) s_part[(warp * COUT + o) * 32 + lane] = acc[o];
-        __syncthreads();
+            for (int o = 0; o < COUT; ++o) s_part[(warp * COUT + o) * 32 + lane] = acc[o];
+            __syncthreads();
 #pragma unroll
-        for (int j = 0; j < OG; ++j) {
-            const int o = warp * OG + j;
-            fin[j] = (s_part[(0 * COUT + o) * 32 + lane] + s_part[(1 * COUT + o) * 32 + lane]) +
-                     (s_part[(2 * COUT + o) * 32 + lane] + s_part[(3 * COUT + o) * 32 + lane]);
+            for (int j = 0; j < OG; ++j) {
+                const int o = warp * OG + j;
+                fin[j] = (s_part[(0 * COUT + o) * 32 + lane] + s_part[(1 * COUT + o) * 32 + lane]) +
+                         (s_part[(2 * COUT + o) * 32 + lane] + s_part[(3 * COUT + o) * 32 + lane]);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < OG; ++j) fin[j] = acc[j];
         }
-    } else {
+        if (active) {
+            float* dst = out + ((size_t)b * COUT + warp * OG) * Hout * Wout + pix;
 #pragma unroll
-        for (int j = 0; j < OG; ++j) fin[j] = acc[j];
-    }
-    if (active) {
-        float* dst = out + ((size_t)b * COUT + warp * OG) * Hout * Wout + pix;
-#pragma unroll
-        for (int j = 0; j < OG; ++j) dst[(size_t)j * Hout * Wout] = fin[j];
+            for (int j = 0; j < OG; ++j) {
+                dst[(size_t)j * Hout * Wout] = fin[j];
+                ssum[j] += fin[j], qsum[j] += fin[j] * fin[j];
+            }
+        }
     }
     // per-channel sum / sum of squares of the raw outputs (for the next BatchNorm): a warp reduction (fixed order), then
     // one fp64 atomic per channel and CTA into this CTA's slot, whose order only matters below fp32 resolution
 #pragma unroll
     for (int j = 0; j < OG; ++j) {
-        float sv = active ? fin[j] : 0.f, q = sv * sv;
-        sv = warp_sum(sv);
-        q = warp_sum(q);
+        const float sv = warp_sum(ssum[j]), q = warp_sum(qsum[j]);
         if (lane == 0) {
             double* slot = out_sums + (blockIdx.x % DISC_SLOTS) * DISC_SUMS;
             atomicAdd(&slot[2 * (warp * OG + j)], (double)sv);
@@ -470,12 +480,19 @@ int discriminator_forward(const float* mask, int B, int fs, const DiscWeights& w
         bn3{w.bn3_w, w.bn3_b, w.bn3_mean, w.bn3_var}, none{nullptr, nullptr, nullptr, nullptr};
     ProfScope ps(KC_OTHER, stream, (double)groups * B * (32 * h1 * h1 + 16 * h2 * h2 + 8 * h3 * h3) * 8);
     const size_t gf = gstride / 4;  // group stride of an activation pointer, in floats
-    disc_conv_kernel<1, 32, 1, false><<<dim3(ceil_div(h1 * h1, 32), B, groups), 128, 0, stream>>>(
-        mask, w.conv1, a1, s1, nullptr, none, 0, 0, eps, mom, B, fs, fs, h1, h1, (size_t)B * fs * fs, gstride);
-    disc_conv_kernel<32, 16, 2, true><<<dim3(ceil_div(h2 * h2, 32), B, groups), 128, 0, stream>>>(
-        a1, w.conv2, a2, s2, s1, bn1, bn_train, update_running, eps, mom, B, h1, h1, h2, h2, gf, gstride);
-    disc_conv_kernel<16, 8, 2, true><<<dim3(ceil_div(h3 * h3, 32), B, groups), 128, 0, stream>>>(
-        a2, w.conv3, a3, s3, s2, bn2, bn_train, update_running, eps, mom, B, h2, h2, h3, h3, gf, gstride);
+    // tiles of 32 pixels per CTA: enough CTAs for ~4 per SM, not more (each CTA re-stages the weights / BN constants)
+    auto tiles_per_block = [&](int npix) {
+        const int n_tiles = ceil_div(npix, 32);
+        const int want = ceil_div(4 * device_sm_count(), B * groups);  // CTAs per (image, call)
+        return ceil_div(n_tiles, want < 1 ? 1 : (want > n_tiles ? n_tiles : want));
+    };
+    const int t1 = tiles_per_block(h1 * h1), t2 = tiles_per_block(h2 * h2), t3 = tiles_per_block(h3 * h3);
+    disc_conv_kernel<1, 32, 1, false><<<dim3(ceil_div(ceil_div(h1 * h1, 32), t1), B, groups), 128, 0, stream>>>(
+        mask, w.conv1, a1, s1, nullptr, none, 0, 0, eps, mom, B, fs, fs, h1, h1, (size_t)B * fs * fs, gstride, t1);
+    disc_conv_kernel<32, 16, 2, true><<<dim3(ceil_div(ceil_div(h2 * h2, 32), t2), B, groups), 128, 0, stream>>>(
+        a1, w.conv2, a2, s2, s1, bn1, bn_train, update_running, eps, mom, B, h1, h1, h2, h2, gf, gstride, t2);
+    disc_conv_kernel<16, 8, 2, true><<<dim3(ceil_div(ceil_div(h3 * h3, 32), t3), B, groups), 128, 0, stream>>>(
+        a2, w.conv3, a3, s3, s2, bn2, bn_train, update_running, eps, mom, B, h2, h2, h3, h3, gf, gstride, t3);
     disc_head_kernel<8><<<dim3(B, groups), 256, 0, stream>>>(a3, s3, bn3, bn_train, update_running, eps, mom, w.lin_w,
                                                               w.lin_b, prob, B, h3, h3, gstride);
     UCOD_CHECK_CUDA(cudaGetLastError());
