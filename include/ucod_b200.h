@@ -154,10 +154,14 @@ int ucod_pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf
                             float th_bkg, float epsilon, float* cos, uint8_t* bkg, int32_t* ref_idx, float* sim,
                             void* scratch, void* stream);
 /* Same with the reference's `apply_weights` switch (found_bkg_mask.py:44-47,64-65): 0 = neither the descriptors nor the
- * per-patch attention sum are weighted by the head sparsity weights beta. */
+ * per-patch attention sum are weighted by the head sparsity weights beta.  A scratch of
+ * ucod_pseudo_label_scratch_bytes(batch, heads) (256-byte aligned) selects the two-launch path: the weights /
+ * reference-patch prologue for all images first, then a streaming kernel over (image, slab of patches); with the
+ * 4-byte scratch the single-launch kernel runs.  Results are identical. */
+uint64_t ucod_pseudo_label_scratch_bytes(int batch, int heads);
 int ucod_pseudo_label_score_ex(const float* attn_cls, const void* keys, int keys_bf16, int batch, int heads, int patches,
                                float th_bkg, float epsilon, int apply_weights, float* cos, uint8_t* bkg,
-                               int32_t* ref_idx, float* sim, void* scratch, void* stream);
+                               int32_t* ref_idx, float* sim, void* scratch, uint64_t scratch_bytes, void* stream);
 /* `refine_post_process` (generate_pseudo_label.py:30-67): flip 8-connected foreground components with
  * area < area_threshold whose 1-px ring is entirely the opposite label; OpenCV label order; h*w <= 1024.
  * mask_in/mask_out: uint8 {0,1} [batch, h, w] (may alias). */

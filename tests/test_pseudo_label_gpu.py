@@ -45,6 +45,28 @@ def test_score_batched_equals_per_image_masks():
         assert torch.equal(bkg[b], bkg1[0]) and ref[b] == ref1[0]
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_two_launch_path_equals_single_launch_kernel(dtype):
+    """ops.pseudo_label_score runs the prologue / streaming pair (large scratch); the legacy C entry with its 4-byte
+    scratch runs the one-CTA-per-image kernel: same arithmetic up to the order of the block-wide sums (256 vs 512
+    threads), so the cosines agree to a few ulp and the masks wherever the cosine is not within 1e-5 of the threshold."""
+    from ucod_dpl_b200 import _lib
+    att, keys = planted(9, seed=21)
+    att, keys = att.cuda(), keys.cuda().to(dtype)
+    cos, bkg, ref, sim = ops.pseudo_label_score(att, keys, 0.6, want_sim=True)
+    B, nh, P = att.shape
+    cos1, sim1 = torch.empty_like(cos), torch.empty_like(sim)
+    bkg1, ref1 = torch.empty_like(bkg), torch.empty_like(ref)
+    scratch = torch.empty(1, device="cuda", dtype=torch.int32)
+    _lib.call("ucod_pseudo_label_score", _lib.ptr(att), _lib.ptr(keys), 1 if dtype == torch.bfloat16 else 0, B, nh, P,
+              _lib.c_float(0.6), _lib.c_float(1e-10), _lib.ptr(cos1), _lib.ptr(bkg1), _lib.ptr(ref1), _lib.ptr(sim1),
+              _lib.ptr(scratch), _lib.stream_ptr())
+    assert torch.equal(ref, ref1)
+    assert (cos - cos1).abs().max().item() < 2e-6 and (sim - sim1).abs().max().item() < 1e-5
+    differ = bkg != bkg1
+    assert ((cos - 0.6).abs()[differ] < 1e-5).all()
+
+
 def test_dropin_signature():
     from ucod_dpl_b200.data.utils.found_bkg_mask import compute_img_bkg_seg
     att, keys = planted(1, seed=9)

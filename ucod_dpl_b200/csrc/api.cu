@@ -119,11 +119,15 @@ int ucod_pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf
     return pseudo_label_score(attn_cls, keys, keys_bf16, batch, heads, patches, th_bkg, epsilon, cos, bkg, ref_idx,
                               sim, static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream));
 }
+uint64_t ucod_pseudo_label_scratch_bytes(int batch, int heads) {
+    return (uint64_t)pseudo_label_scratch_bytes(batch, heads);
+}
 int ucod_pseudo_label_score_ex(const float* attn_cls, const void* keys, int keys_bf16, int batch, int heads, int patches,
                                float th_bkg, float epsilon, int apply_weights, float* cos, uint8_t* bkg,
-                               int32_t* ref_idx, float* sim, void* scratch, void* stream) {
+                               int32_t* ref_idx, float* sim, void* scratch, uint64_t scratch_bytes, void* stream) {
     return pseudo_label_score(attn_cls, keys, keys_bf16, batch, heads, patches, th_bkg, epsilon, cos, bkg, ref_idx,
-                              sim, static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream), apply_weights);
+                              sim, static_cast<int*>(scratch), reinterpret_cast<cudaStream_t>(stream), apply_weights,
+                              (size_t)scratch_bytes);
 }
 int ucod_refine_small_components(const uint8_t* mask_in, uint8_t* mask_out, int batch, int h, int w,
                                  int area_threshold, void* stream) {

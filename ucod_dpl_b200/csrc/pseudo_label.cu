@@ -38,14 +38,22 @@ __device__ __forceinline__ float key_at<__nv_bfloat16>(const __nv_bfloat16* p, i
 
 // attn [B, nh, P] fp32 ; keys [B, P, nh*64] (TK) ; outputs cos [B,P] fp32, bkg [B,P] u8, ref_idx [B] i32,
 // gmax: device scalar (ordered-int encoded) receiving max over the launch of (1 - cos).
-template <typename TK>
+// MODE 0: everything in one launch, one CTA per image (4-byte scratch; the legacy entry point).
+// MODE 1 + MODE 2 (the fast path): the prologue (weights, reference patch, normalised reference descriptor) is a chain of
+// block-wide reductions that touches 12 KB of attention per image, while the cosine row streams the whole key block.
+// With both in one CTA per image the stream waits for the chain and runs at one CTA's memory parallelism (0.27-0.38
+// of HBM with bf16 keys).  MODE 1 runs the chain for all images at once (one small CTA per image) and leaves
+// refvec [B, C] / beta [B, 16] in the scratch; MODE 2 is a pure streaming kernel over (image, slab of PL_SLAB patches).
+constexpr int PL_SLAB = 32;
+template <typename TK, int MODE>
 __global__ void __launch_bounds__(PL_THREADS)
     pseudo_label_score_kernel(const float* __restrict__ attn, const TK* __restrict__ keys, float* __restrict__ cos_out,
                               uint8_t* __restrict__ bkg_out, int* __restrict__ ref_out, int* __restrict__ gmax,
-                              int nh, int P, float th_bkg, float epsilon, int apply_weights) {
+                              int nh, int P, float th_bkg, float epsilon, int apply_weights,
+                              float* __restrict__ refvec, float* __restrict__ betas) {
     extern __shared__ float sm[];
-    float* s_att = sm;              // nh * P
-    float* s_ref = s_att + nh * P;  // nh * 64 (normalised, beta-weighted reference descriptor)
+    float* s_att = sm;                                  // nh * P (MODE 0 / 1)
+    float* s_ref = MODE == 2 ? sm : s_att + nh * P;     // nh * 64 (normalised, beta-weighted reference descriptor)
     __shared__ float red[PL_THREADS / 32];
     __shared__ float s_beta[PL_MAX_HEADS];
     __shared__ int s_cnt[PL_MAX_HEADS];
@@ -59,83 +67,81 @@ __global__ void __launch_bounds__(PL_THREADS)
     const float* att_b = attn + (size_t)b * nh * P;
     const TK* keys_b = keys + (size_t)b * P * C;
 
-    // The weights / reference-patch prologue below only touches the 12 KB of attention; the image's key block is
-    // pulled into L2 meanwhile (bulk L2 prefetch, no register or shared-memory destination), so the streaming pass
-    // that follows is not serialised behind the prologue's latency chain.
-    {
-        const size_t bytes = (size_t)P * C * sizeof(TK);  // C = nh*64: a multiple of 128 bytes
-        const char* base = reinterpret_cast<const char*>(keys_b);
-        constexpr unsigned CH = 16384;
-        for (size_t off = (size_t)threadIdx.x * CH; off < bytes; off += (size_t)blockDim.x * CH) {
-            const unsigned n = (unsigned)(bytes - off < CH ? bytes - off : CH);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(n) : "memory");
+    if constexpr (MODE != 2) {
+        // ---- threshold = mean attention; Q_h = fraction of patches above it; beta_h ----
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < nh * P; i += blockDim.x) {
+            const float a = att_b[i];
+            s_att[i] = a;
+            acc += a;
         }
-    }
-
-    // ---- threshold = mean attention; Q_h = fraction of patches above it; beta_h ----
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < nh * P; i += blockDim.x) {
-        const float a = att_b[i];
-        s_att[i] = a;
-        acc += a;
-    }
-    if (threadIdx.x < PL_MAX_HEADS) s_cnt[threadIdx.x] = 0;
-    const float thr = block_sum(acc, red) / (float)(nh * P);
-    for (int h = 0; h < nh; ++h) {
-        int c = 0;
-        for (int p = threadIdx.x; p < P; p += blockDim.x) c += s_att[h * P + p] > thr ? 1 : 0;
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0 && c) atomicAdd(&s_cnt[h], c);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float tot = 0.f;
-        for (int h = 0; h < nh; ++h) tot += (float)s_cnt[h] / (float)P + epsilon;
-        // apply_weights = False (found_bkg_mask.py:44-47,64-65): neither the descriptors nor the attention sum are weighted
-        for (int h = 0; h < nh; ++h) s_beta[h] = apply_weights ? logf(tot / ((float)s_cnt[h] / (float)P + epsilon)) : 1.f;
-    }
-    __syncthreads();
-
-    // ---- reference patch = argmin_p sum_h att[h,p] * beta[h] (first index on ties) ----
-    float best = INFINITY;
-    int besti = 0x7fffffff;
-    for (int p = threadIdx.x; p < P; p += blockDim.x) {
-        float s = 0.f;
-        for (int h = 0; h < nh; ++h) s += s_att[h * P + p] * s_beta[h];
-        if (s < best) best = s, besti = p;  // p increases per thread -> keeps the first minimum
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-        if (ov < best || (ov == best && oi < besti)) best = ov, besti = oi;
-    }
-    if (lane == 0) s_minv[warp] = best, s_mini[warp] = besti;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float bv = s_minv[0];
-        int bi = s_mini[0];
-        for (int i = 1; i < nw; ++i)
-            if (s_minv[i] < bv || (s_minv[i] == bv && s_mini[i] < bi)) bv = s_minv[i], bi = s_mini[i];
-        s_refidx = bi;
-        ref_out[b] = bi;
-    }
-    __syncthreads();
-    const int ref = s_refidx;
-
-    // ---- normalised reference descriptor ----
-    {
-        const TK* kr = keys_b + (size_t)ref * C;
-        float q = 0.f;
-        for (int i = threadIdx.x; i < C; i += blockDim.x) {
-            const float v = key_at<TK>(kr, i) * s_beta[i >> 6];
-            s_ref[i] = v;
-            q += v * v;
+        if (threadIdx.x < PL_MAX_HEADS) s_cnt[threadIdx.x] = 0;
+        const float thr = block_sum(acc, red) / (float)(nh * P);
+        for (int h = 0; h < nh; ++h) {
+            int c = 0;
+            for (int p = threadIdx.x; p < P; p += blockDim.x) c += s_att[h * P + p] > thr ? 1 : 0;
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0 && c) atomicAdd(&s_cnt[h], c);
         }
-        const float nrm = fmaxf(sqrtf(block_sum(q, red)), 1e-12f);
-        for (int i = threadIdx.x; i < C; i += blockDim.x) s_ref[i] /= nrm;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float tot = 0.f;
+            for (int h = 0; h < nh; ++h) tot += (float)s_cnt[h] / (float)P + epsilon;
+            // apply_weights = False (found_bkg_mask.py:44-47,64-65): neither the descriptors nor the attention sum are weighted
+            for (int h = 0; h < nh; ++h) s_beta[h] = apply_weights ? logf(tot / ((float)s_cnt[h] / (float)P + epsilon)) : 1.f;
+        }
+        __syncthreads();
+
+        // ---- reference patch = argmin_p sum_h att[h,p] * beta[h] (first index on ties) ----
+        float best = INFINITY;
+        int besti = 0x7fffffff;
+        for (int p = threadIdx.x; p < P; p += blockDim.x) {
+            float s = 0.f;
+            for (int h = 0; h < nh; ++h) s += s_att[h * P + p] * s_beta[h];
+            if (s < best) best = s, besti = p;  // p increases per thread -> keeps the first minimum
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+            if (ov < best || (ov == best && oi < besti)) best = ov, besti = oi;
+        }
+        if (lane == 0) s_minv[warp] = best, s_mini[warp] = besti;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float bv = s_minv[0];
+            int bi = s_mini[0];
+            for (int i = 1; i < nw; ++i)
+                if (s_minv[i] < bv || (s_minv[i] == bv && s_mini[i] < bi)) bv = s_minv[i], bi = s_mini[i];
+            s_refidx = bi;
+            ref_out[b] = bi;
+        }
+        __syncthreads();
+        const int ref = s_refidx;
+
+        // ---- normalised reference descriptor ----
+        {
+            const TK* kr = keys_b + (size_t)ref * C;
+            float q = 0.f;
+            for (int i = threadIdx.x; i < C; i += blockDim.x) {
+                const float v = key_at<TK>(kr, i) * s_beta[i >> 6];
+                s_ref[i] = v;
+                q += v * v;
+            }
+            const float nrm = fmaxf(sqrtf(block_sum(q, red)), 1e-12f);
+            for (int i = threadIdx.x; i < C; i += blockDim.x) s_ref[i] /= nrm;
+            __syncthreads();
+        }
+
+        if constexpr (MODE == 1) {  // publish for the streaming kernel
+            for (int i = threadIdx.x; i < C; i += blockDim.x) refvec[(size_t)b * C + i] = s_ref[i];
+            if (threadIdx.x < PL_MAX_HEADS) betas[b * PL_MAX_HEADS + threadIdx.x] = threadIdx.x < nh ? s_beta[threadIdx.x] : 0.f;
+            return;
+        }
+    } else {
+        for (int i = threadIdx.x; i < C; i += blockDim.x) s_ref[i] = refvec[(size_t)b * C + i];
+        if (threadIdx.x < PL_MAX_HEADS) s_beta[threadIdx.x] = betas[b * PL_MAX_HEADS + threadIdx.x];
         __syncthreads();
     }
-
     // ---- one warp per patch: cos(ref, p); 128-bit key loads (8 bf16 / 4 fp32 per lane and step).
     // Two patches per iteration with all their loads issued before the first reduction: with one patch in flight a
     // warp alternates between a DRAM round trip and two dependent shuffle trees, and the kernel took the same time
@@ -144,11 +150,13 @@ __global__ void __launch_bounds__(PL_THREADS)
     constexpr int VMAX = (PL_MAX_HEADS * 64 / EPV + 31) / 32;  // vectors per lane and patch (upper bound)
     const int nvec = C / EPV;
     float wmax = -INFINITY;
-    for (int p0 = 2 * warp; p0 < P; p0 += 2 * nw) {
+    const int p_begin = MODE == 2 ? (int)blockIdx.y * PL_SLAB : 0;
+    const int p_end = MODE == 2 ? min(P, p_begin + PL_SLAB) : P;
+    for (int p0 = p_begin + 2 * warp; p0 < p_end; p0 += 2 * nw) {
         uint4 raw[2][VMAX];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            const int p = p0 + u < P ? p0 + u : p0;
+            const int p = p0 + u < p_end ? p0 + u : p0;
             const uint4* kr = reinterpret_cast<const uint4*>(keys_b + (size_t)p * C);
 #pragma unroll
             for (int i = 0; i < VMAX; ++i) {
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(PL_THREADS)
             q[0] += __shfl_xor_sync(0xffffffffu, q[0], o);
             q[1] += __shfl_xor_sync(0xffffffffu, q[1], o);
         }
-        if (lane < 2 && p0 + lane < P) {
+        if (lane < 2 && p0 + lane < p_end) {
             const float c = (lane == 0 ? dot[0] : dot[1]) / fmaxf(sqrtf(lane == 0 ? q[0] : q[1]), 1e-12f);
             cos_out[(size_t)b * P + p0 + lane] = c;
             bkg_out[(size_t)b * P + p0 + lane] = c > th_bkg ? 1 : 0;
@@ -323,33 +331,58 @@ __global__ void __launch_bounds__(256)
 
 }  // namespace
 
+size_t pseudo_label_scratch_bytes(int B, int nh) {
+    return 256 + (size_t)B * ((size_t)nh * 64 + PL_MAX_HEADS) * sizeof(float);
+}
+
+template <typename TK>
+static int launch_score(const float* attn_cls, const TK* keys, int B, int nh, int P, float th_bkg, float epsilon,
+                        float* cos_out, uint8_t* bkg_out, int* ref_out, int* scratch, size_t scratch_bytes,
+                        cudaStream_t stream, int apply_weights, double bytes) {
+    const size_t smem = ((size_t)nh * P + (size_t)nh * 64) * sizeof(float);
+    UCOD_REQUIRE(smem <= 200 * 1024, "pseudo_label_score: %d patches do not fit in shared memory", P);
+    if (scratch != nullptr && scratch_bytes >= pseudo_label_scratch_bytes(B, nh)) {
+        float* refvec = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(scratch) + 256);
+        float* betas = refvec + (size_t)B * nh * 64;
+        auto k1 = pseudo_label_score_kernel<TK, 1>;
+        auto k2 = pseudo_label_score_kernel<TK, 2>;
+        if (smem > 48 * 1024)
+            UCOD_CHECK_CUDA(cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope ps(KC_PSEUDO, stream, bytes);
+        k1<<<B, 256, smem, stream>>>(attn_cls, keys, cos_out, bkg_out, ref_out, scratch, nh, P, th_bkg, epsilon,
+                                     apply_weights, refvec, betas);
+        k2<<<dim3(B, ceil_div(P, PL_SLAB)), 256, (size_t)nh * 64 * sizeof(float), stream>>>(
+                attn_cls, keys, cos_out, bkg_out, ref_out, scratch, nh, P, th_bkg, epsilon, apply_weights, refvec, betas);
+    } else {
+        auto kern = pseudo_label_score_kernel<TK, 0>;
+        if (smem > 48 * 1024)
+            UCOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ProfScope ps(KC_PSEUDO, stream, bytes);
+        kern<<<B, PL_THREADS, smem, stream>>>(attn_cls, keys, cos_out, bkg_out, ref_out, scratch, nh, P, th_bkg, epsilon,
+                                              apply_weights, nullptr, nullptr);
+    }
+    return 0;
+}
+
 int pseudo_label_score(const float* attn_cls, const void* keys, int keys_bf16, int B, int nh, int P, float th_bkg,
                        float epsilon, float* cos_out, uint8_t* bkg_out, int* ref_out, float* sim_out, int* scratch,
-                       cudaStream_t stream, int apply_weights) {
+                       cudaStream_t stream, int apply_weights, size_t scratch_bytes) {
     UCOD_REQUIRE(attn_cls && keys && cos_out && bkg_out && ref_out, "pseudo_label_score: null argument");
     UCOD_REQUIRE(B > 0 && P > 0 && nh > 0 && nh <= PL_MAX_HEADS, "pseudo_label_score: bad geometry (heads <= 16)");
     UCOD_REQUIRE(sim_out == nullptr || scratch != nullptr, "pseudo_label_score: sim_map needs the 4-byte scratch");
-    const size_t smem = ((size_t)nh * P + (size_t)nh * 64) * sizeof(float);
-    UCOD_REQUIRE(smem <= 200 * 1024, "pseudo_label_score: %d patches do not fit in shared memory", P);
     if (scratch) {
         // 0x80808080 decodes (ordered-int encoding) to about -3.39e38: below any real 1 - cos
         UCOD_CHECK_CUDA(cudaMemsetAsync(scratch, 0x80, sizeof(int), stream));
     }
     const double bytes = (double)B * P * nh * 64 * (keys_bf16 ? 2 : 4) + (double)B * nh * P * 4 + (double)B * P * 5;
     if (keys_bf16) {
-        auto kern = pseudo_label_score_kernel<__nv_bfloat16>;
-        if (smem > 48 * 1024)
-            UCOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ProfScope ps(KC_PSEUDO, stream, bytes);
-        kern<<<B, PL_THREADS, smem, stream>>>(attn_cls, static_cast<const __nv_bfloat16*>(keys), cos_out, bkg_out,
-                                              ref_out, scratch, nh, P, th_bkg, epsilon, apply_weights);
+        if (int rc = launch_score(attn_cls, static_cast<const __nv_bfloat16*>(keys), B, nh, P, th_bkg, epsilon, cos_out,
+                                  bkg_out, ref_out, scratch, scratch_bytes, stream, apply_weights, bytes))
+            return rc;
     } else {
-        auto kern = pseudo_label_score_kernel<float>;
-        if (smem > 48 * 1024)
-            UCOD_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        ProfScope ps(KC_PSEUDO, stream, bytes);
-        kern<<<B, PL_THREADS, smem, stream>>>(attn_cls, static_cast<const float*>(keys), cos_out, bkg_out, ref_out,
-                                              scratch, nh, P, th_bkg, epsilon, apply_weights);
+        if (int rc = launch_score(attn_cls, static_cast<const float*>(keys), B, nh, P, th_bkg, epsilon, cos_out, bkg_out,
+                                  ref_out, scratch, scratch_bytes, stream, apply_weights, bytes))
+            return rc;
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     if (sim_out) {

@@ -107,11 +107,14 @@ def pseudo_label_score(attn_cls: torch.Tensor, keys: torch.Tensor, th_bkg: float
     bkg = torch.empty(B, P, device=dev, dtype=torch.uint8)
     ref = torch.empty(B, device=dev, dtype=torch.int32)
     sim = torch.empty(B, P, device=dev, dtype=torch.float32) if want_sim else None
-    scratch = torch.empty(1, device=dev, dtype=torch.int32)
+    lib = _lib.load()
+    lib.ucod_pseudo_label_scratch_bytes.restype = _u64
+    ws = _ws(lib.ucod_pseudo_label_scratch_bytes(B, nh), dev)
+    wp, wn = _aligned(ws)
     with torch.cuda.device(dev):
         _lib.call("ucod_pseudo_label_score_ex", ptr(attn_cls), ptr(keys), 1 if keys.dtype == torch.bfloat16 else 0, B,
                   nh, P, c_float(th_bkg), c_float(epsilon), 1 if apply_weights else 0, ptr(cos), ptr(bkg), ptr(ref),
-                  ptr(sim), ptr(scratch), stream_ptr(dev))
+                  ptr(sim), wp, wn, stream_ptr(dev))
     return cos, bkg, ref, sim
 
 
