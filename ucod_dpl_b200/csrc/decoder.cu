@@ -210,68 +210,89 @@ __global__ void __launch_bounds__(256)
 
 // Orthogonality loss pieces from the normalised features fhat [B, npix, 128] (first 64 = branch 1):
 //   gram[b, 0|1, 64, 64] = F_k^T F_k ; diag[b] = sum_i (f1_i . f2_i)^2
-// Stage 1: one CTA per (pixel chunk, image) computes both 64x64 Grams of its chunk with 4x4 register tiles (256 threads
-// = 16 x 16 tiles; per pixel a thread reads two float4 per branch from shared memory for 32 FMAs) and writes them to
-// its own slot of `part` — no atomics.  Stage 2 sums the slots in a fixed order (bit-reproducible), stage 3 reduces
+// Stage 1: one CTA per (pixel chunk, image) computes both 64x64 Grams of its chunk (below) and writes them to its own
+// slot of `part` — no atomics.  Stage 2 sums the slots in a fixed order (bit-reproducible), stage 3 reduces
 // <G1, G2>_F - diag in fp64.  (Round 1: 8-pixel tiles, 34 shared loads per 32 FMAs and 8 192 float atomics per CTA:
-// 240 us for 16 images; this version: see DESIGN.md.)
-constexpr int GRAM_CHUNK = 128;  // pixels per CTA
-constexpr int GRAM_TILE = 32;    // pixels staged per synchronisation
+// 240 us for 16 images.)
+constexpr int GRAM_CHUNK = 256;  // pixels per CTA (two staged passes): 19 partial Grams per 68x68 image (128: no faster, twice the partials)
+constexpr int GRAM_TILE = 128;   // pixels staged per pass
+constexpr int GRAM_LD = 136;     // shared-memory row pitch in words: fragment loads (4 rows x 8 columns) hit 32 banks
 
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// D (16x8, fp32) += A (16x8, row) * B (8x8, col), TF32 inputs.  g = lane >> 2, t = lane & 3:
+//   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4) | b0 (k=t, n=g)  b1 (k=t+4, n=g) | c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// Both 64x64 Grams of a pixel chunk on the tensor cores (mma.sync TF32, fp32 accumulate; round 2a: 4x4 register tiles
+// of FFMAs, 47 us for 16 images).  G_k = F_k^T F_k is a [64 x npix] x [npix x 64] product whose two operands are the
+// SAME shared-memory tile F[pixel][channel]: the A fragment reads it transposed (m = channel, k = pixel), the B fragment
+// directly (k = pixel, n = channel); with a pitch of 136 words both are conflict-free.  The features are rounded to
+// TF32 once when staged (round-to-nearest: no bias; the Gram entries are sums over thousands of pixels).  The diagonal
+// term sum_p (f1_p . f2_p)^2 is taken from the unrounded values while staging.  Warp w: branch w>>2, channel rows
+// 16*(w&3).., all 8 column tiles: 32 accumulator registers.  Partial Grams are written per chunk (fixed-order reduce).
 __global__ void __launch_bounds__(256)
     decoder_gram_kernel(const float* __restrict__ fhat, float* __restrict__ part, float* __restrict__ dpart, int npix) {
-    __shared__ __align__(16) float sf[GRAM_TILE][128];
+    extern __shared__ __align__(16) uint32_t sF[];  // [GRAM_TILE][GRAM_LD] TF32 bit patterns
     __shared__ float sdiag[8];
     const int b = blockIdx.y, nchunks = gridDim.x;
     const int p0 = blockIdx.x * GRAM_CHUNK;
     const int p1 = min(npix, p0 + GRAM_CHUNK);
-    const int tr = (threadIdx.x >> 4) * 4, tc = (threadIdx.x & 15) * 4;  // this thread's 4x4 tile: rows tr.., cols tc..
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float g1[4][4], g2[4][4];
+    const int g = lane >> 2, t = lane & 3;
+    const int br = warp >> 2, m0 = br * 64 + (warp & 3) * 16;
+    float acc[8][4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) g1[i][j] = 0.f, g2[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float dacc = 0.f;
     for (int p = p0; p < p1; p += GRAM_TILE) {
         const int n = min(GRAM_TILE, p1 - p);
         __syncthreads();
         const float4* src = reinterpret_cast<const float4*>(fhat + ((size_t)b * npix + p) * 128);
-        for (int i = threadIdx.x; i < n * 32; i += 256) reinterpret_cast<float4*>(&sf[0][0])[i] = src[i];
-        __syncthreads();
-        for (int k = 0; k < n; ++k) {
-            const float4 a1 = *reinterpret_cast<const float4*>(&sf[k][tr]);
-            const float4 b1 = *reinterpret_cast<const float4*>(&sf[k][tc]);
-            const float4 a2 = *reinterpret_cast<const float4*>(&sf[k][64 + tr]);
-            const float4 b2 = *reinterpret_cast<const float4*>(&sf[k][64 + tc]);
-            const float av1[4] = {a1.x, a1.y, a1.z, a1.w}, bv1[4] = {b1.x, b1.y, b1.z, b1.w};
-            const float av2[4] = {a2.x, a2.y, a2.z, a2.w}, bv2[4] = {b2.x, b2.y, b2.z, b2.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    g1[i][j] = fmaf(av1[i], bv1[j], g1[i][j]);
-                    g2[i][j] = fmaf(av2[i], bv2[j], g2[i][j]);
-                }
-        }
-        for (int k = warp; k < n; k += 8) {  // per-pixel dot product f1 . f2
-            float d = sf[k][lane] * sf[k][64 + lane] + sf[k][lane + 32] * sf[k][96 + lane];
+        for (int k = warp; k < GRAM_TILE; k += 8) {  // warp = pixel row, lane = 4 channels (lanes 0-15: branch 1)
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < n) v = src[k * 32 + lane];
+            *reinterpret_cast<uint4*>(sF + k * GRAM_LD + 4 * lane) =
+                    make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+            const float ox = __shfl_xor_sync(0xffffffffu, v.x, 16), oy = __shfl_xor_sync(0xffffffffu, v.y, 16);
+            const float oz = __shfl_xor_sync(0xffffffffu, v.z, 16), ow = __shfl_xor_sync(0xffffffffu, v.w, 16);
+            float d = lane < 16 ? v.x * ox + v.y * oy + v.z * oz + v.w * ow : 0.f;
             d = warp_sum(d);
-            dacc += d * d;  // identical in every lane
+            dacc += d * d;  // identical in every lane; zero rows add nothing
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k0 = 0; k0 < GRAM_TILE; k0 += 8) {
+            const uint32_t* r0 = sF + (k0 + t) * GRAM_LD;
+            const uint32_t* r1 = sF + (k0 + t + 4) * GRAM_LD;
+            const uint32_t a[4] = {r0[m0 + g], r0[m0 + g + 8], r1[m0 + g], r1[m0 + g + 8]};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], a, r0[br * 64 + nt * 8 + g], r1[br * 64 + nt * 8 + g]);
         }
     }
-    float* gp = part + ((size_t)b * nchunks + blockIdx.x) * 8192;
+    float* gp = part + ((size_t)b * nchunks + blockIdx.x) * 8192 + br * 4096;
+    const int row = (warp & 3) * 16 + g;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        *reinterpret_cast<float4*>(gp + (tr + i) * 64 + tc) = make_float4(g1[i][0], g1[i][1], g1[i][2], g1[i][3]);
-        *reinterpret_cast<float4*>(gp + 4096 + (tr + i) * 64 + tc) = make_float4(g2[i][0], g2[i][1], g2[i][2], g2[i][3]);
+    for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<float2*>(gp + row * 64 + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+        *reinterpret_cast<float2*>(gp + (row + 8) * 64 + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
     }
     if (lane == 0) sdiag[warp] = dacc;
     __syncthreads();
     if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += sdiag[w];
-        dpart[(size_t)b * nchunks + blockIdx.x] = t;
+        float tt = 0.f;
+        for (int w = 0; w < 8; ++w) tt += sdiag[w];
+        dpart[(size_t)b * nchunks + blockIdx.x] = tt;
     }
 }
 
@@ -398,7 +419,14 @@ int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_
         dim3 g2(nchunks, B);
         {
             ProfScope ps(KC_DECODER, stream, (double)B * npix * 128 * 4);
-            decoder_gram_kernel<<<g2, 256, 0, stream>>>(fhat, part, dpart, npix);
+            constexpr int gram_smem = GRAM_TILE * GRAM_LD * 4;
+            static bool configured = false;
+            if (!configured) {
+                UCOD_CHECK_CUDA(cudaFuncSetAttribute(decoder_gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                     gram_smem));
+                configured = true;
+            }
+            decoder_gram_kernel<<<g2, 256, gram_smem, stream>>>(fhat, part, dpart, npix);
         }
         UCOD_CHECK_CUDA(cudaGetLastError());
         {
@@ -443,7 +471,27 @@ constexpr int BWD_IMG = 132;    // per-image head sums: gw [128] | gb [2] | bce 
 constexpr int BWD_MAXW = 128;   // largest grid side the backward supports
 constexpr int BWD_TAPS = 6;     // y-adjoint weights kept in shared memory (37 -> 68 needs at most 5)
 
-constexpr int BWD_WARPS = 8;  // a 68-pixel row = 23 three-pixel groups = 3 balanced passes; 128 registers, 2 CTAs per SM
+constexpr int BWD_WARPS = 8;
+constexpr int BWD_GLD = 72;    // pitch of the TF32 Gram rows (B fragments: 4 rows x 8 columns -> 32 banks)
+constexpr int BWD_FLD = 132;   // pitch of the TF32 feature rows (A fragments: 8 rows x 4 columns -> 32 banks)
+constexpr int BWD_OLD = 136;   // pitch of the O / P1 rows (fp32)
+// words of the region that first holds the two TF32 Grams and later the blended input rows + the reduction slots
+__host__ __device__ constexpr size_t bwd_region_a_words(int gin_w) {
+    const size_t g = 2 * 64 * BWD_GLD, r = (size_t)gin_w * 128 + BWD_WARPS * 32 * 5;
+    return g > r ? g : r;
+}
+__host__ __device__ constexpr size_t bwd_rows_smem_bytes(int gin_w, int out_w) {
+    return (bwd_region_a_words(gin_w) + (size_t)out_w * BWD_FLD + (size_t)out_w * BWD_OLD) * 4;
+}
+
+// CTA = one output row of one image.
+//   phase M: O[px, :] = fh_own[px, :] . G_other for the whole row on the tensor cores (mma.sync TF32, fp32 accumulate):
+//            10 (pixel tile, branch) units of 64 MMAs over 8 warps.  (Round 2b first cut: CUDA-core FFMAs with 3-pixel
+//            register tiles, ~290 of the ~700 instructions per pixel.)  O only enters the gradient through the small
+//            orthogonality term; TF32 (round-to-nearest when staged) changes it by ~1e-4 relative.
+//   phase E: one pixel per warp pass, lane = 4 channels: d from the y-blended input rows, sigmoid gates, BCE, P1 written
+//            over O in place.
+//   phase X: x-adjoint of the upsample from shared memory, partial sums to `part`.
 __global__ void __launch_bounds__(BWD_WARPS * 32, 2)
     decoder_bwd_rows_kernel(const float* __restrict__ d_in, const float* __restrict__ sumsq,
                             const float* __restrict__ emb, const float* __restrict__ w_fg,
@@ -454,28 +502,81 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2)
                             const float* __restrict__ dortho, float* __restrict__ t1, float* __restrict__ part, int B,
                             int gin_h, int gin_w, int out_h, int out_w) {
     extern __shared__ __align__(16) float dyn_smem[];
-    float* sG = dyn_smem;               // [2][64*64]
-    float* sP1 = dyn_smem + 2 * 4096;   // [out_w][128]
-    float* rowbuf = sP1 + (size_t)out_w * 128;  // [gin_w][128]: the two input rows of this output row, blended in y
-    constexpr int PT = 3;               // pixels per warp pass: one read of the Gram rows serves PT pixels
-    __shared__ __align__(16) float sf[BWD_WARPS][PT][128];
-    __shared__ float4 red4[BWD_WARPS][32];
-    __shared__ float red1[BWD_WARPS][32];
-    __shared__ int s_lo[DEC_MAXW], s_cnt[DEC_MAXW];  // per input column: first contributing output column, how many
-    __shared__ int s_x0[DEC_MAXW], s_x1[DEC_MAXW];   // per output column: its two taps
-    __shared__ float s_lx[DEC_MAXW];
+    uint32_t* sGt = reinterpret_cast<uint32_t*>(dyn_smem);              // [2][64][BWD_GLD] (phase M)
+    float* rowbuf = dyn_smem;                                            // [gin_w][128]     (phases E, X; aliases sGt)
+    float4* red4 = reinterpret_cast<float4*>(dyn_smem + (size_t)gin_w * 128);  // [BWD_WARPS][32]
+    float* red1 = reinterpret_cast<float*>(red4 + BWD_WARPS * 32);              // [BWD_WARPS][32]
+    uint32_t* sFt = reinterpret_cast<uint32_t*>(dyn_smem + bwd_region_a_words(gin_w));  // [out_w][BWD_FLD] (phase M)
+    float* sO = dyn_smem + bwd_region_a_words(gin_w) + (size_t)out_w * BWD_FLD;         // [out_w][BWD_OLD] O, then P1
+    __shared__ int s_lo[BWD_MAXW], s_cnt[BWD_MAXW];  // per input column: first contributing output column, how many
+    __shared__ int s_x0[BWD_MAXW], s_x1[BWD_MAXW];   // per output column: its two taps
+    __shared__ float s_lx[BWD_MAXW];
+    __shared__ float s_lg[2][BWD_MAXW], s_up[2][BWD_MAXW];  // this row's logits and targets / upstream gradients (fg, bg)
     const int b = blockIdx.y, oy = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int branch = lane >> 4, ch0 = lane * 4, col = ch0 & 63;
+    const int branch = lane >> 4;
     const int npix = out_h * out_w;
-    for (int i = threadIdx.x; i < 2 * 4096; i += BWD_WARPS * 32) sG[i] = gram[(size_t)b * 8192 + i];
+    const float* frow = fhat + ((size_t)b * npix + (size_t)oy * out_w) * 128;
+    for (int i = threadIdx.x; i < 2 * out_w; i += BWD_WARPS * 32) {  // per-pixel scalars: no global latency in phase E
+        const int br = i >= out_w, ox = i - br * out_w;
+        const size_t pix = (size_t)b * npix + (size_t)oy * out_w + ox;
+        s_lg[br][ox] = br == 0 ? fg[pix] : bg[pix];
+        if (dfg != nullptr)
+            s_up[br][ox] = br == 0 ? dfg[pix] : dbg[pix];
+        else
+            s_up[br][ox] = br == 0 ? target[pix] : 1.f - target[pix];
+    }
+    for (int i = threadIdx.x; i < 2 * 4096; i += BWD_WARPS * 32)
+        sGt[(i >> 6) * BWD_GLD + (i & 63)] = to_tf32(gram[(size_t)b * 8192 + i]);
+    for (int i = threadIdx.x; i < out_w * 32; i += BWD_WARPS * 32) {
+        const float4 v = reinterpret_cast<const float4*>(frow)[i];
+        *reinterpret_cast<uint4*>(sFt + (i >> 5) * BWD_FLD + 4 * (i & 31)) =
+                make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+    }
     for (int qx = threadIdx.x; qx < gin_w; qx += BWD_WARPS * 32) tap_range(qx, gin_w, out_w, s_lo[qx], s_cnt[qx]);
     for (int ox = threadIdx.x; ox < out_w; ox += BWD_WARPS * 32) bilinear_tap(ox, gin_w, out_w, s_x0[ox], s_x1[ox], s_lx[ox]);
+    __syncthreads();
+
+    // ---- phase M ----
+    {
+        const int g = lane >> 2, t = lane & 3;
+        const int m_tiles = (out_w + 15) / 16;
+        for (int u = warp; u < 2 * m_tiles; u += BWD_WARPS) {
+            const int mt = u % m_tiles, br = u / m_tiles;
+            const int ra = min(mt * 16 + g, out_w - 1), rb = min(mt * 16 + g + 8, out_w - 1);  // clamped tail rows
+            const uint32_t* fa = sFt + ra * BWD_FLD + br * 64;
+            const uint32_t* fb = sFt + rb * BWD_FLD + br * 64;
+            const uint32_t* G = sGt + (br ^ 1) * 64 * BWD_GLD;
+            float acc[8][4];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 2
+            for (int k0 = 0; k0 < 64; k0 += 8) {
+                const uint32_t a[4] = {fa[k0 + t], fb[k0 + t], fa[k0 + t + 4], fb[k0 + t + 4]};
+                const uint32_t* g0 = G + (k0 + t) * BWD_GLD + g;
+                const uint32_t* g1 = G + (k0 + t + 4) * BWD_GLD + g;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) mma_tf32_16x8x8(acc[nt], a, g0[nt * 8], g1[nt * 8]);
+            }
+            const int r0 = mt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                if (r0 < out_w)
+                    *reinterpret_cast<float2*>(sO + r0 * BWD_OLD + br * 64 + nt * 8 + 2 * t) = make_float2(acc[nt][0], acc[nt][1]);
+                if (r1 < out_w)
+                    *reinterpret_cast<float2*>(sO + r1 * BWD_OLD + br * 64 + nt * 8 + 2 * t) = make_float2(acc[nt][2], acc[nt][3]);
+            }
+        }
+    }
+    __syncthreads();  // the Grams are dead: their region now takes the blended input rows
+
     const float* d_img = d_in + (size_t)b * gin_h * gin_w * 128;
-    int y0, y1;
-    float ly;
-    bilinear_tap(oy, gin_h, out_h, y0, y1, ly);
     {   // same arithmetic as decoder_head_kernel, so d is reproduced bit for bit
+        int y0, y1;
+        float ly;
+        bilinear_tap(oy, gin_h, out_h, y0, y1, ly);
         const float hy = 1.f - ly;
         const float4* ra = reinterpret_cast<const float4*>(d_img + (size_t)y0 * gin_w * 128);
         const float4* rb = reinterpret_cast<const float4*>(d_img + (size_t)y1 * gin_w * 128);
@@ -485,7 +586,6 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2)
                     make_float4(hy * u.x + ly * v.x, hy * u.y + ly * v.y, hy * u.z + ly * v.z, hy * u.w + ly * v.w);
         }
     }
-    __syncthreads();
     const float4 ss = reinterpret_cast<const float4*>(sumsq + (size_t)b * 128)[lane];
     const float4 e = __ldg(reinterpret_cast<const float4*>(emb) + lane);
     const float4 wh = lane < 16 ? __ldg(reinterpret_cast<const float4*>(w_fg) + lane)
@@ -497,112 +597,81 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2)
     r.w = e.w / fmaxf(fabsf(e.w) * sqrtf(ss.w), 1e-12f);
     const float inv_n = 1.0f / ((float)B * (float)npix);
     const float oc = 2.0f / ((float)B * (float)npix * (float)npix) * (dortho != nullptr ? __ldg(dortho) : 1.f);
-    const float* Gother = sG + (branch ^ 1) * 4096;
     float4 gw = make_float4(0.f, 0.f, 0.f, 0.f), tacc = make_float4(0.f, 0.f, 0.f, 0.f);
     float gb = 0.f, lacc = 0.f;
+    __syncthreads();
 
-    for (int ox0 = warp * PT; ox0 < out_w; ox0 += BWD_WARPS * PT) {
-        float4 d[PT], f[PT], fo[PT], O[PT];
-        float sp[PT];
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < PT; ++t) {
-            const int ox = ox0 + t < out_w ? ox0 + t : out_w - 1;  // tail pixels are computed twice, stored once
-            {
-                const float lx = s_lx[ox], hx = 1.f - lx;
-                const float4 u = reinterpret_cast<const float4*>(rowbuf + (size_t)s_x0[ox] * 128)[lane];
-                const float4 v = reinterpret_cast<const float4*>(rowbuf + (size_t)s_x1[ox] * 128)[lane];
-                d[t] = make_float4(hx * u.x + lx * v.x, hx * u.y + lx * v.y, hx * u.z + lx * v.z, hx * u.w + lx * v.w);
-            }
-            f[t] = reinterpret_cast<const float4*>(fhat + ((size_t)b * npix + oy * out_w + ox) * 128)[lane];
-            reinterpret_cast<float4*>(sf[warp][t])[lane] = f[t];
-            O[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    // ---- phase E ----  (the features of the next pixel are requested before the current one is worked on)
+    float4 ff_next = warp < out_w ? reinterpret_cast<const float4*>(frow + (size_t)warp * 128)[lane]
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ox = warp; ox < out_w; ox += BWD_WARPS) {
+        const float4 ff = ff_next;
+        if (ox + BWD_WARPS < out_w) ff_next = reinterpret_cast<const float4*>(frow + (size_t)(ox + BWD_WARPS) * 128)[lane];
+        const float lx = s_lx[ox], hx = 1.f - lx;
+        const float4 u = reinterpret_cast<const float4*>(rowbuf + (size_t)s_x0[ox] * 128)[lane];
+        const float4 v = reinterpret_cast<const float4*>(rowbuf + (size_t)s_x1[ox] * 128)[lane];
+        const float4 dd = make_float4(hx * u.x + lx * v.x, hx * u.y + lx * v.y, hx * u.z + lx * v.z, hx * u.w + lx * v.w);
+        float4 fo;  // other branch, same column
+        fo.x = __shfl_xor_sync(0xffffffffu, ff.x, 16), fo.y = __shfl_xor_sync(0xffffffffu, ff.y, 16);
+        fo.z = __shfl_xor_sync(0xffffffffu, ff.z, 16), fo.w = __shfl_xor_sync(0xffffffffu, ff.w, 16);
+        const float sp = 0.5f * warp_sum(ff.x * fo.x + ff.y * fo.y + ff.z * fo.z + ff.w * fo.w);
+        float4* oslot = reinterpret_cast<float4*>(sO + (size_t)ox * BWD_OLD) + lane;
+        float4 Ot = *oslot;
+        Ot.x -= sp * fo.x, Ot.y -= sp * fo.y, Ot.z -= sp * fo.z, Ot.w -= sp * fo.w;
+        const float logit = s_lg[branch][ox];
+        float dlog;
+        if (dfg != nullptr) {  // upstream gradients given (autograd entry)
+            dlog = s_up[branch][ox];
+        } else {               // fused BCE-with-logits against the merged pseudo label
+            const float tt = s_up[branch][ox];
+            // one exponential serves the sigmoid and the softplus; evaluated by every lane (no divergent slow path)
+            const float en = __expf(-fabsf(logit)), inv1 = __fdividef(1.f, 1.f + en);
+            const float sig = logit >= 0.f ? inv1 : en * inv1;
+            dlog = (sig - tt) * inv_n;
+            const float term = fmaxf(logit, 0.f) - logit * tt + __logf(1.f + en);
+            if ((lane & 15) == 0) lacc += term;
         }
-        __syncwarp();
-#pragma unroll
-        for (int t = 0; t < PT; ++t) {
-            fo[t] = reinterpret_cast<const float4*>(sf[warp][t])[lane ^ 16];  // other branch, same column
-            sp[t] = 0.5f * warp_sum(f[t].x * fo[t].x + f[t].y * fo[t].y + f[t].z * fo[t].z + f[t].w * fo[t].w);
-        }
-        // O[t] = (fh_branch[t] . G_other): one pass over the 64 Gram rows for the PT pixels
-#pragma unroll 2
-        for (int c = 0; c < 64; c += 4) {
-            const float4 g0 = *reinterpret_cast<const float4*>(Gother + (c + 0) * 64 + col);
-            const float4 g1 = *reinterpret_cast<const float4*>(Gother + (c + 1) * 64 + col);
-            const float4 g2 = *reinterpret_cast<const float4*>(Gother + (c + 2) * 64 + col);
-            const float4 g3 = *reinterpret_cast<const float4*>(Gother + (c + 3) * 64 + col);
-#pragma unroll
-            for (int t = 0; t < PT; ++t) {
-                const float4 fc = *reinterpret_cast<const float4*>(sf[warp][t] + branch * 64 + c);  // half-warp broadcast
-                O[t].x += fc.x * g0.x, O[t].y += fc.x * g0.y, O[t].z += fc.x * g0.z, O[t].w += fc.x * g0.w;
-                O[t].x += fc.y * g1.x, O[t].y += fc.y * g1.y, O[t].z += fc.y * g1.z, O[t].w += fc.y * g1.w;
-                O[t].x += fc.z * g2.x, O[t].y += fc.z * g2.y, O[t].z += fc.z * g2.z, O[t].w += fc.z * g2.w;
-                O[t].x += fc.w * g3.x, O[t].y += fc.w * g3.y, O[t].z += fc.w * g3.z, O[t].w += fc.w * g3.w;
-            }
-        }
-#pragma unroll
-        for (int t = 0; t < PT; ++t) {
-            const int ox = ox0 + t;
-            if (ox >= out_w) break;  // warp-uniform
-            const int pix = oy * out_w + ox;
-            const float4 dd = d[t], ff = f[t];
-            float4 Ot = O[t];
-            Ot.x -= sp[t] * fo[t].x, Ot.y -= sp[t] * fo[t].y, Ot.z -= sp[t] * fo[t].z, Ot.w -= sp[t] * fo[t].w;
-            const float logit = branch == 0 ? fg[(size_t)b * npix + pix] : bg[(size_t)b * npix + pix];
-            float dlog;
-            if (dfg != nullptr) {  // upstream gradients given (autograd entry)
-                dlog = branch == 0 ? dfg[(size_t)b * npix + pix] : dbg[(size_t)b * npix + pix];
-            } else {               // fused BCE-with-logits against the merged pseudo label
-                const float t0 = target[(size_t)b * npix + pix];
-                const float tt = branch == 0 ? t0 : 1.f - t0;
-                // one exponential serves the sigmoid and the softplus; evaluated by every lane (no divergent slow path)
-                const float en = __expf(-fabsf(logit)), inv1 = __fdividef(1.f, 1.f + en);
-                const float sig = logit >= 0.f ? inv1 : en * inv1;
-                dlog = (sig - tt) * inv_n;
-                const float term = fmaxf(logit, 0.f) - logit * tt + __logf(1.f + en);
-                if ((lane & 15) == 0) lacc += term;
-            }
-            float4 sg, a, da, dfh, p1;
-            sg.x = __fdividef(1.f, 1.f + __expf(-ff.x * dd.x)), sg.y = __fdividef(1.f, 1.f + __expf(-ff.y * dd.y));
-            sg.z = __fdividef(1.f, 1.f + __expf(-ff.z * dd.z)), sg.w = __fdividef(1.f, 1.f + __expf(-ff.w * dd.w));
-            a.x = sg.x + dd.x, a.y = sg.y + dd.y, a.z = sg.z + dd.z, a.w = sg.w + dd.w;
-            da.x = dlog * wh.x, da.y = dlog * wh.y, da.z = dlog * wh.z, da.w = dlog * wh.w;
-            gw.x += dlog * a.x, gw.y += dlog * a.y, gw.z += dlog * a.z, gw.w += dlog * a.w;
-            if ((lane & 15) == 0) gb += dlog;
-            const float4 ds = make_float4(sg.x * (1.f - sg.x), sg.y * (1.f - sg.y), sg.z * (1.f - sg.z), sg.w * (1.f - sg.w));
-            dfh.x = da.x * ds.x * dd.x + oc * Ot.x, dfh.y = da.y * ds.y * dd.y + oc * Ot.y;
-            dfh.z = da.z * ds.z * dd.z + oc * Ot.z, dfh.w = da.w * ds.w * dd.w + oc * Ot.w;
-            tacc.x += dfh.x * ff.x, tacc.y += dfh.y * ff.y, tacc.z += dfh.z * ff.z, tacc.w += dfh.w * ff.w;
-            p1.x = da.x * (1.f + ds.x * ff.x) + r.x * dfh.x, p1.y = da.y * (1.f + ds.y * ff.y) + r.y * dfh.y;
-            p1.z = da.z * (1.f + ds.z * ff.z) + r.z * dfh.z, p1.w = da.w * (1.f + ds.w * ff.w) + r.w * dfh.w;
-            reinterpret_cast<float4*>(sP1 + (size_t)ox * 128)[lane] = p1;
-        }
+        float4 sg, a, da, dfh, p1;
+        sg.x = __fdividef(1.f, 1.f + __expf(-ff.x * dd.x)), sg.y = __fdividef(1.f, 1.f + __expf(-ff.y * dd.y));
+        sg.z = __fdividef(1.f, 1.f + __expf(-ff.z * dd.z)), sg.w = __fdividef(1.f, 1.f + __expf(-ff.w * dd.w));
+        a.x = sg.x + dd.x, a.y = sg.y + dd.y, a.z = sg.z + dd.z, a.w = sg.w + dd.w;
+        da.x = dlog * wh.x, da.y = dlog * wh.y, da.z = dlog * wh.z, da.w = dlog * wh.w;
+        gw.x += dlog * a.x, gw.y += dlog * a.y, gw.z += dlog * a.z, gw.w += dlog * a.w;
+        if ((lane & 15) == 0) gb += dlog;
+        const float4 ds = make_float4(sg.x * (1.f - sg.x), sg.y * (1.f - sg.y), sg.z * (1.f - sg.z), sg.w * (1.f - sg.w));
+        dfh.x = da.x * ds.x * dd.x + oc * Ot.x, dfh.y = da.y * ds.y * dd.y + oc * Ot.y;
+        dfh.z = da.z * ds.z * dd.z + oc * Ot.z, dfh.w = da.w * ds.w * dd.w + oc * Ot.w;
+        tacc.x += dfh.x * ff.x, tacc.y += dfh.y * ff.y, tacc.z += dfh.z * ff.z, tacc.w += dfh.w * ff.w;
+        p1.x = da.x * (1.f + ds.x * ff.x) + r.x * dfh.x, p1.y = da.y * (1.f + ds.y * ff.y) + r.y * dfh.y;
+        p1.z = da.z * (1.f + ds.z * ff.z) + r.z * dfh.z, p1.w = da.w * (1.f + ds.w * ff.w) + r.w * dfh.w;
+        *oslot = p1;  // P1 over O, same lane, same slot
     }
+    float* sP1 = sO;
     // fixed-order block reduction of the per-lane accumulators -> this row's slot of `part`
     float* prow = part + ((size_t)b * out_h + oy) * BWD_PART;
-    red4[warp][lane] = tacc;
-    red1[warp][lane] = (lane & 15) == 0 ? gb : 0.f;
+    red4[warp * 32 + lane] = tacc;
+    red1[warp * 32 + lane] = (lane & 15) == 0 ? gb : 0.f;
     __syncthreads();  // also publishes sP1
     if (warp == 0) {
-        float4 t = red4[0][lane];
-        float g1 = red1[0][lane];
+        float4 t = red4[lane];
+        float g1 = red1[lane];
         for (int w = 1; w < BWD_WARPS; ++w) {
-            t.x += red4[w][lane].x, t.y += red4[w][lane].y, t.z += red4[w][lane].z, t.w += red4[w][lane].w;
-            g1 += red1[w][lane];
+            t.x += red4[w * 32 + lane].x, t.y += red4[w * 32 + lane].y, t.z += red4[w * 32 + lane].z, t.w += red4[w * 32 + lane].w;
+            g1 += red1[w * 32 + lane];
         }
         reinterpret_cast<float4*>(prow)[lane] = t;
         if ((lane & 15) == 0) prow[256 + (lane >> 4)] = g1;
     }
     __syncthreads();
-    red4[warp][lane] = gw;
-    red1[warp][lane] = lacc;
+    red4[warp * 32 + lane] = gw;
+    red1[warp * 32 + lane] = lacc;
     __syncthreads();
     if (warp == 0) {
-        float4 t = red4[0][lane];
-        float l = red1[0][lane];
+        float4 t = red4[lane];
+        float l = red1[lane];
         for (int w = 1; w < BWD_WARPS; ++w) {
-            t.x += red4[w][lane].x, t.y += red4[w][lane].y, t.z += red4[w][lane].z, t.w += red4[w][lane].w;
-            l += red1[w][lane];
+            t.x += red4[w * 32 + lane].x, t.y += red4[w * 32 + lane].y, t.z += red4[w * 32 + lane].z, t.w += red4[w * 32 + lane].w;
+            l += red1[w * 32 + lane];
         }
         reinterpret_cast<float4*>(prow + 128)[lane] = t;
         if ((lane & 15) == 0) prow[258 + (lane >> 4)] = l;
@@ -616,7 +685,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32, 2)
         for (int k = 0; k < n; ++k) {
             const int ox = lo + k;
             const float w = (s_x0[ox] == qx ? 1.f - s_lx[ox] : 0.f) + (s_x1[ox] == qx ? s_lx[ox] : 0.f);
-            const float4 v = reinterpret_cast<const float4*>(sP1 + (size_t)ox * 128)[l4];
+            const float4 v = reinterpret_cast<const float4*>(sP1 + (size_t)ox * BWD_OLD)[l4];
             acc.x += w * v.x, acc.y += w * v.y, acc.z += w * v.z, acc.w += w * v.w;
         }
         reinterpret_cast<float4*>(trow + (size_t)qx * 128)[l4] = acc;
@@ -820,7 +889,7 @@ int decoder_backward(const void* keys_bf16, int B, int gin_h, int gin_w, int out
     if (int rc = wgrad_plan((int)rows, w.dim, wg_ws, ws_bytes - front, &plan)) return rc;
     // every buffer below is fully written by its producer: nothing to zero
     {
-        const size_t smem = (2 * 4096 + (size_t)out_w * 128 + (size_t)gin_w * 128) * sizeof(float);
+        const size_t smem = bwd_rows_smem_bytes(gin_w, out_w);
         static size_t configured = 0;
         if (smem > configured) {
             UCOD_CHECK_CUDA(cudaFuncSetAttribute(decoder_bwd_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

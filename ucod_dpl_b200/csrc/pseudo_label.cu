@@ -44,7 +44,7 @@ __device__ __forceinline__ float key_at<__nv_bfloat16>(const __nv_bfloat16* p, i
 // With both in one CTA per image the stream waits for the chain and runs at one CTA's memory parallelism (0.27-0.38
 // of HBM with bf16 keys).  MODE 1 runs the chain for all images at once (one small CTA per image) and leaves
 // refvec [B, C] / beta [B, 16] in the scratch; MODE 2 is a pure streaming kernel over (image, slab of PL_SLAB patches).
-constexpr int PL_SLAB = 32;
+constexpr int PL_SLAB = 64;
 template <typename TK, int MODE>
 __global__ void __launch_bounds__(PL_THREADS)
     pseudo_label_score_kernel(const float* __restrict__ attn, const TK* __restrict__ keys, float* __restrict__ cos_out,
@@ -137,10 +137,6 @@ __global__ void __launch_bounds__(PL_THREADS)
             if (threadIdx.x < PL_MAX_HEADS) betas[b * PL_MAX_HEADS + threadIdx.x] = threadIdx.x < nh ? s_beta[threadIdx.x] : 0.f;
             return;
         }
-    } else {
-        for (int i = threadIdx.x; i < C; i += blockDim.x) s_ref[i] = refvec[(size_t)b * C + i];
-        if (threadIdx.x < PL_MAX_HEADS) s_beta[threadIdx.x] = betas[b * PL_MAX_HEADS + threadIdx.x];
-        __syncthreads();
     }
     // ---- one warp per patch: cos(ref, p); 128-bit key loads (8 bf16 / 4 fp32 per lane and step).
     // Two patches per iteration with all their loads issued before the first reduction: with one patch in flight a
@@ -152,8 +148,7 @@ __global__ void __launch_bounds__(PL_THREADS)
     float wmax = -INFINITY;
     const int p_begin = MODE == 2 ? (int)blockIdx.y * PL_SLAB : 0;
     const int p_end = MODE == 2 ? min(P, p_begin + PL_SLAB) : P;
-    for (int p0 = p_begin + 2 * warp; p0 < p_end; p0 += 2 * nw) {
-        uint4 raw[2][VMAX];
+    auto load_pair = [&](int p0, uint4 (&raw)[2][VMAX]) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int p = p0 + u < p_end ? p0 + u : p0;
@@ -164,6 +159,8 @@ __global__ void __launch_bounds__(PL_THREADS)
                 raw[u][i] = v < nvec ? __ldg(kr + v) : make_uint4(0u, 0u, 0u, 0u);
             }
         }
+    };
+    auto finish_pair = [&](int p0, const uint4 (&raw)[2][VMAX]) {
         float dot[2] = {0.f, 0.f}, q[2] = {0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < VMAX; ++i) {
@@ -206,6 +203,25 @@ __global__ void __launch_bounds__(PL_THREADS)
             cos_out[(size_t)b * P + p0 + lane] = c;
             bkg_out[(size_t)b * P + p0 + lane] = c > th_bkg ? 1 : 0;
             wmax = fmaxf(wmax, 1.f - c);
+        }
+    };
+    if constexpr (MODE == 2) {
+        // the first pair's loads are in flight while the reference descriptor arrives from L2
+        int p0 = p_begin + 2 * warp;
+        uint4 raw[2][VMAX];
+        if (p0 < p_end) load_pair(p0, raw);
+        for (int i = threadIdx.x; i < C; i += blockDim.x) s_ref[i] = refvec[(size_t)b * C + i];
+        if (threadIdx.x < PL_MAX_HEADS) s_beta[threadIdx.x] = betas[b * PL_MAX_HEADS + threadIdx.x];
+        __syncthreads();
+        for (bool first = true; p0 < p_end; p0 += 2 * nw, first = false) {
+            if (!first) load_pair(p0, raw);
+            finish_pair(p0, raw);
+        }
+    } else {
+        for (int p0 = p_begin + 2 * warp; p0 < p_end; p0 += 2 * nw) {
+            uint4 raw[2][VMAX];
+            load_pair(p0, raw);
+            finish_pair(p0, raw);
         }
     }
     wmax = fmaxf(wmax, __shfl_xor_sync(0xffffffffu, wmax, 1));

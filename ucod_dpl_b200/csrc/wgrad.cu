@@ -137,14 +137,21 @@ __global__ void __launch_bounds__(WG_THREADS, 1)
 __global__ void __launch_bounds__(256)
     wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, float* __restrict__ dW, int n_elem,
                         const float* __restrict__ bpart, int n_blocks, float* __restrict__ db) {
-    const int i = (blockIdx.x * 256 + threadIdx.x) * 4;
+    // one element per thread (4x the CTAs of a float4 mapping: the sum over the splits is a serial chain per element,
+    // so the kernel is latency-bound and wants threads, not wide loads); 8 independent loads in flight per thread
+    const int i = blockIdx.x * 256 + threadIdx.x;
     if (i < n_elem) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < n_splits; ++k) {
-            const float4 v = *reinterpret_cast<const float4*>(partial + (size_t)k * n_elem + i);
-            s.x += v.x, s.y += v.y, s.z += v.z, s.w += v.w;
+        float s = 0.f;
+        int k = 0;
+        for (; k + 8 <= n_splits; k += 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = partial[(size_t)(k + u) * n_elem + i];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += v[u];
         }
-        *reinterpret_cast<float4*>(dW + i) = s;
+        for (; k < n_splits; ++k) s += partial[(size_t)k * n_elem + i];
+        dW[i] = s;
     }
     if (blockIdx.x == 0 && threadIdx.x < 128) {
         float s = 0.f;
@@ -208,7 +215,7 @@ int wgrad_contract(const WgradPlan& plan, const void* keys_bf16, int T, int dim,
     {
         const int n_elem = 128 * dim;
         ProfScope ps(KC_DECODER, stream, (double)plan.splits * n_elem * 4);
-        wgrad_reduce_kernel<<<ceil_div(n_elem / 4, 256), 256, 0, stream>>>(plan.partial, plan.splits, dW, n_elem,
+        wgrad_reduce_kernel<<<ceil_div(n_elem, 256), 256, 0, stream>>>(plan.partial, plan.splits, dW, n_elem,
                                                                            plan.bpart, plan.n_kblocks, db);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
