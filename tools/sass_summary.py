@@ -35,5 +35,7 @@ for chunk in re.split(r"\n\s+Function : ", out)[1:]:
         print(" " * 6 + ", ".join(f"{k} x{v}" for k, v in sorted(variants.items())))
     total.update(c)
 print(f"{'TOTAL (kernels listed)':72s} " + " ".join(f"{total[k]:8d}" for k in KEYS))
-print("# HMMA / HGMMA (mma.sync / wgmma) = 0 everywhere: no legacy tensor-core path; ldd shows libcudart only")
+print("# HGMMA (wgmma) = 0 everywhere.  HMMA (mma.sync, TF32) appears only in decoder_gram_kernel / decoder_bwd_rows_kernel: the "
+      "64x64 Gram products of the training step (1.2 GFLOP per 16 images, operands already in a CTA's shared memory); every "
+      "GEMM / attention / weight-gradient kernel is UTCHMMA (tcgen05) fed by UTMALDG (TMA).  ldd shows libcudart only")
 print(subprocess.run(["ldd", str(LIB)], capture_output=True, text=True).stdout)
