@@ -986,57 +986,101 @@ int features_to_tokens_bf16(const float* in, void* out, int B, int C, int P, lon
 // ------------------------------------------------------------------------------------------------
 #define UCOD_SIGMOID_HALF_THRESHOLD 0x1.8p-24f
 
+constexpr int UP_ROWS = 8;       // output rows per CTA
+constexpr int UP_MAXW = 16384;   // widest output the column-tap table in shared memory covers (12 bytes per column)
 template <int MODE>
-__global__ void upsample_bilinear_kernel(const float* __restrict__ in, void* __restrict__ out, int in_h, int in_w,
-                                         int out_h, int out_w) {
-    const int b = blockIdx.z, oy = blockIdx.y;
-    const int ox0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (ox0 >= out_w) return;
+__global__ void __launch_bounds__(256)
+    upsample_bilinear_kernel(const float* __restrict__ in, void* __restrict__ out, int in_h, int in_w, int out_h,
+                             int out_w) {
+    // CTA = UP_ROWS output rows of one image.  The column taps are computed once per CTA (a float division each) into
+    // shared memory; round 2a recomputed five taps per thread for four pixels and was issue-bound (90 % issue active,
+    // 0.3 TB/s).  One thread = 4 consecutive output pixels, packed store.
+    extern __shared__ __align__(16) uint8_t up_smem[];
+    int* s_x0 = reinterpret_cast<int*>(up_smem);
+    int* s_x1 = s_x0 + out_w;
+    float* s_lx = reinterpret_cast<float*>(s_x1 + out_w);
+    const int b = blockIdx.y;
+    for (int ox = threadIdx.x; ox < out_w; ox += blockDim.x) bilinear_tap(ox, in_w, out_w, s_x0[ox], s_x1[ox], s_lx[ox]);
+    __syncthreads();
     const float* src = in + (size_t)b * in_h * in_w;
-    int y0, y1;
-    float ly;
-    bilinear_tap(oy, in_h, out_h, y0, y1, ly);
-    float v[4];
+    const int oy_end = min(out_h, ((int)blockIdx.x + 1) * UP_ROWS);
+    for (int oy = blockIdx.x * UP_ROWS; oy < oy_end; ++oy) {
+        int y0, y1;
+        float ly;
+        bilinear_tap(oy, in_h, out_h, y0, y1, ly);
+        const float hy = 1.f - ly;
+        const float* r0 = src + y0 * in_w;
+        const float* r1 = src + y1 * in_w;
+        for (int ox0 = threadIdx.x * 4; ox0 < out_w; ox0 += blockDim.x * 4) {
+            float v[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int ox = ox0 + i;
-        int x0, x1;
-        float lx;
-        bilinear_tap(ox < out_w ? ox : out_w - 1, in_w, out_w, x0, x1, lx);
-        const float hx = 1.f - lx, hy = 1.f - ly;
-        float t00 = __ldg(src + y0 * in_w + x0), t01 = __ldg(src + y0 * in_w + x1);
-        float t10 = __ldg(src + y1 * in_w + x0), t11 = __ldg(src + y1 * in_w + x1);
-        if constexpr (MODE == 2) {  // probabilities first, then interpolate (loop_CORAL.py:331-338)
-            t00 = 1.f / (1.f + expf(-t00)), t01 = 1.f / (1.f + expf(-t01));
-            t10 = 1.f / (1.f + expf(-t10)), t11 = 1.f / (1.f + expf(-t11));
+            for (int i = 0; i < 4; ++i) {
+                const int ox = ox0 + i < out_w ? ox0 + i : out_w - 1;
+                const int x0 = s_x0[ox], x1 = s_x1[ox];
+                const float lx = s_lx[ox], hx = 1.f - lx;
+                float t00 = __ldg(r0 + x0), t01 = __ldg(r0 + x1), t10 = __ldg(r1 + x0), t11 = __ldg(r1 + x1);
+                if constexpr (MODE == 2) {  // probabilities first, then interpolate (loop_CORAL.py:331-338)
+                    t00 = 1.f / (1.f + expf(-t00)), t01 = 1.f / (1.f + expf(-t01));
+                    t10 = 1.f / (1.f + expf(-t10)), t11 = 1.f / (1.f + expf(-t11));
+                }
+                v[i] = hy * (hx * t00 + lx * t01) + ly * (hx * t10 + lx * t11);
+            }
+            const size_t o = ((size_t)b * out_h + oy) * out_w + ox0;
+            const int nv = min(4, out_w - ox0);
+            if constexpr (MODE == 0) {
+                float* dst = static_cast<float*>(out) + o;
+                if (nv == 4 && (o & 3) == 0) {
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                } else {
+                    for (int i = 0; i < nv; ++i) dst[i] = v[i];
+                }
+            } else {
+                uint8_t* dst = static_cast<uint8_t*>(out) + o;
+                uint8_t m[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) m[i] = (MODE == 1 ? v[i] > UCOD_SIGMOID_HALF_THRESHOLD : v[i] > 0.5f) ? 1 : 0;
+                if (nv == 4 && (o & 3) == 0) {
+                    *reinterpret_cast<uint32_t*>(dst) = (uint32_t)m[0] | ((uint32_t)m[1] << 8) | ((uint32_t)m[2] << 16) | ((uint32_t)m[3] << 24);
+                } else if (nv == 4 && (o & 1) == 0) {
+                    reinterpret_cast<uint16_t*>(dst)[0] = (uint16_t)(m[0] | (m[1] << 8));
+                    reinterpret_cast<uint16_t*>(dst)[1] = (uint16_t)(m[2] | (m[3] << 8));
+                } else {
+                    for (int i = 0; i < nv; ++i) dst[i] = m[i];
+                }
+            }
         }
-        v[i] = hy * (hx * t00 + lx * t01) + ly * (hx * t10 + lx * t11);
     }
-    const size_t o = ((size_t)b * out_h + oy) * out_w + ox0;
-    if constexpr (MODE == 0) {
-        float* dst = static_cast<float*>(out) + o;
-        for (int i = 0; i < 4 && ox0 + i < out_w; ++i) dst[i] = v[i];
-    } else {
-        uint8_t* dst = static_cast<uint8_t*>(out) + o;
-        for (int i = 0; i < 4 && ox0 + i < out_w; ++i)
-            dst[i] = (MODE == 1 ? v[i] > UCOD_SIGMOID_HALF_THRESHOLD : v[i] > 0.5f) ? 1 : 0;
+}
+
+template <int MODE>
+static int launch_upsample(const float* in, void* out, int B, int in_h, int in_w, int out_h, int out_w,
+                           cudaStream_t stream) {
+    const size_t smem = (size_t)out_w * 12;
+    static size_t configured = 48 * 1024;
+    if (smem > configured) {
+        UCOD_CHECK_CUDA(cudaFuncSetAttribute(upsample_bilinear_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem));
+        configured = smem;
     }
+    upsample_bilinear_kernel<MODE><<<dim3(ceil_div(out_h, UP_ROWS), B), 256, smem, stream>>>(in, out, in_h, in_w, out_h,
+                                                                                                 out_w);
+    return 0;
 }
 
 int upsample_bilinear(const float* in, void* out, int B, int in_h, int in_w, int out_h, int out_w, int binarize,
                       cudaStream_t stream) {
     UCOD_REQUIRE(in && out && B > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0, "upsample: bad argument");
-    dim3 block(128), grid(ceil_div(ceil_div(out_w, 4), 128), out_h, B);
+    UCOD_REQUIRE(out_w <= UP_MAXW, "upsample: outputs up to %d pixels wide", UP_MAXW);
     ProfScope ps(KC_RESAMPLE, stream, (double)B * in_h * in_w * 4 + (double)B * out_h * out_w * (binarize ? 1 : 4));
     UCOD_REQUIRE(binarize >= 0 && binarize <= 3, "upsample: binarize mode %d unknown", binarize);
     if (binarize == 1)
-        upsample_bilinear_kernel<1><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
+        launch_upsample<1>(in, out, B, in_h, in_w, out_h, out_w, stream);
     else if (binarize == 2)
-        upsample_bilinear_kernel<2><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
+        launch_upsample<2>(in, out, B, in_h, in_w, out_h, out_w, stream);
     else if (binarize == 3)
-        upsample_bilinear_kernel<3><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
+        launch_upsample<3>(in, out, B, in_h, in_w, out_h, out_w, stream);
     else
-        upsample_bilinear_kernel<0><<<grid, block, 0, stream>>>(in, out, in_h, in_w, out_h, out_w);
+        launch_upsample<0>(in, out, B, in_h, in_w, out_h, out_w, stream);
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -787,39 +787,62 @@ __global__ void paste_hpass_kernel(const float* __restrict__ logits, int g_h, in
 // ascending rank, so a job skips every pixel that a later job of the same image (entries job+1.. in `all_jobs`) covers;
 // all jobs can then run in one launch, in any order, across chunks.  rank >= 0 restores the round-1 behaviour (one
 // launch per rank, no look-ahead) for callers that pass unordered tables.
+constexpr int PV_ROWS = 16;
 __global__ void paste_vpass_kernel(const uint8_t* __restrict__ tmp, int g_h, const int* __restrict__ jobs,
                                    const int2* __restrict__ bounds, const int* __restrict__ coef,
                                    uint8_t* __restrict__ mask, int S_h, int S_w, int out_cap, int rank, int kmax,
                                    const int* __restrict__ njobs_dev, const int* __restrict__ all_jobs,
                                    int first_index, int n_all, const int* __restrict__ n_all_dev) {
+    // CTA = 128 columns x PV_ROWS rows of one job's rectangle: the grid is sized for the largest admissible box, so the
+    // finer one-row-per-CTA grid launched ~160 000 CTAs per chunk of which a few thousand had work (184 us per launch)
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int yy = blockIdx.y, job = blockIdx.z;
+    const int job = blockIdx.z;
     if (njobs_dev != nullptr && job >= __ldg(njobs_dev)) return;
     const int* jb = jobs + job * 6;
     if (rank >= 0 && jb[5] != rank) return;
     const int w = jb[3], h = jb[4];
-    if (w <= 0 || h <= 0 || xx >= w || yy >= h || xx >= out_cap || yy >= out_cap) return;
-    const int dx = jb[1] + xx, dy = jb[2] + yy;
-    if (dx < 0 || dx >= S_w || dy < 0 || dy >= S_h) return;  // Image.paste clips
-    if (all_jobs != nullptr) {
-        const int total = n_all_dev != nullptr ? min(n_all, __ldg(n_all_dev)) : n_all;
+    const int y_begin = blockIdx.y * PV_ROWS;
+    if (w <= 0 || h <= 0 || xx >= w || y_begin >= h || xx >= out_cap) return;
+    const int dx = jb[1] + xx;
+    if (dx < 0 || dx >= S_w) return;  // Image.paste clips
+    const int total = all_jobs == nullptr ? 0 : (n_all_dev != nullptr ? min(n_all, __ldg(n_all_dev)) : n_all);
+    const uint8_t* src = tmp + (size_t)job * g_h * out_cap + xx;
+    const int y_end = min(min(y_begin + PV_ROWS, h), out_cap);
+    for (int yy = y_begin; yy < y_end; ++yy) {
+        const int dy = jb[2] + yy;
+        if (dy < 0 || dy >= S_h) continue;
+        bool owned = false;
         for (int k = first_index + job + 1; k < total; ++k) {
             const int* o = all_jobs + (size_t)k * 6;
             if (o[0] != jb[0]) break;
             if (o[3] > 0 && o[4] > 0 && o[3] <= out_cap && o[4] <= out_cap && dx >= o[1] && dx < o[1] + o[3] &&
-                dy >= o[2] && dy < o[2] + o[4])
-                return;  // a later paste of this image owns the pixel
+                dy >= o[2] && dy < o[2] + o[4]) {
+                owned = true;  // a later paste of this image owns the pixel
+                break;
+            }
         }
+        if (owned) continue;
+        const size_t vb = ((size_t)job * 2 + 1) * out_cap + yy;
+        const int2 bd = bounds[vb];
+        const int* kk = coef + ((size_t)job * 2 + 1) * kmax * out_cap + yy;
+        int acc = 1 << (RS_PRECISION_BITS - 1);
+        for (int k = 0; k < bd.y; ++k) acc += (int)src[(size_t)(bd.x + k) * out_cap] * __ldg(kk + (size_t)k * out_cap);
+        mask[((size_t)jb[0] * S_h + dy) * S_w + dx] = clip8(acc);
     }
-    const size_t vb = ((size_t)job * 2 + 1) * out_cap + yy;
-    const int2 bd = bounds[vb];
-    const int* kk = coef + ((size_t)job * 2 + 1) * kmax * out_cap + yy;
-    const uint8_t* src = tmp + (size_t)job * g_h * out_cap + xx;
-    int acc = 1 << (RS_PRECISION_BITS - 1);
-    for (int k = 0; k < bd.y; ++k) acc += (int)src[(size_t)(bd.x + k) * out_cap] * __ldg(kk + (size_t)k * out_cap);
-    mask[((size_t)jb[0] * S_h + dy) * S_w + dx] = clip8(acc);
 }
 
+// out = in ? mul : 0, 16 bytes per thread where the pointers allow
+__global__ void mask_scale_vec_kernel(const uint4* __restrict__ in, uint4* __restrict__ out, size_t n16, int mul) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n16) return;
+    const uint4 v = in[i];
+    const uint32_t m = (uint32_t)mul * 0x01010101u;
+    auto sc = [&](uint32_t x) {  // per byte: non-zero -> mul
+        uint32_t nz = (x | (x >> 1) | (x >> 2) | (x >> 3) | (x >> 4) | (x >> 5) | (x >> 6) | (x >> 7)) & 0x01010101u;
+        return (nz * 0xffu) & m;
+    };
+    out[i] = make_uint4(sc(v.x), sc(v.y), sc(v.z), sc(v.w));
+}
 __global__ void mask_scale_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, size_t n, int mul) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = in[i] ? (uint8_t)mul : 0;
@@ -1087,7 +1110,7 @@ static int paste_core(const float* logits, int njobs, const int* njobs_dev, int 
         dim3 g(ceil_div(out_cap, 128), g_h, njobs);
         paste_hpass_kernel<<<g, 128, 0, stream>>>(logits, g_h, g_w, jobs, bounds, coef, tmp, out_cap, kmax, njobs_dev);
     }
-    dim3 g(ceil_div(out_cap, 128), out_cap, njobs);
+    dim3 g(ceil_div(out_cap, 128), ceil_div(out_cap, PV_ROWS), njobs);
     if (all_jobs != nullptr) {
         ProfScope ps(KC_RESAMPLE, stream, 0.0);
         paste_vpass_kernel<<<g, 128, 0, stream>>>(tmp, g_h, jobs, bounds, coef, mask, S_h, S_w, out_cap, -1, kmax,
@@ -1215,7 +1238,15 @@ int mask_scale_u8(const uint8_t* in, uint8_t* out, size_t n, int mul, cudaStream
     UCOD_REQUIRE(in && out, "mask_scale_u8: null argument");
     if (n == 0) return 0;
     ProfScope ps(KC_RESAMPLE, stream, (double)n * 2);
-    mask_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(in, out, n, mul);
+    size_t head = 0;
+    if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0 && n >= 16) {
+        const size_t n16 = n / 16;
+        mask_scale_vec_kernel<<<(unsigned)((n16 + 255) / 256), 256, 0, stream>>>(
+                reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(out), n16, mul);
+        head = n16 * 16;
+    }
+    if (head < n)
+        mask_scale_kernel<<<(unsigned)((n - head + 255) / 256), 256, 0, stream>>>(in + head, out + head, n - head, mul);
     UCOD_CHECK_CUDA(cudaGetLastError());
     return 0;
 }

@@ -69,6 +69,17 @@ __global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloa
         tile[px * Kpad + k] = __float2bfloat16_rn(0.f);
     }
     if constexpr (sizeof(TIn) == 1) {
+        // ToTensor + Normalize of a byte has 256 possible results per channel: a 3 x 256 bf16 table built once per CTA
+        // (same arithmetic as before, so the patches are bit-identical) replaces a float division, two FP ops and a
+        // conversion per pixel by one shared-memory read
+        __shared__ __nv_bfloat16 lut[3][256];
+        for (int t = threadIdx.x; t < 768; t += blockDim.x) {
+            const int c = t >> 8;
+            const float m = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
+            const float sd = c == 0 ? inv_std.x : (c == 1 ? inv_std.y : inv_std.z);
+            lut[c][t & 255] = __float2bfloat16_rn(((float)(t & 255) / 255.0f - m) * sd);
+        }
+        __syncthreads();
         // uint8 input: the p image rows of one channel are one contiguous span of p * Ww bytes; read it with 16-byte
         // loads from the aligned-down address (byte loads keep only 32 B per warp request in flight) and walk the
         // (row, x, patch, column) indices incrementally
@@ -78,8 +89,7 @@ __global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloa
             const int head = (int)(reinterpret_cast<uintptr_t>(span) & 15);
             const uint4* base = reinterpret_cast<const uint4*>(span - head);
             const int nvec = (head + nbytes + 15) >> 4;
-            const float m = c == 0 ? mean.x : (c == 1 ? mean.y : mean.z);
-            const float sd = c == 0 ? inv_std.x : (c == 1 ? inv_std.y : inv_std.z);
+            const __nv_bfloat16* lc = lut[c];
             __nv_bfloat16* tc = tile + c * p * p;
             for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
                 const uint4 w = __ldg(base + v);
@@ -93,10 +103,7 @@ __global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloa
 #pragma unroll
                 for (int k = 0; k < 16; ++k) {
                     if (k >= first && o + k < nbytes) {
-                        if (x < wused) {
-                            const float f = (float)((ww[k >> 2] >> (8 * (k & 3))) & 0xffu);
-                            tc[px * Kpad + i * p + j] = __float2bfloat16_rn((f / 255.0f - m) * sd);
-                        }
+                        if (x < wused) tc[px * Kpad + i * p + j] = lc[(ww[k >> 2] >> (8 * (k & 3))) & 0xffu];
                         ++x;
                         if (++j == p) j = 0, ++px;
                         if (x == Ww) x = 0, px = 0, j = 0, ++i;
