@@ -300,6 +300,9 @@ int ucod_decoder_bwd(const void* keys_bf16, int batch, int dim, int gin_h, int g
                      uint64_t fwd_workspace_bytes, float* g_w_dec, float* g_b_dec, float* g_w_fg,
                      float* g_b_fg, float* g_w_bg, float* g_b_bg, float* loss2, void* workspace,
                      uint64_t workspace_bytes, void* stream);
+/* Total of `_process_batch` (loop_UCOD_DPL.py:176-180): out = loss2[0] + loss2[1] + ortho - dis_loss, all device scalars;
+ * dis_loss may be NULL (finetune epochs). */
+int ucod_train_loss(const float* loss2, const float* ortho, const float* dis_loss, float* out, void* stream);
 /* torch.optim.AdamW step (decoupled weight decay, bias correction with step >= 1) on flat fp32 buffers, fused with
  * `update_ema_decoder` (loop_UCOD_DPL.py:186-191): ema = ema_alpha*ema + (1-ema_alpha)*param (ema may be NULL).
  * grads are multiplied by grad_scale first (1/world_size after the gradient all-reduce). */

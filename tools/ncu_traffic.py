@@ -10,12 +10,12 @@ from collections import defaultdict
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parents[1]
-CLASS = [("gemm", ("gemm_bf16_tcgen05", "gemm2_bf16_tcgen05", "wgrad_tcgen05")), ("attention", ("attention_fwd", "attention_rows")),
+CLASS = [("gemm", ("gemm_bf16_tcgen05", "gemm2_bf16_tcgen05")), ("attention", ("attention_fwd", "attention_rows")),
          ("layernorm", ("layernorm",)), ("embed", ("im2col", "cls_init", "cls_row")),
          ("decoder", ("decoder_",)), ("ccl", ("ccl_", "lt_boxes", "lt_build", "lt_init")),
          ("resample", ("upsample", "crop_", "paste_", "resample_", "fill_", "mask_scale", "to_tensor")),
          ("pseudo_label", ("pseudo_", "pl_", "refine_")), ("coral", ("entropy", "coral_", "window_")),
-         ("train", ("apm_", "discriminator", "disc_", "adamw", "ema_", "bce_"))]
+         ("train", ("apm_", "discriminator", "disc_", "adamw", "ema_", "bce_", "wgrad_"))]
 WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_tensor_subpipe_hmma.sum", "sm__cycles_elapsed.avg",

@@ -259,6 +259,9 @@ int ucod_decoder_bwd(const void* keys_bf16, int batch, int dim, int gin_h, int g
                             fwd_workspace, (size_t)fwd_workspace_bytes, g, loss2, workspace, (size_t)workspace_bytes,
                             reinterpret_cast<cudaStream_t>(stream));
 }
+int ucod_train_loss(const float* loss2, const float* ortho, const float* dis_loss, float* out, void* stream) {
+    return train_loss(loss2, ortho, dis_loss, out, reinterpret_cast<cudaStream_t>(stream));
+}
 int ucod_adamw_ema_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* ema, uint64_t n,
                         float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                         float ema_alpha, void* stream) {

@@ -912,6 +912,20 @@ int decoder_backward(const void* keys_bf16, int B, int gin_h, int gin_w, int out
     return wgrad_contract(plan, keys_bf16, (int)rows, w.dim, g.w_dec, g.b_dec, stream);
 }
 
+// loss = bce_fg + bce_bg + ortho - dis_loss (loop_UCOD_DPL.py:176-180; dis_loss == NULL in the finetune epochs)
+__global__ void train_loss_kernel(const float* __restrict__ loss2, const float* __restrict__ ortho,
+                                  const float* __restrict__ dis_loss, float* __restrict__ out) {
+    float v = (loss2[0] + loss2[1]) + ortho[0];
+    if (dis_loss != nullptr) v -= dis_loss[0];
+    out[0] = v;
+}
+int train_loss(const float* loss2, const float* ortho, const float* dis_loss, float* out, cudaStream_t stream) {
+    UCOD_REQUIRE(loss2 && ortho && out, "train_loss: null argument");
+    train_loss_kernel<<<1, 1, 0, stream>>>(loss2, ortho, dis_loss, out);
+    UCOD_CHECK_CUDA(cudaGetLastError());
+    return 0;
+}
+
 // Fused AdamW (torch semantics, decoupled weight decay) + EMA of the updated parameters
 // (engine/runner/runner.py:282-285, loop_UCOD_DPL.py:186-191) over flat fp32 buffers.
 __global__ void adamw_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,

@@ -29,6 +29,7 @@ int decoder_backward(const void* keys_bf16, int B, int gin_h, int gin_w, int out
                      const float* fg, const float* bg, const float* target, const float* dfg, const float* dbg,
                      const float* dortho, void* fwd_workspace, size_t fwd_ws_bytes, const DecoderGrads& g, float* loss2,
                      void* workspace, size_t ws_bytes, cudaStream_t stream);
+int train_loss(const float* loss2, const float* ortho, const float* dis_loss, float* out, cudaStream_t stream);
 int adamw_ema_step(float* p, const float* g, float* m, float* v, float* ema, size_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int step_t, float grad_scale, float ema_alpha,
                    cudaStream_t stream);

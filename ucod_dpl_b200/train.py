@@ -185,10 +185,11 @@ class FirstStageTrainer:
         merged, dis_loss = merge_pseudo_label(self.discriminator, pl, teacher, fg, None, cur_epoch=self.cur_epoch,
                                               max_epoch=self.max_epoch, start_finetune=self.start_finetune)
         loss2 = _backward(dec, key_tokens_bf16, grid_in, fs, fg, bg, ws, self.grads, target=merged)
-        self.views["learnable_embedding"].zero_()
-        loss = loss2.sum() + ortho
-        if not self.finetune:
-            loss = loss - dis_loss
+        # (the gradient slot of learnable_embedding is never written: it stays at the zeros it was created with)
+        loss = torch.empty((), device=loss2.device)
+        with torch.cuda.device(loss2.device):  # loss = bce_fg + bce_bg + ortho [- dis_loss], one launch
+            _lib.call("ucod_train_loss", ptr(loss2), ptr(ortho), ptr(None if self.finetune else dis_loss), ptr(loss),
+                      stream_ptr(loss2.device))
         return loss, {"merged": merged, "dis_loss": dis_loss, "ortho": ortho, "bce": loss2}
 
     @torch.no_grad()
@@ -233,12 +234,21 @@ class FirstStageTrainer:
             with torch.cuda.graph(g):
                 self._s_loss, self._s_last = self._forward_backward(self._s_tok, grid_in, self._s_pl)
             self._graph = g
-        self._s_tok.copy_(key_tokens_bf16)
-        self._s_pl.copy_(pseudo_labels)
+        # a caller that assembles its batch directly in the graph's input buffers (`graph_inputs()`; e.g.
+        # `torch.index_select(store, 0, idx, out=tok_buf)` from an HBM-resident training set) skips these copies
+        if key_tokens_bf16.data_ptr() != self._s_tok.data_ptr():
+            self._s_tok.copy_(key_tokens_bf16)
+        if pseudo_labels.data_ptr() != self._s_pl.data_ptr():
+            self._s_pl.copy_(pseudo_labels)
         self._graph.replay()
         self.last = self._s_last
         self._optimizer_step()
         return self._s_loss
+
+
+    def graph_inputs(self):
+        """(key-token buffer, pseudo-label buffer) the captured graph reads, or None before the capture."""
+        return None if self._graph is None else (self._s_tok, self._s_pl)
 
 
 class _DiscPtrs(ctypes.Structure):
