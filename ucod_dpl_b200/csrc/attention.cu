@@ -57,7 +57,10 @@ struct AttCfg {
     static constexpr int SK_BYTES = NKB * BLK_BYTES;
     static constexpr int SV_BYTES = NKB * BLK_BYTES;
     static constexpr int STAGES = 2;
-    static constexpr int SMEM = SQ_BYTES + STAGES * (SK_BYTES + SV_BYTES) + 256 + 1024;
+#ifndef UCOD_ATT_SMEM_PAD
+#define UCOD_ATT_SMEM_PAD 0  // experiment knob: extra dynamic shared memory per CTA (120000 forces one CTA per SM)
+#endif
+    static constexpr int SMEM = SQ_BYTES + STAGES * (SK_BYTES + SV_BYTES) + 256 + 1024 + UCOD_ATT_SMEM_PAD;
     static constexpr int TM_S = 0, TM_P = 128, TM_O = 192;
     static constexpr int TMEM_COLS = (D == 64) ? 256 : 512;
     static constexpr int THREADS = 256;
@@ -204,7 +207,7 @@ __global__ void __launch_bounds__(256, AttCfg<D>::CTAS_PER_SM)
     const int col0 = h * D;
     const int n_tiles = (Tk + C::BN - 1) / C::BN;
 #ifdef UCOD_ATT_TIMELINE
-    const bool tl_on = (blockIdx.x == 5 && blockIdx.y == 300) && (lane == 0);
+    const bool tl_on = (blockIdx.x == (gridDim.x > 5 ? 5u : gridDim.x - 1) && blockIdx.y == 300) && (lane == 0);
     const long long tl_t0 = clock64();
 #endif
 
