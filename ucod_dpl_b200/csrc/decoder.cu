@@ -77,7 +77,7 @@ constexpr int DEC_MAXW = 256;  // largest supported grid side (input or output)
 //   sum_p (U d)_p^2 = d^T (U^T U) d,  U^T U = (Uy^T Uy) x (Ux^T Ux), each factor tridiagonal
 // i.e. a 3x3 stencil per input pixel instead of a 4-tap gather per output pixel (3.4x fewer pixels at 37 -> 68), and
 // the per-row partial sums are written, not accumulated: a fixed summation order, no memset.
-// Stage 1: one CTA per (input row, image); stage 2 adds the rows in order.
+// One CTA per (input row, image); the head kernel adds the rows in order.
 __global__ void __launch_bounds__(256)
     decoder_sumsq_rows_kernel(const float* __restrict__ d_in, float* __restrict__ part, int gin_h, int gin_w, int out_h,
                               int out_w, const int* __restrict__ batch_dev) {
@@ -132,15 +132,6 @@ __global__ void __launch_bounds__(256)
         part[((size_t)b * gin_h + qy) * 128 + c] = t;
     }
 }
-__global__ void __launch_bounds__(128)
-    decoder_sumsq_reduce_kernel(const float* __restrict__ part, float* __restrict__ sumsq, int gin_h,
-                                const int* __restrict__ batch_dev) {
-    const int b = blockIdx.x, c = threadIdx.x;
-    if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
-    float s = 0.f;
-    for (int qy = 0; qy < gin_h; ++qy) s += part[((size_t)b * gin_h + qy) * 128 + c];
-    sumsq[(size_t)b * 128 + c] = s;
-}
 
 // gate + heads (+ the normalised features for the orthogonality loss / backward).  CTA = one output row of one image:
 // the two input rows it interpolates between are blended in y ONCE per input column into shared memory (gin_w x 128
@@ -150,10 +141,12 @@ __global__ void __launch_bounds__(256)
                         const float* __restrict__ w_fg, const float* __restrict__ b_fg, const float* __restrict__ w_bg,
                         const float* __restrict__ b_bg, float* __restrict__ fg, float* __restrict__ bg,
                         float* __restrict__ fhat_out, int gin_h, int gin_w, int out_h, int out_w,
-                        const int* __restrict__ batch_dev) {
+                        const int* __restrict__ batch_dev, const float* __restrict__ sq_part,
+                        float* __restrict__ sumsq_out) {
     extern __shared__ __align__(16) float rowbuf[];  // [gin_w][128]
     __shared__ int s_x0[DEC_MAXW], s_x1[DEC_MAXW];
     __shared__ float s_lx[DEC_MAXW];
+    __shared__ __align__(16) float s_ss[128];
     const int b = blockIdx.y, oy = blockIdx.x;
     if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -173,8 +166,31 @@ __global__ void __launch_bounds__(256)
         }
     }
     for (int ox = threadIdx.x; ox < out_w; ox += 256) bilinear_tap(ox, gin_w, out_w, s_x0[ox], s_x1[ox], s_lx[ox]);
+    if (sq_part != nullptr) {
+        // sum of squares = the input-row partials added in row order.  Every CTA of the image forms the same sum (a
+        // separate B-CTA reduction launch cost more than these 37 L2 reads per thread); row 0's CTA publishes it for
+        // the backward
+        if (threadIdx.x < 128) {
+            float t = 0.f;
+            const float* sp = sq_part + (size_t)b * gin_h * 128 + threadIdx.x;
+            int qy = 0;
+            for (; qy + 8 <= gin_h; qy += 8) {  // 8 loads in flight, added in row order
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = sp[(size_t)(qy + u) * 128];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) t += v[u];
+            }
+            for (; qy < gin_h; ++qy) t += sp[(size_t)qy * 128];
+            s_ss[threadIdx.x] = t;
+            if (oy == 0) sumsq_out[(size_t)b * 128 + threadIdx.x] = t;
+        }
+    } else if (threadIdx.x < 128) {
+        s_ss[threadIdx.x] = sumsq[(size_t)b * 128 + threadIdx.x];
+    }
+    __syncthreads();
     // per-channel constants for this lane's 4 channels
-    const float4 ss = reinterpret_cast<const float4*>(sumsq + (size_t)b * 128)[lane];
+    const float4 ss = reinterpret_cast<const float4*>(s_ss)[lane];
     const float4 e = __ldg(reinterpret_cast<const float4*>(emb) + lane);  // emb[2,64] flat == channel order
     const float4 wh = lane < 16 ? __ldg(reinterpret_cast<const float4*>(w_fg) + lane)
                                 : __ldg(reinterpret_cast<const float4*>(w_bg) + (lane - 16));
@@ -394,8 +410,8 @@ int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_
         float* sq_part = reinterpret_cast<float*>(base + (need - 4096 - (size_t)B * gin_h * 128 * 4));
         ProfScope ps(KC_DECODER, stream, batch_dev ? 0.0 : d_bytes);
         decoder_sumsq_rows_kernel<<<dim3(gin_h, B), 256, 0, stream>>>(d_in, sq_part, gin_h, gin_w, out_h, out_w, batch_dev);
-        decoder_sumsq_reduce_kernel<<<B, 128, 0, stream>>>(sq_part, sumsq, gin_h, batch_dev);
     }
+    const float* sq_part = reinterpret_cast<const float*>(base + (need - 4096 - (size_t)B * gin_h * 128 * 4));
     UCOD_CHECK_CUDA(cudaGetLastError());
     {
         const size_t row_smem = (size_t)gin_w * 128 * sizeof(float);
@@ -408,7 +424,7 @@ int decoder_forward(const void* keys_bf16, int B, int gin_h, int gin_w, int out_
         ProfScope ps(KC_DECODER, stream, batch_dev ? 0.0 : d_bytes + (double)B * npix * 8);
         decoder_head_kernel<<<dim3(out_h, B), 256, row_smem, stream>>>(d_in, sumsq, w.emb, w.w_fg, w.b_fg, w.w_bg, w.b_bg,
                                                                        fg, bg, fhat, gin_h, gin_w, out_h, out_w,
-                                                                       batch_dev);
+                                                                       batch_dev, sq_part, sumsq);
     }
     UCOD_CHECK_CUDA(cudaGetLastError());
     if (ortho) {
@@ -700,7 +716,15 @@ __global__ void __launch_bounds__(288)
     if (t >= BWD_PART) return;
     const float* p = part + (size_t)b * out_h * BWD_PART + t;
     float s = 0.f;
-    for (int oy = 0; oy < out_h; ++oy) s += p[(size_t)oy * BWD_PART];
+    int oy = 0;
+    for (; oy + 8 <= out_h; oy += 8) {  // 8 loads in flight, added in row order
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(oy + u) * BWD_PART];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; oy < out_h; ++oy) s += p[(size_t)oy * BWD_PART];
     if (t < 128)
         tsum[(size_t)b * 128 + t] = s;
     else

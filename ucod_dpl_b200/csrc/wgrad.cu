@@ -153,10 +153,25 @@ __global__ void __launch_bounds__(256)
         for (; k < n_splits; ++k) s += partial[(size_t)k * n_elem + i];
         dW[i] = s;
     }
-    if (blockIdx.x == 0 && threadIdx.x < 128) {
+    // db: the column sums of the 64-row blocks.  One CTA, two threads per channel, 32 independent loads in flight per
+    // thread (a plain serial loop over the ~340 blocks was a 20 us dependent-latency chain and set the kernel's time);
+    // fixed order: even blocks, odd blocks, then even + odd
+    if (blockIdx.x == 0) {
+        __shared__ float s_half[128];
+        const int c = threadIdx.x & 127, half = threadIdx.x >> 7;
         float s = 0.f;
-        for (int k = 0; k < n_blocks; ++k) s += bpart[(size_t)k * 128 + threadIdx.x];
-        db[threadIdx.x] = s;
+        int k = half;
+        for (; k + 62 < n_blocks; k += 64) {
+            float v[32];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) v[u] = bpart[(size_t)(k + 2 * u) * 128 + c];
+#pragma unroll
+            for (int u = 0; u < 32; ++u) s += v[u];
+        }
+        for (; k < n_blocks; k += 2) s += bpart[(size_t)k * 128 + c];
+        if (half == 1) s_half[c] = s;
+        __syncthreads();
+        if (half == 0) db[c] = s + s_half[c];
     }
 }
 
