@@ -5,7 +5,7 @@ numpy restatement of `cv2.connectedComponents[WithStats](img, connectivity=8)` a
 4.13.0 installed here).  OpenCV's default 8-connectivity labeller (block-based "Spaghetti"/BBDT scan over 2x2
 pixel blocks, then label flattening) numbers components in the order in which their first 2x2 block is met in
 a raster scan over BLOCKS — i.e. by min over the component's pixels of (y//2)*ceil(W/2) + x//2 — not by first
-pixel in pixel-raster order.  Parity pin: tests/test_oracle_cc.py compares against cv2 itself on random and
+pixel in pixel-raster order.  Parity pin: tests/test_oracle_golden.py::test_connected_components_match_cv2 compares against cv2 itself on random and
 hand-built masks (cv2 is part of the image), and tests/golden/cc_*.npz stores cv2 outputs generated here.
 """
 from __future__ import annotations

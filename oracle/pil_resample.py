@@ -9,7 +9,7 @@ dependency of the reference, 12.2.0 installed here), as reached from
 
 Algorithm: per axis, coefficients in float64 (`precompute_coeffs`), converted to 22-bit fixed point
 (`normalize_coeffs_8bpc`), horizontal pass then vertical pass, each pass rounding to uint8
-(`clip8((1<<21) + sum(px*k)) >> 22`).  Pinned against PIL itself in tests/test_oracle_pil.py.
+(`clip8((1<<21) + sum(px*k)) >> 22`).  Pinned against PIL itself in tests/test_oracle_golden.py (test_pil_*_bit_exact).
 """
 from __future__ import annotations
 

@@ -13,7 +13,7 @@ the key-hook glue around it:
 
 Weights use the HF state_dict key names so real checkpoints load unchanged.  Parity pin: `tools/make_golden.py`
 loads `random_vit_state_dict` into the installed HF `Dinov2Model` / `ViTModel` and stores output slices in
-`tests/golden/vit_*.npz`; `tests/test_oracle_vit.py` checks this restatement against them.
+`tests/golden/vit_*.npz`; `tests/test_oracle_golden.py::test_vit_matches_hf` checks this restatement against them.
 """
 from __future__ import annotations
 

@@ -165,6 +165,18 @@ def test_process_preds_boxes(g_lt, S, th):
     assert {"none", "default", "boxes"} <= kinds
 
 
+def test_sigmoid_half_threshold_is_pinned():
+    """The CUDA binarisation compares the interpolated logit with 1.5 * 2^-24 instead of evaluating
+    `sigmoid(x) > 0.5` (csrc/decoder.cu UCOD_SIGMOID_HALF_THRESHOLD, loop_UCOD_DPL.py:356-361): in fp32 the two
+    predicates are the same function of x (torch CPU, dense scan around the threshold and over the normal range)."""
+    thr = float(np.float32(1.5 * 2.0 ** -24))
+    around = torch.linspace(-4 * 2.0 ** -24, 4 * 2.0 ** -24, 400001, dtype=torch.float64).float().unique()
+    wide = torch.cat([torch.linspace(-30, 30, 200001), torch.tensor([thr, float(np.nextafter(np.float32(thr), np.float32(1))),
+                                                                    float(np.nextafter(np.float32(thr), np.float32(0)))])])
+    for x in (around, wide):
+        assert torch.equal(torch.sigmoid(x) > 0.5, x > thr)
+
+
 def test_resize_bbox():
     meta = json.loads((GOLD / "looktwice_meta.json").read_text())["resize_bbox"]
     for box, want, (W0, H0) in meta:

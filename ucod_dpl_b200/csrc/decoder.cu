@@ -1019,7 +1019,7 @@ int features_to_tokens_bf16(const float* in, void* out, int B, int C, int P, lon
 // ------------------------------------------------------------------------------------------------
 // Bilinear upsample of [B,in_h,in_w] fp32 (align_corners=False).  MODE 0: write fp32 ; MODE 1: write the
 // binarised u8 mask `sigmoid(x) > 0.5` of loop_UCOD_DPL.py:356-361 without materialising the fp32 map
-// (fp32 sigmoid(x) > 0.5  <=>  x > 1.5 * 2^-24, probed on torch CPU; pinned in tests/test_oracle_looktwice.py).
+// (fp32 sigmoid(x) > 0.5  <=>  x > 1.5 * 2^-24, probed on torch CPU; pinned in tests/test_oracle_golden.py::test_sigmoid_half_threshold_is_pinned).
 // One thread = 4 consecutive output pixels (32-bit store of 4 mask bytes / float4 store).
 // ------------------------------------------------------------------------------------------------
 #define UCOD_SIGMOID_HALF_THRESHOLD 0x1.8p-24f

@@ -5,7 +5,7 @@ API-compatible with the part of the reference's `engine.config.CfgNode` (engine/
 `CfgNode.load_with_base(path)` with recursive `_BASE_` lists resolved relative to the including file,
 python-source configs exporting `cfg = dict(...)`, YAML configs, `dump()`, `get()`, `clone()`,
 `merge_from_file/merge_from_other_cfg/merge_from_list`, `freeze()/defrost()`.
-The reference's own config files load unchanged (tests/test_config_registry.py).
+The reference's own config files load unchanged (tests/test_host_api.py::test_configs_resolve_like_the_reference).
 """
 from __future__ import annotations
 
