@@ -1,5 +1,8 @@
-import sys, torch
-sys.path.insert(0, "/root/repo")
+"""Attention at the pseudo-label shape (256 images, T = 257): target for ncu launch lists."""
+import sys
+from pathlib import Path
+import torch
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 from ucod_dpl_b200 import _lib
 B, H, D, T = 256, 12, 64, 257
 qkv = torch.randn(B, T, 3 * H * D, device="cuda").to(torch.bfloat16)
