@@ -703,7 +703,8 @@ __global__ void __launch_bounds__(256)
                              const int* __restrict__ jobs /*[n,5] img,x,y,w,h*/, const int2* __restrict__ bounds,
                              const int* __restrict__ coef, uint8_t* __restrict__ out, int out_cap, int out_w, int out_h,
                              int kmax, const int* __restrict__ njobs_dev) {
-    extern __shared__ uint8_t cr_rows[];  // [CR_ROWS][out_w]
+    extern __shared__ __align__(16) uint8_t cr_rows[];  // [CR_ROWS][pitch]
+    const int pitch = (out_w + 3) & ~3;
     const int job = blockIdx.z;
     if (njobs_dev != nullptr && job >= __ldg(njobs_dev)) return;
     const int c = blockIdx.y;
@@ -728,33 +729,75 @@ __global__ void __launch_bounds__(256)
         const int hi = bounds[vb + yb - 1].x + bounds[vb + yb - 1].y;   // crop rows [lo, hi)
         const int span = min(hi - lo, CR_ROWS);  // (one output row never needs more than kmax <= CR_ROWS rows: checked by the host)
         __syncthreads();
-        // horizontal pass of the staged rows
-        for (int i = threadIdx.x; i < span * out_w; i += blockDim.x) {
-            const int r = i / out_w, xx = i - r * out_w;
-            const int sy = jb[2] + lo + r;
-            int acc = 1 << (RS_PRECISION_BITS - 1);
-            if (sy >= 0 && sy < H0) {
-                const int2 bd = bounds[hb + xx];
-                const uint8_t* row = plane + (size_t)sy * row_stride;
-                const int* kk = kh + xx;
-                for (int k = 0; k < bd.y; ++k) {
-                    const int sx = jb[1] + bd.x + k;
-                    const int px = (sx >= 0 && sx < W0) ? row[(size_t)sx * px_stride] : 0;
-                    acc += px * __ldg(kk + (size_t)k * out_cap);
+        // horizontal pass of the staged rows; (row, column) walked incrementally: no integer division per pixel, 32-bit
+        // offsets inside the image plane (64-bit index arithmetic tripled the instruction count of the tap loop)
+        {
+            const int rs = (int)row_stride, ps = (int)px_stride;
+            int r = 0, xx = threadIdx.x;
+            while (xx >= out_w) xx -= out_w, ++r;
+            while (r < span) {
+                const int sy = jb[2] + lo + r;
+                int acc = 1 << (RS_PRECISION_BITS - 1);
+                if (sy >= 0 && sy < H0) {
+                    const int2 bd = bounds[hb + xx];
+                    const int* kk = kh + xx;
+                    const int sx0 = jb[1] + bd.x;
+                    if (sx0 >= 0 && sx0 + bd.y <= W0) {  // all taps inside the image: no per-tap test
+                        const uint8_t* px = plane + (sy * rs + sx0 * ps);
+                        int ko = 0, po = 0;
+                        for (int k = 0; k < bd.y; ++k, ko += out_cap, po += ps) acc += (int)px[po] * __ldg(kk + ko);
+                    } else {
+                        const uint8_t* row = plane + sy * rs;
+                        int ko = 0;
+                        for (int k = 0; k < bd.y; ++k, ko += out_cap) {
+                            const int sx = sx0 + k;
+                            const int px = (sx >= 0 && sx < W0) ? row[sx * ps] : 0;
+                            acc += px * __ldg(kk + ko);
+                        }
+                    }
                 }
+                cr_rows[r * pitch + xx] = clip8(acc);
+                xx += blockDim.x;
+                while (xx >= out_w) xx -= out_w, ++r;
             }
-            cr_rows[i] = clip8(acc);
         }
         __syncthreads();
-        // vertical pass
-        for (int i = threadIdx.x; i < (yb - ya) * out_w; i += blockDim.x) {
-            const int yy = ya + i / out_w, xx = i % out_w;
-            const int2 bd = bounds[vb + yy];
-            const int* kk = kv + yy;
-            int acc = 1 << (RS_PRECISION_BITS - 1);
-            for (int k = 0; k < bd.y; ++k)
-                acc += (int)cr_rows[(bd.x - lo + k) * out_w + xx] * __ldg(kk + (size_t)k * out_cap);
-            dst[(size_t)yy * out_w + xx] = clip8(acc);
+        // vertical pass: one thread = 4 consecutive pixels of one output row (32-bit shared-memory reads of the staged
+        // rows, whose pitch is a multiple of 4; the row's taps are the same for the whole row)
+        {
+            const int groups = (out_w + 3) >> 2;
+            int yy = ya, g = threadIdx.x;
+            while (g >= groups) g -= groups, ++yy;
+            while (yy < yb) {
+                const int2 bd = bounds[vb + yy];
+                const int* kk = kv + yy;
+                const uint8_t* col = cr_rows + (bd.x - lo) * pitch + 4 * g;
+                const int half = 1 << (RS_PRECISION_BITS - 1);
+                int a0 = half, a1 = half, a2 = half, a3 = half;
+                int ko = 0, co = 0;
+                for (int k = 0; k < bd.y; ++k, ko += out_cap, co += pitch) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(col + co);
+                    const int cf = __ldg(kk + ko);
+                    a0 += (int)(w & 0xffu) * cf, a1 += (int)((w >> 8) & 0xffu) * cf;
+                    a2 += (int)((w >> 16) & 0xffu) * cf, a3 += (int)(w >> 24) * cf;
+                }
+                uint8_t* d = dst + (yy * out_w + 4 * g);
+                const int nv = min(4, out_w - 4 * g);
+                const uint8_t v0 = clip8(a0), v1 = clip8(a1), v2 = clip8(a2), v3 = clip8(a3);
+                if (nv == 4 && (reinterpret_cast<uintptr_t>(d) & 3) == 0) {
+                    *reinterpret_cast<uint32_t*>(d) = (uint32_t)v0 | ((uint32_t)v1 << 8) | ((uint32_t)v2 << 16) | ((uint32_t)v3 << 24);
+                } else if (nv == 4 && (reinterpret_cast<uintptr_t>(d) & 1) == 0) {
+                    reinterpret_cast<uint16_t*>(d)[0] = (uint16_t)(v0 | (v1 << 8));
+                    reinterpret_cast<uint16_t*>(d)[1] = (uint16_t)(v2 | (v3 << 8));
+                } else {
+                    d[0] = v0;
+                    if (nv > 1) d[1] = v1;
+                    if (nv > 2) d[2] = v2;
+                    if (nv > 3) d[3] = v3;
+                }
+                g += blockDim.x;
+                while (g >= groups) g -= groups, ++yy;
+            }
         }
         ya = yb;
     }
@@ -1011,9 +1054,9 @@ static int crop_resize_core(const uint8_t* images, int H0, int W0, long long img
         resample_coeffs_kernel<<<g, 128, 0, stream>>>(sizes, sizes + njobs * 2, njobs, cap, kmax, 0, bounds, coef,
                                                       err_flag, njobs_dev);
     }
-    if (kmax <= CR_ROWS && (size_t)CR_ROWS * out_w <= 200 * 1024) {
+    if (kmax <= CR_ROWS && (size_t)CR_ROWS * (out_w + 3) <= 200 * 1024) {
         // fused path: no intermediate image in HBM
-        const size_t smem = (size_t)CR_ROWS * out_w;
+        const size_t smem = (size_t)CR_ROWS * ((out_w + 3) & ~3);
         static size_t configured = 0;
         if (smem > configured && smem > 48 * 1024) {
             UCOD_CHECK_CUDA(cudaFuncSetAttribute(crop_resize_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
