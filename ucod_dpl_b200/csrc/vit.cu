@@ -64,9 +64,10 @@ __global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloa
     if (batch_dev != nullptr && b >= __ldg(batch_dev)) return;
     const int kvalid = 3 * p * p;
     const int wused = gw * p;
+    const int pitch = Kpad + 8;  // shared-memory row pitch: the patches' rows start 4 banks apart instead of on one bank
     for (int idx = threadIdx.x; idx < gw * (Kpad - kvalid); idx += blockDim.x) {
         const int px = idx / (Kpad - kvalid), k = kvalid + idx % (Kpad - kvalid);
-        tile[px * Kpad + k] = __float2bfloat16_rn(0.f);
+        tile[px * pitch + k] = __float2bfloat16_rn(0.f);
     }
     if constexpr (sizeof(TIn) == 1) {
         // ToTensor + Normalize of a byte has 256 possible results per channel: a 3 x 256 bf16 table built once per CTA
@@ -80,35 +81,26 @@ __global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloa
             lut[c][t & 255] = __float2bfloat16_rn(((float)(t & 255) / 255.0f - m) * sd);
         }
         __syncthreads();
-        // uint8 input: the p image rows of one channel are one contiguous span of p * Ww bytes; read it with 16-byte
-        // loads from the aligned-down address (byte loads keep only 32 B per warp request in flight) and walk the
-        // (row, x, patch, column) indices incrementally
-        for (int c = 0; c < 3; ++c) {
-            const uint8_t* span = reinterpret_cast<const uint8_t*>(img) + (((size_t)b * 3 + c) * Hh + (size_t)py * p) * Ww;
-            const int nbytes = p * Ww;
-            const int head = (int)(reinterpret_cast<uintptr_t>(span) & 15);
-            const uint4* base = reinterpret_cast<const uint4*>(span - head);
-            const int nvec = (head + nbytes + 15) >> 4;
+        // one work item = the p bytes of one patch row (channel c, row i, patch px): p table look-ups, written as
+        // 32-bit pairs (the destination offset (c*p*p + i*p) is even when p is).  The former 16-byte vector walk with
+        // per-byte (row, patch, column) bookkeeping cost ~38 instructions per byte and was issue-bound.
+        const int items = 3 * p * gw;
+        for (int it = threadIdx.x; it < items; it += blockDim.x) {
+            const int px = it % gw;
+            const int ci = it / gw;  // c * p + i
+            const int c = ci / p, i = ci - c * p;
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(img) + (((size_t)b * 3 + c) * Hh + (size_t)py * p + i) * Ww + px * p;
             const __nv_bfloat16* lc = lut[c];
-            __nv_bfloat16* tc = tile + c * p * p;
-            for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
-                const uint4 w = __ldg(base + v);
-                const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
-                const int o = v * 16 - head;  // span offset of byte 0 of this vector
-                const int first = o < 0 ? -o : 0;
-                int i = (o + first) / Ww;
-                int x = (o + first) - i * Ww;
-                int px = x / p;
-                int j = x - px * p;
-#pragma unroll
-                for (int k = 0; k < 16; ++k) {
-                    if (k >= first && o + k < nbytes) {
-                        if (x < wused) tc[px * Kpad + i * p + j] = lc[(ww[k >> 2] >> (8 * (k & 3))) & 0xffu];
-                        ++x;
-                        if (++j == p) j = 0, ++px;
-                        if (x == Ww) x = 0, px = 0, j = 0, ++i;
-                    }
+            __nv_bfloat16* dstp = tile + px * pitch + c * p * p + i * p;
+            if ((p & 1) == 0) {
+                uint32_t* d32 = reinterpret_cast<uint32_t*>(dstp);
+                for (int j = 0; j < p; j += 2) {
+                    const uint32_t lo = *reinterpret_cast<const uint16_t*>(lc + src[j]);
+                    const uint32_t hi = *reinterpret_cast<const uint16_t*>(lc + src[j + 1]);
+                    d32[j >> 1] = lo | (hi << 16);
                 }
+            } else {
+                for (int j = 0; j < p; ++j) dstp[j] = lc[src[j]];
             }
         }
     } else {
@@ -118,13 +110,16 @@ __global__ void im2col_patch_smem_kernel(const TIn* __restrict__ img, __nv_bfloa
             const int c = ci / p, i = ci - c * p;
             const float v = static_cast<float>(img[(((size_t)b * 3 + c) * Hh + (size_t)py * p + i) * Ww + x]);
             const int px = x / p, j = x - px * p;
-            tile[px * Kpad + c * p * p + i * p + j] = __float2bfloat16_rn(v);
+            tile[px * pitch + c * p * p + i * p + j] = __float2bfloat16_rn(v);
         }
     }
     __syncthreads();
     uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)b * gh * gw + (size_t)py * gw) * Kpad);
-    const uint4* src = reinterpret_cast<const uint4*>(tile);
-    for (int idx = threadIdx.x; idx < gw * Kpad / 8; idx += blockDim.x) dst[idx] = src[idx];
+    const int vec_per_row = Kpad / 8;
+    for (int idx = threadIdx.x; idx < gw * vec_per_row; idx += blockDim.x) {
+        const int px = idx / vec_per_row, v = idx - px * vec_per_row;
+        dst[idx] = *reinterpret_cast<const uint4*>(tile + px * pitch + v * 8);
+    }
 }
 
 // x[b*T + 0, :] = cls + pos[0, :]
@@ -346,7 +341,7 @@ int vit_keys(void* handle, const void* images, int image_dtype, int B, int img_h
     const float3 istd = make_float3(1.0f / 0.229f, 1.0f / 0.224f, 1.0f / 0.225f);
     dim3 g_im(gh, B);
     prof_pre(KC_EMBED, stream, batch_dev ? 0.0 : (double)B * 3 * img_h * img_w * (image_dtype ? 1 : 4) + (double)B * P * c.patch_kpad * 2);
-    const size_t im_smem = (size_t)gw * c.patch_kpad * sizeof(__nv_bfloat16);
+    const size_t im_smem = (size_t)gw * (c.patch_kpad + 8) * sizeof(__nv_bfloat16);
     if (im_smem <= 200 * 1024 && c.patch_kpad % 8 == 0) {
         static bool im_configured = false;
         if (!im_configured) {
